@@ -1,0 +1,164 @@
+/* oshb.h -- C ABI of the B200-native omega_h refine path (liboshb.so).
+ *
+ * The reference has no FFI registry: its seam is the public C++ API of libomega_h
+ * (SURVEY.md section 8b). This header is the flat boundary a maintainer binds instead:
+ * the host C++ bodies of Omega_h::Mesh::derive_adj / ask_lengths, refine_by_size,
+ * modify_ents, transfer_refine, ... call these entry points (INTEGRATION.md shows the
+ * shim). Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *  - every function returns 0 on success, nonzero on failure; oshb_last_error() gives the
+ *    message (the reference aborts through Omega_h_fail, src/Omega_h_fail.cpp:25-71 -- the
+ *    C++ shim maps nonzero to Omega_h_fail).
+ *  - "d_" parameters are DEVICE pointers (HBM of the GPU selected by oshb_init); "h_"
+ *    parameters are HOST pointers. Nothing is allocated behind the caller's back by the
+ *    d_-primitives except stream-ordered temporaries that are released before return.
+ *  - index types follow the reference: LO=int32_t, GO=int64_t, I8=int8_t, Real=double
+ *    (src/Omega_h_defines.hpp:73-82).
+ *  - all work is enqueued on the library's stream; functions that return host-visible
+ *    results synchronise that stream, the others may return before the GPU finishes
+ *    (call oshb_sync()).
+ *  - there is NO CPU path: without a usable sm_100 device every call fails.
+ */
+#ifndef OSHB_H
+#define OSHB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ------------------------------------------------------------------------ */
+/* Library(argc, argv) device selection, src/Omega_h_library.cpp:152-167 */
+int oshb_init(int device);
+int oshb_sync(void);
+const char* oshb_last_error(void);
+/* 1 when built as the test-only host emulation (tests/emu); the product library returns 0 */
+int oshb_is_emulation(void);
+/* counters: kernels launched / blocking read-backs / peak device bytes since oshb_init */
+uint64_t oshb_launch_count(void);
+uint64_t oshb_sync_count(void);
+uint64_t oshb_peak_bytes(void);
+/* raw device memory for callers without their own allocator (Write<T>, src/Omega_h_array.hpp:23) */
+int oshb_dev_alloc(uint64_t bytes, void** d_out);
+int oshb_dev_free(void* d_ptr, uint64_t bytes);
+int oshb_h2d(void* d_dst, const void* h_src, uint64_t bytes);
+int oshb_d2h(void* h_dst, const void* d_src, uint64_t bytes);
+
+/* ---- array primitives on device pointers ------------------------------------------------ */
+/* offset_scan: out[0]=0, out[i+1]=sum(in[0..i]); out has n+1 entries.
+ * src/Omega_h_int_scan.cpp:10-33 */
+int oshb_offset_scan_i8(const int8_t* d_in, int64_t n, int32_t* d_out);
+int oshb_offset_scan_i32(const int32_t* d_in, int64_t n, int32_t* d_out);
+int oshb_offset_scan_i32_i64(const int32_t* d_in, int64_t n, int64_t* d_out);
+/* collect_marked: indices of nonzero marks in increasing order; returns the count.
+ * d_out must hold n entries. src/Omega_h_map.cpp:174-185 */
+int oshb_collect_marked(const int8_t* d_marks, int64_t n, int32_t* d_out, int32_t* h_count);
+/* get_max over I8 marks, src/Omega_h_array_ops.cpp:47-68 */
+int oshb_max_i8(const int8_t* d_in, int64_t n, int32_t* h_max);
+int oshb_minmax_f64(const double* d_in, int64_t n, double* h_min, double* h_max);
+/* sort_by_keys: stable lexicographic sort of n keys of `width` words; d_perm[sorted]=original.
+ * src/Omega_h_sort.cpp:57-92 */
+int oshb_sort_by_keys_i32(const int32_t* d_keys, int64_t n, int width, int32_t* d_perm);
+int oshb_sort_by_keys_i64(const int64_t* d_keys, int64_t n, int width, int32_t* d_perm);
+
+/* ---- adjacency derivation on device pointers --------------------------------------------- */
+/* invert_adj: upward adjacency (offsets nlow+1, entries nhigh*deg, codes nhigh*deg) from a
+ * downward one; rows sorted by high index. d_down_codes may be NULL (target = vertices).
+ * src/Omega_h_adj.cpp:231-263 */
+int oshb_invert_adj(const int32_t* d_hl2l, const int8_t* d_down_codes, int64_t nhigh, int deg, int32_t nlow,
+    int32_t* d_l2lh, int32_t* d_lh2h, int8_t* d_codes);
+/* transit: high->low through mid (R->E from R->F,F->E; F->V; R->V). d_codes_out only for
+ * low_dim==1. src/Omega_h_adj.cpp:443-510 */
+int oshb_transit(const int32_t* d_hm2m, const int8_t* d_hm_codes, const int32_t* d_ml2l, const int8_t* d_ml_codes,
+    int64_t nhigh, int high_dim, int low_dim, int32_t* d_hl2l, int8_t* d_codes_out);
+/* reflect_down: for each high entity (vertex tuples hv2v) the low entities (vertex tuples
+ * lv2v) on its boundary + alignment codes. src/Omega_h_adj.cpp:424-441 */
+int oshb_reflect_down(const int32_t* d_hv2v, int64_t nhigh, int high_dim, const int32_t* d_lv2v, int64_t nlow,
+    int low_dim, int32_t nverts, int32_t* d_hl2l, int8_t* d_codes);
+/* find_unique: unique low entities (vertex tuples, sorted by canonical tuple) of the highs.
+ * d_lv2v_out must hold nhigh*nlows_per_high*(low_dim+1) entries; returns the count.
+ * src/Omega_h_adj.cpp:133-153 */
+int oshb_find_unique(const int32_t* d_hv2v, int64_t nhigh, int high_dim, int low_dim, int32_t* d_lv2v_out,
+    int64_t* h_nlow);
+
+/* ---- geometry kernels on device pointers -------------------------------------------------- */
+/* measure_edges_metric: metric length of edges a2e[0..n) (NULL = edges 0..n).
+ * metric_ncomps 1 (isotropic) or dim*(dim+1)/2. src/Omega_h_shape.cpp:7-37 */
+int oshb_measure_edges_metric(int dim, int metric_ncomps, const int32_t* d_ev2v, const double* d_coords,
+    const double* d_metrics, const int32_t* d_a2e, int32_t n, double* d_out);
+/* measure_qualities: mean-ratio quality in the max-determinant vertex metric.
+ * src/Omega_h_quality.cpp:7-52 */
+int oshb_measure_qualities(int dim, int metric_ncomps, const int32_t* d_cv2v, const double* d_coords,
+    const double* d_metrics, const int32_t* d_a2e, int32_t n, double* d_out);
+
+/* ---- mesh handle: the Omega_h::Mesh contract (src/Omega_h_mesh.hpp:36-177) ------------------ */
+typedef struct oshb_mesh oshb_mesh;
+enum { OSHB_I8 = 0, OSHB_I32 = 1, OSHB_I64 = 2, OSHB_F64 = 3 };
+
+int oshb_mesh_create(int dim, oshb_mesh** out);
+int oshb_mesh_destroy(oshb_mesh* m);
+int oshb_mesh_clone(const oshb_mesh* m, oshb_mesh** out); /* shallow, shares arrays (Mesh copy) */
+int oshb_mesh_dim(const oshb_mesh* m, int* dim);
+int oshb_mesh_nents(const oshb_mesh* m, int ent_dim, int32_t* n);
+/* Mesh::set_verts / Mesh::set_ents, src/Omega_h_mesh.cpp:76-95. Pointers are HOST when
+ * host!=0 (copied to the device inside the call), DEVICE otherwise (copied device->device). */
+int oshb_mesh_set_verts(oshb_mesh* m, int32_t nverts);
+int oshb_mesh_set_ents(oshb_mesh* m, int ent_dim, int32_t nents, const int32_t* down, const int8_t* codes, int host);
+/* Mesh::add_tag / set_tag, src/Omega_h_mesh.cpp:132-165 (internal!=0 skips cache invalidation) */
+int oshb_mesh_add_tag(oshb_mesh* m, int ent_dim, const char* name, int type, int ncomps, const void* data, int host,
+    int internal);
+int oshb_mesh_remove_tag(oshb_mesh* m, int ent_dim, const char* name);
+int oshb_mesh_ntags(const oshb_mesh* m, int ent_dim, int* ntags);
+int oshb_mesh_tag_info(const oshb_mesh* m, int ent_dim, int i, char* name_out, int name_cap, int* type, int* ncomps);
+/* Mesh::get_array: copies the tag to h_out/d_out (nents*ncomps values) */
+int oshb_mesh_get_tag(const oshb_mesh* m, int ent_dim, const char* name, void* out, int host);
+/* Mesh::ask_down / ask_verts_of (derives + caches): entries nents(from)*degree; codes may be
+ * NULL; codes are absent when to==0 */
+int oshb_mesh_ask_down(oshb_mesh* m, int from, int to, int32_t* ab2b_out, int8_t* codes_out, int host);
+/* Mesh::ask_up: first call with NULL outputs to learn the entry count */
+int oshb_mesh_ask_up(oshb_mesh* m, int from, int to, int64_t* nentries, int32_t* a2ab_out, int32_t* ab2b_out,
+    int8_t* codes_out, int host);
+/* Mesh::ask_star(EDGE), src/Omega_h_mesh.cpp:331-338 */
+int oshb_mesh_ask_star(oshb_mesh* m, int ent_dim, int64_t* nentries, int32_t* a2ab_out, int32_t* ab2b_out, int host);
+/* Mesh::ask_lengths / ask_qualities, src/Omega_h_mesh.cpp:374-388 (result stays a tag) */
+int oshb_mesh_ask_lengths(oshb_mesh* m);
+int oshb_mesh_ask_qualities(oshb_mesh* m);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* AdaptOpts, src/Omega_h_adapt.hpp:50-82; defaults from oshb_adapt_opts_init(dim),
+ * src/Omega_h_adapt.cpp:52-85 */
+typedef struct oshb_adapt_opts {
+  double min_length_desired;
+  double max_length_desired;
+  double max_length_allowed;
+  double min_quality_allowed;
+  double min_quality_desired;
+  int32_t verbosity;
+} oshb_adapt_opts;
+int oshb_adapt_opts_init(int dim, oshb_adapt_opts* opts);
+
+/* per-stage intermediates of one pass (used by parity tests; mirrors the locals of
+ * refine_ghosted, src/Omega_h_refine.cpp:17-41) */
+int oshb_refine_qualities(oshb_mesh* m, const int32_t* cands2edges, int32_t ncands, double* quals_out, int host);
+int oshb_mident_metrics(oshb_mesh* m, const int32_t* a2e, int32_t n, double* out, int host);
+int oshb_find_indset(oshb_mesh* m, const double* edge_quals, const int8_t* initial, int8_t* keys_out, int host,
+    int32_t* nrounds);
+int oshb_rep_vertex2md_order(oshb_mesh* m, const int8_t* keys, int32_t* order_out, int host);
+
+/* refine_by_size(Mesh*, AdaptOpts const&) -> bool, src/Omega_h_refine.cpp:92-100.
+ * *did = 0 when no edge is longer than max_length_desired or no candidate is good enough;
+ * otherwise the mesh behind the handle is replaced by the refined mesh. */
+int oshb_refine_by_size(oshb_mesh* m, const oshb_adapt_opts* opts, int* did);
+typedef struct oshb_pass_stats {
+  int32_t ncands, nkeys, indset_rounds;
+  int32_t nents_before[4];
+  int32_t nents_after[4];
+} oshb_pass_stats;
+int oshb_last_pass_stats(oshb_pass_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSHB_H */

@@ -1,0 +1,430 @@
+// Adjacency derivation kernels: invert_adj, transit, reflect_down, edge star,
+// form_uses / find_unique, plus the scan/compaction maps they need.
+// Outputs are bit-identical to the reference's (src/Omega_h_adj.cpp, src/Omega_h_map.cpp)
+// but the algorithms are re-designed for HBM: no materialised use lists, no per-use
+// linear search through vertex stars.
+#include "mesh.hpp"
+
+namespace oshb {
+
+// ---------------------------------------------------------------------------------------
+// device error cell
+// ---------------------------------------------------------------------------------------
+int* device_error_cell() { return reinterpret_cast<int*>(static_cast<char*>(ctx().dscratch) + 1024); }
+
+void device_error_reset() {
+  int z = 0;
+  h2d(device_error_cell(), &z, sizeof(int));
+}
+
+void device_error_check(char const* where) {
+  int v = read_scalar(device_error_cell());
+  if (v != 0) {
+    device_error_reset();
+    fail(__FILE__, __LINE__, std::string("device-side check failed (bits ") + std::to_string(v) + ") at " + where);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// maps
+// ---------------------------------------------------------------------------------------
+LOs offset_scan(Bytes a) {
+  LOs out(a.size() + 1);
+  scan_offsets(a.data(), a.size(), out.data());
+  return out;
+}
+LOs offset_scan(LOs a) {
+  LOs out(a.size() + 1);
+  scan_offsets(a.data(), a.size(), out.data());
+  return out;
+}
+LO last_of(LOs a) {
+  OSHB_CHECK(a.size() > 0);
+  return read_scalar(a.data() + (a.size() - 1));
+}
+
+// order-preserving stream compaction: scan of the marks + guarded scatter
+LOs collect_marked(Bytes marks, LO* count_out) {
+  auto n = marks.size();
+  auto offsets = offset_scan(marks);
+  LO nmarked = last_of(offsets);
+  LOs out(nmarked);
+  I8 const* m = marks.data();
+  LO const* off = offsets.data();
+  LO* o = out.data();
+  parallel_for(n, OSHB_LAMBDA(LO i) {
+    if (m[i]) o[off[i]] = i;
+  }, "collect_marked");
+  if (count_out) *count_out = nmarked;
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------
+// invert_adj: upward adjacency from downward.
+//   1. degree histogram of the lows (integer atomics)
+//   2. offset scan
+//   3. slot claim (atomics; arrival order is arbitrary)
+//   4. one thread per low sorts its short row by high-low use index (== by high index,
+//      src/Omega_h_adj.cpp:178-200) and emits high index + upward code in the same pass
+// Algorithmic bytes: in 4*N*d (+N*d codes); out 4*(L+1) + 4*N*d + N*d.
+// ---------------------------------------------------------------------------------------
+Adj invert_adj(Adj const& down, int nlows_per_high, LO nlows) {
+  int64_t const nhl = down.ab2b.size();
+  LOs degrees = filled<LO>(nlows, 0);
+  LO const* hl2l = down.ab2b.data();
+  LO* deg = degrees.data();
+  parallel_for(nhl, OSHB_LAMBDA(LO hl) { atomic_add(&deg[hl2l[hl]], 1); }, "invert_adj(count)");
+  LOs l2lh = offset_scan(degrees);
+  LOs lh2hl(nhl);
+  LO const* off = l2lh.data();
+  LO* slots = lh2hl.data();
+  parallel_for(nhl, OSHB_LAMBDA(LO hl) {
+    LO l = hl2l[hl];
+    LO j = atomic_add(&deg[l], -1);  // counts back down to zero: no second cursor array
+    slots[off[l] + j - 1] = hl;
+  }, "invert_adj(fill)");
+  degrees.reset();
+  LOs lh2h(nhl);
+  Bytes codes(nhl);
+  LO* h_out = lh2h.data();
+  I8* c_out = codes.data();
+  I8 const* dcodes = down.codes.exists() ? down.codes.data() : nullptr;
+  int const deg_h = nlows_per_high;
+  parallel_for(nlows, OSHB_LAMBDA(LO l) {
+    LO const b = off[l];
+    LO const e = off[l + 1];
+    // insertion sort of the row (rows are short: ~5 for E->F/E->R, ~14 for V->E, ~35 for V->F)
+    for (LO i = b + 1; i < e; ++i) {
+      LO x = slots[i];
+      LO j = i - 1;
+      while (j >= b && slots[j] > x) {
+        slots[j + 1] = slots[j];
+        --j;
+      }
+      slots[j + 1] = x;
+    }
+    for (LO i = b; i < e; ++i) {
+      LO hl = slots[i];
+      LO h = hl / deg_h;
+      int which_down = hl - h * deg_h;
+      h_out[i] = h;
+      if (dcodes) {
+        I8 dc = dcodes[hl];
+        c_out[i] = make_code(code_is_flipped(dc), code_rotation(dc), which_down);
+      } else {
+        c_out[i] = make_code(false, 0, which_down);
+      }
+    }
+  }, "invert_adj(sort+separate)");
+  Adj up;
+  up.a2ab = l2lh;
+  up.ab2b = lh2h;
+  up.codes = codes;
+  return up;
+}
+
+// ---------------------------------------------------------------------------------------
+// transit: two-level downward adjacency through the upward template and the alignment
+// algebra (src/Omega_h_adj.cpp:443-510). One thread per high entity.
+// ---------------------------------------------------------------------------------------
+Adj transit(Adj const& h2m, Adj const& m2l, int high_dim, int low_dim) {
+  OSHB_CHECK(low_dim == 0 || low_dim == 1);
+  int const mid_dim = low_dim + 1;
+  OSHB_CHECK(high_dim > mid_dim);
+  int const nmids_per_high = simplex_degree(high_dim, mid_dim);
+  int const nlows_per_mid = simplex_degree(mid_dim, low_dim);
+  int const nlows_per_high = simplex_degree(high_dim, low_dim);
+  int64_t const nhighs = h2m.ab2b.size() / nmids_per_high;
+  LOs hl2l(nhighs * nlows_per_high);
+  Bytes codes;
+  if (low_dim == 1) codes = Bytes(nhighs * nlows_per_high);
+  LO const* hm2m = h2m.ab2b.data();
+  I8 const* m2hm_codes = h2m.codes.data();
+  LO const* ml2l = m2l.ab2b.data();
+  I8 const* ml_codes = m2l.codes.exists() ? m2l.codes.data() : nullptr;
+  LO* out = hl2l.data();
+  I8* cout = codes.exists() ? codes.data() : nullptr;
+  OSHB_CHECK(m2hm_codes != nullptr);
+  parallel_for(nhighs, OSHB_LAMBDA(LO h) {
+    int64_t const hl_begin = int64_t(h) * nlows_per_high;
+    int64_t const hm_begin = int64_t(h) * nmids_per_high;
+    for (int hl = 0; hl < nlows_per_high; ++hl) {
+      TemplateUp ut = simplex_up_template0(high_dim, low_dim, hl);
+      LO m = hm2m[hm_begin + ut.up];
+      I8 m2hm_code = m2hm_codes[hm_begin + ut.up];
+      I8 hm2m_code = invert_alignment(nlows_per_mid, m2hm_code);
+      int ml = align_index(nlows_per_mid, low_dim, ut.which_down, hm2m_code);
+      int64_t ml_begin = int64_t(m) * nlows_per_mid;
+      out[hl_begin + hl] = ml2l[ml_begin + ml];
+      if (low_dim == 1) {
+        bool region_face_flipped = code_is_flipped(hm2m_code);
+        bool face_edge_flipped = (code_rotation(ml_codes[ml_begin + ml]) == 1);
+        bool flipped = region_face_flipped ^ face_edge_flipped ^ ut.is_flipped;
+        cout[hl_begin + hl] = make_code(false, int(flipped), 0);
+      }
+    }
+  }, "transit");
+  Adj a;
+  a.ab2b = hl2l;
+  a.codes = codes;
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------
+// form_uses (src/Omega_h_adj.cpp:155-176) -- only used by find_unique / tests;
+// reflect_down below never materialises the use list.
+// ---------------------------------------------------------------------------------------
+LOs form_uses(LOs hv2v, int high_dim, int low_dim) {
+  int const nvh = high_dim + 1;
+  int const nvl = low_dim + 1;
+  int const nlh = simplex_degree(high_dim, low_dim);
+  int64_t const nhigh = hv2v.size() / nvh;
+  LOs uv2v(nhigh * nlh * nvl);
+  LO const* in = hv2v.data();
+  LO* out = uv2v.data();
+  parallel_for(nhigh * nlh, OSHB_LAMBDA(LO u) {
+    LO h = u / nlh;
+    int w = u - h * nlh;
+    for (int uv = 0; uv < nvl; ++uv) {
+      out[int64_t(u) * nvl + uv] = in[int64_t(h) * nvh + simplex_down_template(high_dim, low_dim, w, uv)];
+    }
+  }, "form_uses");
+  return uv2v;
+}
+
+// ---------------------------------------------------------------------------------------
+// reflect_down: downward adjacency (+codes) of highs given only vertex tuples.
+//
+// The reference materialises every use and linearly searches all lows around the use's
+// first vertex (find_matches_deg, src/Omega_h_adj.cpp:357-396; 52 % of its CPU time).
+// The result (the unique low with the same vertex set + the alignment code,
+// IsMatch<2>/<3> src/Omega_h_adj.cpp:297-330) does not depend on how it is found, so
+// here it is a bucket join:
+//   build : every low is filed under its SMALLEST vertex, stored with its other
+//           vertices in cyclic order -> rows of ~7 (edges) / ~11 (tris) packed entries
+//           (8 B / 16 B each), contiguous per vertex
+//   probe : one thread per use rotates the use to its smallest vertex, streams that one
+//           row and compares; the code follows from the two rotations and the flip.
+// Algorithmic bytes: 4*N*(hd+1) + 4*L*(ld+1) in, 5*N*n_l out; the bucket
+// table adds one write + ~one read of (8|16)*L.
+// ---------------------------------------------------------------------------------------
+Adj reflect_down(LOs hv2v, LOs lv2v, LO nverts, int high_dim, int low_dim) {
+  OSHB_CHECK(low_dim == 1 || low_dim == 2);
+  int const nvh = high_dim + 1;
+  int const nvl = low_dim + 1;
+  int const nlh = simplex_degree(high_dim, low_dim);
+  int64_t const nhigh = hv2v.size() / nvh;
+  int64_t const nlow = lv2v.size() / nvl;
+  OSHB_CHECK(nlow < (int64_t(1) << 30));
+  LO const* lv = lv2v.data();
+  // --- build buckets
+  LOs degrees = filled<LO>(nverts, 0);
+  LO* deg = degrees.data();
+  parallel_for(nlow, OSHB_LAMBDA(LO l) {
+    LO m = lv[int64_t(l) * nvl];
+    for (int j = 1; j < nvl; ++j) {
+      LO v = lv[int64_t(l) * nvl + j];
+      if (v < m) m = v;
+    }
+    atomic_add(&deg[m], 1);
+  }, "reflect_down(count)");
+  LOs offsets = offset_scan(degrees);
+  LO const* off = offsets.data();
+  // entry layout: edges {other, (l<<1)|jm}; tris {va, vb, l, jm}
+  int const ewords = (low_dim == 1) ? 2 : 4;
+  LOs table(nlow * ewords);
+  LO* tab = table.data();
+  parallel_for(nlow, OSHB_LAMBDA(LO l) {
+    int jm = 0;
+    LO m = lv[int64_t(l) * nvl];
+    for (int j = 1; j < nvl; ++j) {
+      LO v = lv[int64_t(l) * nvl + j];
+      if (v < m) {
+        m = v;
+        jm = j;
+      }
+    }
+    LO slot = off[m] + atomic_add(&deg[m], -1) - 1;
+    if (nvl == 2) {
+      tab[int64_t(slot) * 2 + 0] = lv[int64_t(l) * 2 + (1 - jm)];
+      tab[int64_t(slot) * 2 + 1] = (l << 1) | jm;
+    } else {
+      tab[int64_t(slot) * 4 + 0] = lv[int64_t(l) * 3 + (jm + 1) % 3];
+      tab[int64_t(slot) * 4 + 1] = lv[int64_t(l) * 3 + (jm + 2) % 3];
+      tab[int64_t(slot) * 4 + 2] = l;
+      tab[int64_t(slot) * 4 + 3] = jm;
+    }
+  }, "reflect_down(build)");
+  degrees.reset();
+  // --- probe
+  LOs hl2l(nhigh * nlh);
+  Bytes codes(nhigh * nlh);
+  LO* out = hl2l.data();
+  I8* cout = codes.data();
+  LO const* hv = hv2v.data();
+  int* err = device_error_cell();
+  parallel_for(nhigh * nlh, OSHB_LAMBDA(LO u) {
+    LO h = u / nlh;
+    int w = u - h * nlh;
+    LO uv[3];
+    for (int k = 0; k < nvl; ++k) uv[k] = hv[int64_t(h) * nvh + simplex_down_template(high_dim, low_dim, w, k)];
+    // position of the smallest vertex of the use
+    int um = 0;
+    for (int k = 1; k < nvl; ++k)
+      if (uv[k] < uv[um]) um = k;
+    LO const m = uv[um];
+    LO const rb = off[m];
+    LO const re = off[m + 1];
+    LO found = -1;
+    I8 code = 0;
+    if (nvl == 2) {
+      LO other = uv[1 - um];
+      for (LO s = rb; s < re; ++s) {
+        if (tab[int64_t(s) * 2] == other) {
+          LO packed = tab[int64_t(s) * 2 + 1];
+          found = packed >> 1;
+          int jm = packed & 1;
+          // which_down = position in the low of the use's first vertex
+          int which_down = (um == 0) ? jm : (1 - jm);
+          code = make_code(false, which_down, 0);
+          break;
+        }
+      }
+    } else {
+      LO ua = uv[(um + 1) % 3];
+      LO ub = uv[(um + 2) % 3];
+      for (LO s = rb; s < re; ++s) {
+        LO va = tab[int64_t(s) * 4 + 0];
+        LO vb = tab[int64_t(s) * 4 + 1];
+        bool same = (va == ua && vb == ub);
+        bool flip = (va == ub && vb == ua);
+        if (same || flip) {
+          found = tab[int64_t(s) * 4 + 2];
+          int jm = tab[int64_t(s) * 4 + 3];
+          // low's vertex list b: b[jm]=m, b[jm+1]=va, b[jm+2]=vb.
+          // position j in b of the use's first vertex uv[0]:
+          //   same orientation: uv[0] = uv[um - um] sits um steps before m  -> j = jm - um
+          //   flipped         : walking the use forward walks the low backward -> j = jm + um
+          int j = same ? ((jm - um + 3) % 3) : ((jm + um) % 3);
+          code = make_code(flip, rotation_to_first(3, j), 0);
+          break;
+        }
+      }
+    }
+    if (found < 0) atomic_or_i32(err, 1);
+    out[u] = found;
+    cout[u] = code;
+  }, "reflect_down(probe)");
+  Adj a;
+  a.ab2b = hl2l;
+  a.codes = codes;
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------
+// edge star = edges_across_tris (+) edges_across_tets (src/Omega_h_adj.cpp:532-589,
+// add_edges src/Omega_h_graph.cpp:14-40), built in one pass instead of two graphs + merge.
+// ---------------------------------------------------------------------------------------
+Adj edges_star(int dim, Adj const& f2e, Adj const& e2f, Adj const& r2e, Adj const& e2r) {
+  int64_t const ne = e2f.a2ab.size() - 1;
+  LOs degrees(ne);
+  LO* dg = degrees.data();
+  LO const* e2ef = e2f.a2ab.data();
+  LO const* e2er = (dim == 3) ? e2r.a2ab.data() : nullptr;
+  parallel_for(ne, OSHB_LAMBDA(LO e) {
+    LO d = 2 * (e2ef[e + 1] - e2ef[e]);
+    if (e2er) d += e2er[e + 1] - e2er[e];
+    dg[e] = d;
+  }, "edges_star(count)");
+  LOs e2ee = offset_scan(degrees);
+  degrees.reset();
+  LO nee = last_of(e2ee);
+  LOs ee2e(nee);
+  LO* out = ee2e.data();
+  LO const* off = e2ee.data();
+  LO const* ef2f = e2f.ab2b.data();
+  I8 const* ef_codes = e2f.codes.data();
+  LO const* fe2e = f2e.ab2b.data();
+  LO const* er2r = (dim == 3) ? e2r.ab2b.data() : nullptr;
+  I8 const* er_codes = (dim == 3) ? e2r.codes.data() : nullptr;
+  LO const* re2e = (dim == 3) ? r2e.ab2b.data() : nullptr;
+  parallel_for(ne, OSHB_LAMBDA(LO e) {
+    LO k = off[e];
+    for (LO ef = e2ef[e]; ef < e2ef[e + 1]; ++ef) {
+      LO f = ef2f[ef];
+      int ffe = code_which_down(ef_codes[ef]);
+      out[k++] = fe2e[int64_t(f) * 3 + (ffe + 1) % 3];
+      out[k++] = fe2e[int64_t(f) * 3 + (ffe + 2) % 3];
+    }
+    if (e2er) {
+      for (LO er = e2er[e]; er < e2er[e + 1]; ++er) {
+        LO r = er2r[er];
+        int rre = code_which_down(er_codes[er]);
+        out[k++] = re2e[int64_t(r) * 6 + simplex_opposite_template(REGION, EDGE, rre)];
+      }
+    }
+  }, "edges_star(fill)");
+  Adj g;
+  g.a2ab = e2ee;
+  g.ab2b = ee2e;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------
+// find_unique (src/Omega_h_adj.cpp:133-153): uses -> canonical orientation -> stable
+// sort_by_keys -> jumps -> compaction -> first use of every run, in sorted order.
+// ---------------------------------------------------------------------------------------
+LOs find_unique(LOs hv2v, int high_dim, int low_dim) {
+  OSHB_CHECK(low_dim == 1 || low_dim == 2);
+  int const deg = low_dim + 1;
+  LOs uv2v = form_uses(hv2v, high_dim, low_dim);
+  int64_t const nu = uv2v.size() / deg;
+  LOs canon(nu * deg);
+  LO const* in = uv2v.data();
+  LO* cn = canon.data();
+  // get_codes_to_canonical + align_ev2v (src/Omega_h_adj.cpp:71-109): smallest vertex
+  // first, then flip so that the vertex after it is the smaller of the remaining two
+  parallel_for(nu, OSHB_LAMBDA(LO u) {
+    LO v[3];
+    for (int k = 0; k < deg; ++k) v[k] = in[int64_t(u) * deg + k];
+    int mj = 0;
+    for (int k = 1; k < deg; ++k)
+      if (v[k] < v[mj]) mj = k;
+    LO t[3];
+    for (int k = 0; k < deg; ++k) t[k] = v[(mj + k) % deg];
+    if (deg == 3 && t[2] < t[1]) {
+      LO s = t[1];
+      t[1] = t[2];
+      t[2] = s;
+    }
+    for (int k = 0; k < deg; ++k) cn[int64_t(u) * deg + k] = t[k];
+  }, "find_unique(canonicalize)");
+  LOs sorted2u(nu);
+  sort_by_keys(canon.data(), nu, deg, sorted2u.data());
+  Bytes jumps(nu);
+  I8* jp = jumps.data();
+  LO const* s2u = sorted2u.data();
+  parallel_for(nu, OSHB_LAMBDA(LO s) {
+    if (s == LO(nu) - 1) {
+      jp[s] = 1;
+      return;
+    }
+    LO a = s2u[s], b = s2u[s + 1];
+    bool eq = true;
+    for (int k = 0; k < deg; ++k)
+      if (cn[int64_t(a) * deg + k] != cn[int64_t(b) * deg + k]) eq = false;
+    jp[s] = eq ? 0 : 1;
+  }, "find_unique(jumps)");
+  LOs e2sorted = collect_marked(jumps);
+  int64_t const ne = e2sorted.size();
+  LOs ev2v(ne * deg);
+  LO const* e2s = e2sorted.data();
+  LO* out = ev2v.data();
+  parallel_for(ne, OSHB_LAMBDA(LO e) {
+    LO u = s2u[e2s[e]];
+    for (int k = 0; k < deg; ++k) out[int64_t(e) * deg + k] = in[int64_t(u) * deg + k];
+  }, "find_unique(unmap)");
+  return ev2v;
+}
+
+}  // namespace oshb

@@ -1,0 +1,476 @@
+// C ABI (include/oshb.h) over the C++ runtime. Every entry point catches oshb::Error and
+// returns nonzero; the message is kept for oshb_last_error().
+#include "../../include/oshb.h"
+
+#include "mesh.hpp"
+
+using namespace oshb;
+
+namespace oshb {
+std::string& last_error_string();
+}
+
+struct oshb_mesh {
+  Mesh m;
+};
+
+#define OSHB_TRY try {
+#define OSHB_CATCH                                  \
+  }                                                 \
+  catch (std::exception const& e) {                 \
+    if (oshb::last_error_string().empty()) oshb::last_error_string() = e.what(); \
+    return 1;                                       \
+  }                                                 \
+  return 0;
+
+// non-owning view of caller memory as a DArr is not possible (DArr owns); primitives
+// therefore copy in/out through owned arrays only where the C++ layer needs DArr. The
+// pointer-level primitives below work on raw pointers directly.
+template <class T>
+static DArr<T> import_array(T const* p, int64_t n, int host) {
+  DArr<T> a(n);
+  if (n == 0) return a;
+  if (host)
+    h2d(a.data(), p, size_t(n) * sizeof(T));
+  else
+    d2d(a.data(), p, size_t(n) * sizeof(T));
+  return a;
+}
+template <class T>
+static void export_array(DArr<T> const& a, T* out, int host) {
+  if (!out || a.size() == 0) return;
+  if (host)
+    d2h(out, a.data(), size_t(a.size()) * sizeof(T));
+  else
+    d2d(out, a.data(), size_t(a.size()) * sizeof(T));
+}
+
+extern "C" {
+
+int oshb_init(int device) {
+  OSHB_TRY
+  oshb::last_error_string().clear();
+  init_ctx(device);
+  OSHB_CATCH
+}
+int oshb_sync(void) {
+  OSHB_TRY
+  sync_stream();
+  OSHB_CATCH
+}
+const char* oshb_last_error(void) { return oshb::last_error_string().c_str(); }
+int oshb_is_emulation(void) {
+#ifdef OSHB_EMU
+  return 1;
+#else
+  return 0;
+#endif
+}
+uint64_t oshb_launch_count(void) { return ctx().launches; }
+uint64_t oshb_sync_count(void) { return ctx().syncs; }
+uint64_t oshb_peak_bytes(void) { return ctx().peak_bytes; }
+
+int oshb_dev_alloc(uint64_t bytes, void** d_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  *d_out = dev_alloc(size_t(bytes));
+  OSHB_CATCH
+}
+int oshb_dev_free(void* d_ptr, uint64_t bytes) {
+  OSHB_TRY
+  dev_free(d_ptr, size_t(bytes));
+  OSHB_CATCH
+}
+int oshb_h2d(void* d_dst, const void* h_src, uint64_t bytes) {
+  OSHB_TRY
+  h2d(d_dst, h_src, size_t(bytes));
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_d2h(void* h_dst, const void* d_src, uint64_t bytes) {
+  OSHB_TRY
+  d2h(h_dst, d_src, size_t(bytes));
+  OSHB_CATCH
+}
+
+// ---- array primitives ------------------------------------------------------------------
+int oshb_offset_scan_i8(const int8_t* d_in, int64_t n, int32_t* d_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  scan_offsets(d_in, n, d_out);
+  OSHB_CATCH
+}
+int oshb_offset_scan_i32(const int32_t* d_in, int64_t n, int32_t* d_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  scan_offsets(d_in, n, d_out);
+  OSHB_CATCH
+}
+int oshb_offset_scan_i32_i64(const int32_t* d_in, int64_t n, int64_t* d_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  scan_offsets(d_in, n, d_out);
+  OSHB_CATCH
+}
+int oshb_collect_marked(const int8_t* d_marks, int64_t n, int32_t* d_out, int32_t* h_count) {
+  OSHB_TRY
+  init_ctx(-1);
+  LOs offsets(n + 1);
+  scan_offsets(d_marks, n, offsets.data());
+  LO cnt = last_of(offsets);
+  LO const* off = offsets.data();
+  parallel_for(n, OSHB_LAMBDA(LO i) {
+    if (d_marks[i]) d_out[off[i]] = i;
+  }, "collect_marked");
+  *h_count = cnt;
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_max_i8(const int8_t* d_in, int64_t n, int32_t* h_max) {
+  OSHB_TRY
+  init_ctx(-1);
+  *h_max = max_i8(d_in, n);
+  OSHB_CATCH
+}
+int oshb_minmax_f64(const double* d_in, int64_t n, double* h_min, double* h_max) {
+  OSHB_TRY
+  init_ctx(-1);
+  minmax_f64(d_in, n, h_min, h_max);
+  OSHB_CATCH
+}
+int oshb_sort_by_keys_i32(const int32_t* d_keys, int64_t n, int width, int32_t* d_perm) {
+  OSHB_TRY
+  init_ctx(-1);
+  sort_by_keys(d_keys, n, width, d_perm);
+  OSHB_CATCH
+}
+int oshb_sort_by_keys_i64(const int64_t* d_keys, int64_t n, int width, int32_t* d_perm) {
+  OSHB_TRY
+  init_ctx(-1);
+  sort_by_keys(d_keys, n, width, d_perm);
+  OSHB_CATCH
+}
+
+// ---- adjacency ---------------------------------------------------------------------------
+int oshb_invert_adj(const int32_t* d_hl2l, const int8_t* d_down_codes, int64_t nhigh, int deg, int32_t nlow,
+    int32_t* d_l2lh, int32_t* d_lh2h, int8_t* d_codes) {
+  OSHB_TRY
+  init_ctx(-1);
+  Adj down;
+  down.ab2b = LOs::view(d_hl2l, nhigh * deg);
+  if (d_down_codes) down.codes = Bytes::view(d_down_codes, nhigh * deg);
+  Adj up = invert_adj(down, deg, nlow);
+  export_array(up.a2ab, d_l2lh, 0);
+  export_array(up.ab2b, d_lh2h, 0);
+  export_array(up.codes, d_codes, 0);
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_transit(const int32_t* d_hm2m, const int8_t* d_hm_codes, const int32_t* d_ml2l, const int8_t* d_ml_codes,
+    int64_t nhigh, int high_dim, int low_dim, int32_t* d_hl2l, int8_t* d_codes_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  int mid_dim = low_dim + 1;
+  int nmh = simplex_degree(high_dim, mid_dim);
+  int nlh = simplex_degree(high_dim, low_dim);
+  Adj h2m, m2l;
+  h2m.ab2b = LOs::view(d_hm2m, nhigh * nmh);
+  h2m.codes = Bytes::view(d_hm_codes, nhigh * nmh);
+  // the mid arrays are only read at the entries the highs reference; their length is
+  // not needed by the kernel, so view them with a nominal size
+  m2l.ab2b = LOs::view(d_ml2l, 1);
+  if (d_ml_codes) m2l.codes = Bytes::view(d_ml_codes, 1);
+  Adj r = transit(h2m, m2l, high_dim, low_dim);
+  d2d(d_hl2l, r.ab2b.data(), size_t(nhigh) * nlh * sizeof(LO));
+  if (low_dim == 1 && d_codes_out) d2d(d_codes_out, r.codes.data(), size_t(nhigh) * nlh);
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_reflect_down(const int32_t* d_hv2v, int64_t nhigh, int high_dim, const int32_t* d_lv2v, int64_t nlow,
+    int low_dim, int32_t nverts, int32_t* d_hl2l, int8_t* d_codes) {
+  OSHB_TRY
+  init_ctx(-1);
+  device_error_reset();
+  LOs hv2v = LOs::view(d_hv2v, nhigh * (high_dim + 1));
+  LOs lv2v = LOs::view(d_lv2v, nlow * (low_dim + 1));
+  Adj a = reflect_down(hv2v, lv2v, nverts, high_dim, low_dim);
+  export_array(a.ab2b, d_hl2l, 0);
+  export_array(a.codes, d_codes, 0);
+  device_error_check("reflect_down");
+  OSHB_CATCH
+}
+int oshb_find_unique(const int32_t* d_hv2v, int64_t nhigh, int high_dim, int low_dim, int32_t* d_lv2v_out,
+    int64_t* h_nlow) {
+  OSHB_TRY
+  init_ctx(-1);
+  LOs hv2v = LOs::view(d_hv2v, nhigh * (high_dim + 1));
+  LOs lv = find_unique(hv2v, high_dim, low_dim);
+  export_array(lv, d_lv2v_out, 0);
+  *h_nlow = lv.size() / (low_dim + 1);
+  sync_stream();
+  OSHB_CATCH
+}
+
+// ---- geometry ------------------------------------------------------------------------------
+int oshb_measure_edges_metric(int dim, int metric_ncomps, const int32_t* d_ev2v, const double* d_coords,
+    const double* d_metrics, const int32_t* d_a2e, int32_t n, double* d_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  LOs a2e;
+  if (d_a2e) a2e = LOs::view(d_a2e, n);
+  Reals r = measure_edges_metric_raw(dim, LOs::view(d_ev2v, 1), Reals::view(d_coords, 1), Reals::view(d_metrics, 1),
+      metric_ncomps, a2e, n);
+  d2d(d_out, r.data(), size_t(n) * sizeof(Real));
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_measure_qualities(int dim, int metric_ncomps, const int32_t* d_cv2v, const double* d_coords,
+    const double* d_metrics, const int32_t* d_a2e, int32_t n, double* d_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  LOs a2e;
+  if (d_a2e) a2e = LOs::view(d_a2e, n);
+  Reals r = measure_qualities_raw(dim, LOs::view(d_cv2v, 1), Reals::view(d_coords, 1), Reals::view(d_metrics, 1),
+      metric_ncomps, a2e, n);
+  d2d(d_out, r.data(), size_t(n) * sizeof(Real));
+  sync_stream();
+  OSHB_CATCH
+}
+
+// ---- mesh handle -----------------------------------------------------------------------------
+int oshb_mesh_create(int dim, oshb_mesh** out) {
+  OSHB_TRY
+  init_ctx(-1);
+  OSHB_CHECK(dim == 2 || dim == 3);
+  auto* h = new oshb_mesh();
+  h->m.set_dim(dim);
+  *out = h;
+  OSHB_CATCH
+}
+int oshb_mesh_destroy(oshb_mesh* m) {
+  OSHB_TRY
+  delete m;
+  OSHB_CATCH
+}
+int oshb_mesh_clone(const oshb_mesh* m, oshb_mesh** out) {
+  OSHB_TRY
+  auto* h = new oshb_mesh();
+  h->m = m->m;
+  *out = h;
+  OSHB_CATCH
+}
+int oshb_mesh_dim(const oshb_mesh* m, int* dim) {
+  *dim = m->m.dim();
+  return 0;
+}
+int oshb_mesh_nents(const oshb_mesh* m, int ent_dim, int32_t* n) {
+  OSHB_TRY
+  OSHB_CHECK(ent_dim >= 0 && ent_dim <= m->m.dim());
+  *n = m->m.nents(ent_dim);
+  OSHB_CATCH
+}
+int oshb_mesh_set_verts(oshb_mesh* m, int32_t nverts) {
+  m->m.set_verts(nverts);
+  return 0;
+}
+int oshb_mesh_set_ents(oshb_mesh* m, int ent_dim, int32_t nents, const int32_t* down, const int8_t* codes, int host) {
+  OSHB_TRY
+  OSHB_CHECK(ent_dim >= 1 && ent_dim <= m->m.dim());
+  int deg = simplex_degree(ent_dim, ent_dim - 1);
+  Adj a;
+  a.ab2b = import_array<LO>(down, int64_t(nents) * deg, host);
+  if (ent_dim > 1) {
+    OSHB_CHECK(codes != nullptr);
+    a.codes = import_array<I8>(codes, int64_t(nents) * deg, host);
+  }
+  m->m.set_ents(ent_dim, a);
+  if (host) sync_stream();
+  OSHB_CATCH
+}
+int oshb_mesh_add_tag(oshb_mesh* m, int ent_dim, const char* name, int type, int ncomps, const void* data, int host,
+    int internal) {
+  OSHB_TRY
+  OSHB_CHECK(ent_dim >= 0 && ent_dim <= m->m.dim());
+  int64_t n = int64_t(m->m.nents(ent_dim)) * ncomps;
+  Tag t;
+  t.name = name;
+  t.type = type;
+  t.ncomps = ncomps;
+  switch (type) {
+    case OSHB_I8:
+      t.i8 = import_array<I8>(static_cast<I8 const*>(data), n, host);
+      break;
+    case OSHB_I32:
+      t.i32 = import_array<LO>(static_cast<LO const*>(data), n, host);
+      break;
+    case OSHB_I64:
+      t.i64 = import_array<GO>(static_cast<GO const*>(data), n, host);
+      break;
+    case OSHB_F64:
+      t.f64 = import_array<Real>(static_cast<Real const*>(data), n, host);
+      break;
+    default:
+      fail(__FILE__, __LINE__, "unknown tag type");
+  }
+  m->m.add_tag(ent_dim, t, internal != 0);
+  if (host) sync_stream();
+  OSHB_CATCH
+}
+int oshb_mesh_remove_tag(oshb_mesh* m, int ent_dim, const char* name) {
+  OSHB_TRY
+  m->m.remove_tag(ent_dim, name);
+  OSHB_CATCH
+}
+int oshb_mesh_ntags(const oshb_mesh* m, int ent_dim, int* ntags) {
+  OSHB_TRY
+  OSHB_CHECK(ent_dim >= 0 && ent_dim <= m->m.dim());
+  *ntags = int(m->m.tags_[ent_dim].size());
+  OSHB_CATCH
+}
+int oshb_mesh_tag_info(const oshb_mesh* m, int ent_dim, int i, char* name_out, int name_cap, int* type, int* ncomps) {
+  OSHB_TRY
+  OSHB_CHECK(ent_dim >= 0 && ent_dim <= m->m.dim());
+  OSHB_CHECK(i >= 0 && size_t(i) < m->m.tags_[ent_dim].size());
+  Tag const& t = m->m.tags_[ent_dim][size_t(i)];
+  snprintf(name_out, size_t(name_cap), "%s", t.name.c_str());
+  *type = t.type;
+  *ncomps = t.ncomps;
+  OSHB_CATCH
+}
+int oshb_mesh_get_tag(const oshb_mesh* m, int ent_dim, const char* name, void* out, int host) {
+  OSHB_TRY
+  Tag const* t = m->m.find_tag(ent_dim, name);
+  if (!t) fail(__FILE__, __LINE__, std::string("no tag ") + name);
+  size_t bytes = size_t(t->nvalues()) * size_t(Tag::elem_bytes(t->type));
+  if (bytes) {
+    if (host)
+      d2h(out, t->data(), bytes);
+    else
+      d2d(out, t->data(), bytes);
+  }
+  OSHB_CATCH
+}
+int oshb_mesh_ask_down(oshb_mesh* m, int from, int to, int32_t* ab2b_out, int8_t* codes_out, int host) {
+  OSHB_TRY
+  OSHB_CHECK(from > to);
+  Adj a = m->m.ask_down(from, to);
+  export_array(a.ab2b, ab2b_out, host);
+  if (codes_out) {
+    OSHB_CHECK(a.codes.exists());
+    export_array(a.codes, codes_out, host);
+  }
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_mesh_ask_up(oshb_mesh* m, int from, int to, int64_t* nentries, int32_t* a2ab_out, int32_t* ab2b_out,
+    int8_t* codes_out, int host) {
+  OSHB_TRY
+  OSHB_CHECK(from < to);
+  Adj a = m->m.ask_up(from, to);
+  if (nentries) *nentries = a.ab2b.size();
+  export_array(a.a2ab, a2ab_out, host);
+  export_array(a.ab2b, ab2b_out, host);
+  export_array(a.codes, codes_out, host);
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_mesh_ask_star(oshb_mesh* m, int ent_dim, int64_t* nentries, int32_t* a2ab_out, int32_t* ab2b_out, int host) {
+  OSHB_TRY
+  Adj a = m->m.ask_star(ent_dim);
+  if (nentries) *nentries = a.ab2b.size();
+  export_array(a.a2ab, a2ab_out, host);
+  export_array(a.ab2b, ab2b_out, host);
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_mesh_ask_lengths(oshb_mesh* m) {
+  OSHB_TRY
+  m->m.ask_lengths();
+  OSHB_CATCH
+}
+int oshb_mesh_ask_qualities(oshb_mesh* m) {
+  OSHB_TRY
+  m->m.ask_qualities();
+  OSHB_CATCH
+}
+
+// ---- hot path ----------------------------------------------------------------------------------
+int oshb_adapt_opts_init(int dim, oshb_adapt_opts* o) {
+  AdaptOpts a(dim);
+  o->min_length_desired = a.min_length_desired;
+  o->max_length_desired = a.max_length_desired;
+  o->max_length_allowed = a.max_length_allowed;
+  o->min_quality_allowed = a.min_quality_allowed;
+  o->min_quality_desired = a.min_quality_desired;
+  o->verbosity = a.verbosity;
+  return 0;
+}
+
+int oshb_refine_qualities(oshb_mesh* m, const int32_t* cands2edges, int32_t ncands, double* quals_out, int host) {
+  OSHB_TRY
+  device_error_reset();
+  LOs c = import_array<LO>(cands2edges, ncands, host);
+  Reals q = refine_qualities(&m->m, c);
+  export_array(q, quals_out, host);
+  device_error_check("refine_qualities");
+  OSHB_CATCH
+}
+int oshb_mident_metrics(oshb_mesh* m, const int32_t* a2e, int32_t n, double* out, int host) {
+  OSHB_TRY
+  device_error_reset();
+  LOs a = import_array<LO>(a2e, n, host);
+  Reals r = get_mident_metrics(&m->m, EDGE, a, m->m.get_reals(VERT, "metric"));
+  export_array(r, out, host);
+  device_error_check("mident_metrics");
+  OSHB_CATCH
+}
+int oshb_find_indset(oshb_mesh* m, const double* edge_quals, const int8_t* initial, int8_t* keys_out, int host,
+    int32_t* nrounds) {
+  OSHB_TRY
+  LO ne = m->m.nedges();
+  Reals q = import_array<Real>(edge_quals, ne, host);
+  Bytes c = import_array<I8>(initial, ne, host);
+  int rounds = 0;
+  Bytes k = find_indset(&m->m, EDGE, q, c, &rounds);
+  if (nrounds) *nrounds = rounds;
+  export_array(k, keys_out, host);
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_rep_vertex2md_order(oshb_mesh* m, const int8_t* keys, int32_t* order_out, int host) {
+  OSHB_TRY
+  Bytes k = import_array<I8>(keys, m->m.nedges(), host);
+  LOs o = get_rep2md_order_adapt(&m->m, EDGE, VERT, k);
+  export_array(o, order_out, host);
+  sync_stream();
+  OSHB_CATCH
+}
+
+int oshb_refine_by_size(oshb_mesh* m, const oshb_adapt_opts* o, int* did) {
+  OSHB_TRY
+  AdaptOpts a(m->m.dim());
+  if (o) {
+    a.min_length_desired = o->min_length_desired;
+    a.max_length_desired = o->max_length_desired;
+    a.max_length_allowed = o->max_length_allowed;
+    a.min_quality_allowed = o->min_quality_allowed;
+    a.min_quality_desired = o->min_quality_desired;
+    a.verbosity = o->verbosity;
+  }
+  bool r = refine_by_size(&m->m, a);
+  *did = r ? 1 : 0;
+  OSHB_CATCH
+}
+int oshb_last_pass_stats(oshb_pass_stats* out) {
+  PassStats const& s = last_pass_stats();
+  out->ncands = s.ncands;
+  out->nkeys = s.nkeys;
+  out->indset_rounds = s.indset_rounds;
+  for (int i = 0; i < 4; ++i) {
+    out->nents_before[i] = s.nents_before[i];
+    out->nents_after[i] = s.nents_after[i];
+  }
+  return 0;
+}
+
+}  // extern "C"

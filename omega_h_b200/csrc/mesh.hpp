@@ -1,0 +1,163 @@
+// Device-resident mesh: one-level-down adjacencies + tags stored, everything else
+// derived on demand and cached -- the same contract as the reference's Mesh
+// (src/Omega_h_mesh.hpp:36-177, derive_adj src/Omega_h_mesh.cpp:307-357), but every
+// array lives in HBM and every derivation is a kernel from adj.cu.
+#pragma once
+#include <map>
+
+#include "rt.hpp"
+#include "simplex.hpp"
+
+namespace oshb {
+
+struct Adj {
+  LOs a2ab;     // offsets (absent for fixed-degree downward adjacencies)
+  LOs ab2b;     // entries
+  Bytes codes;  // alignment codes (absent when the target is VERT)
+};
+
+enum TagType { TAG_I8 = 0, TAG_I32 = 1, TAG_I64 = 2, TAG_F64 = 3 };
+
+struct Tag {
+  std::string name;
+  int type = TAG_I8;
+  int ncomps = 1;
+  Bytes i8;
+  LOs i32;
+  GOs i64;
+  Reals f64;
+  int64_t nvalues() const {
+    switch (type) {
+      case TAG_I8:
+        return i8.size();
+      case TAG_I32:
+        return i32.size();
+      case TAG_I64:
+        return i64.size();
+      default:
+        return f64.size();
+    }
+  }
+  void* data() const {
+    switch (type) {
+      case TAG_I8:
+        return i8.data();
+      case TAG_I32:
+        return i32.data();
+      case TAG_I64:
+        return i64.data();
+      default:
+        return f64.data();
+    }
+  }
+  static int elem_bytes(int type) { return type == TAG_I8 ? 1 : (type == TAG_I32 ? 4 : 8); }
+};
+
+struct AdaptOpts {
+  // defaults of AdaptOpts(dim), src/Omega_h_adapt.cpp:52-85
+  Real min_length_desired;
+  Real max_length_desired;
+  Real max_length_allowed;
+  Real min_quality_allowed;
+  Real min_quality_desired;
+  int verbosity;
+  explicit AdaptOpts(int dim);
+};
+
+class Mesh {
+ public:
+  int dim_ = 0;
+  LO nents_[4] = {0, 0, 0, 0};
+  std::vector<Tag> tags_[4];
+  Adj adjs_[4][4];
+  bool has_adj_[4][4];
+  Adj star_[4];
+  bool has_star_[4];
+
+  Mesh();
+  int dim() const { return dim_; }
+  LO nents(int d) const { return nents_[d]; }
+  LO nverts() const { return nents_[0]; }
+  LO nedges() const { return nents_[1]; }
+  LO nelems() const { return nents_[dim_]; }
+  void set_dim(int d) { dim_ = d; }
+  void set_verts(LO n) { nents_[0] = n; }
+  void set_ents(int ent_dim, Adj const& down);  // src/Omega_h_mesh.cpp:87-95
+  bool has_adj(int from, int to) const { return has_adj_[from][to]; }
+  void add_adj(int from, int to, Adj const& a) {
+    adjs_[from][to] = a;
+    has_adj_[from][to] = true;
+  }
+  Adj ask_adj(int from, int to);
+  Adj ask_down(int from, int to) { return ask_adj(from, to); }
+  Adj ask_up(int from, int to) { return ask_adj(from, to); }
+  LOs ask_verts_of(int d) { return ask_adj(d, VERT).ab2b; }
+  Adj ask_star(int d);  // EDGE star only (src/Omega_h_mesh.cpp:331-338)
+
+  Tag* find_tag(int d, std::string const& name);
+  Tag const* find_tag(int d, std::string const& name) const;
+  bool has_tag(int d, std::string const& name) const { return find_tag(d, name) != nullptr; }
+  void add_tag(int d, Tag const& t, bool internal = false);  // replaces; src/Omega_h_mesh.cpp:132-177
+  void remove_tag(int d, std::string const& name);
+  void add_tag(int d, std::string const& name, int ncomps, Bytes a, bool internal = false);
+  void add_tag(int d, std::string const& name, int ncomps, LOs a, bool internal = false);
+  void add_tag(int d, std::string const& name, int ncomps, GOs a, bool internal = false);
+  void add_tag(int d, std::string const& name, int ncomps, Reals a, bool internal = false);
+  Reals get_reals(int d, std::string const& name) const;
+  Bytes get_bytes(int d, std::string const& name) const;
+  LOs get_los(int d, std::string const& name) const;
+  GOs get_gos(int d, std::string const& name) const;
+  Reals coords() const { return get_reals(VERT, "coordinates"); }
+  GOs globals(int d) const { return get_gos(d, "global"); }
+  int metric_ncomps() const;
+  int metric_dim() const;
+  Reals ask_lengths();    // src/Omega_h_mesh.cpp:374-380
+  Reals ask_qualities();  // src/Omega_h_mesh.cpp:382-388
+  Mesh copy_meta() const;
+
+ private:
+  Adj derive_adj(int from, int to);
+};
+
+// ---- adjacency kernels (adj.cu) -----------------------------------------------------
+Adj invert_adj(Adj const& down, int nlows_per_high, LO nlows);                          // src/Omega_h_adj.cpp:231-263
+Adj transit(Adj const& h2m, Adj const& m2l, int high_dim, int low_dim);                 // src/Omega_h_adj.cpp:443-510
+Adj reflect_down(LOs hv2v, LOs lv2v, LO nverts, int high_dim, int low_dim);             // src/Omega_h_adj.cpp:424-441
+Adj edges_star(int dim, Adj const& f2e, Adj const& e2f, Adj const& r2e, Adj const& e2r);// src/Omega_h_adj.cpp:532-589
+LOs form_uses(LOs hv2v, int high_dim, int low_dim);                                      // src/Omega_h_adj.cpp:155-176
+LOs find_unique(LOs hv2v, int high_dim, int low_dim);                                    // src/Omega_h_adj.cpp:133-153
+
+// ---- maps (maps.cu) -------------------------------------------------------------------
+LOs collect_marked(Bytes marks, LO* count_out = nullptr);          // src/Omega_h_map.cpp:174-185
+LOs offset_scan(Bytes a);
+LOs offset_scan(LOs a);
+LO last_of(LOs a);
+
+// ---- geometry / metric kernels (geom.cu) ------------------------------------------------
+Reals measure_edges_metric(Mesh* mesh, LOs a2e, Reals metrics);     // src/Omega_h_shape.cpp:7-37 (a2e may be absent = all)
+Reals measure_edges_metric_raw(int dim, LOs ev2v, Reals coords, Reals metrics, int metric_ncomps, LOs a2e, LO n);
+Reals measure_qualities(Mesh* mesh, LOs a2e, Reals metrics);        // src/Omega_h_quality.cpp:7-52
+Reals measure_qualities_raw(int dim, LOs cv2v, Reals coords, Reals metrics, int metric_ncomps, LOs a2e, LO n);
+Reals get_mident_metrics(Mesh* mesh, int ent_dim, LOs a2e, Reals v2m);  // src/Omega_h_metric.cpp:56-99
+Reals refine_qualities(Mesh* mesh, LOs cands2edges);                // src/Omega_h_refine_qualities.cpp:34-107
+
+// ---- refine pass (refine.cu) ------------------------------------------------------------
+Bytes find_indset(Mesh* mesh, int ent_dim, Reals quality, Bytes candidates, int* nrounds = nullptr);  // src/Omega_h_indset.cpp:27-34
+LOs get_rep2md_order_adapt(Mesh* mesh, int key_dim, int rep_dim, Bytes kds_are_keys);  // src/Omega_h_modify.cpp:269-281
+void refine_products(Mesh* mesh, int ent_dim, LOs keys2edges, LOs keys2midverts, LOs old_verts2new_verts,
+    LOs& keys2prods, LOs& prod_verts2verts);                        // src/Omega_h_refine_topology.cpp:186-203
+bool refine_by_size(Mesh* mesh, AdaptOpts const& opts);             // src/Omega_h_refine.cpp:92-100
+
+struct PassStats {
+  LO ncands = 0, nkeys = 0, indset_rounds = 0;
+  LO nents_before[4] = {0, 0, 0, 0};
+  LO nents_after[4] = {0, 0, 0, 0};
+};
+PassStats const& last_pass_stats();
+
+// device error cell: kernels set bits, the host checks at the next read-back
+void device_error_reset();
+void device_error_check(char const* where);
+int* device_error_cell();
+
+}  // namespace oshb

@@ -1,0 +1,135 @@
+// Context, stream-ordered device memory, host<->device copies. See rt.hpp.
+#include "rt.hpp"
+
+namespace oshb {
+
+static Ctx g_ctx;
+static std::string g_last_error;
+
+Ctx& ctx() { return g_ctx; }
+
+std::string& last_error_string() { return g_last_error; }
+
+[[noreturn]] void fail(char const* file, int line, std::string const& msg) {
+  std::string full = std::string(file) + ":" + std::to_string(line) + ": " + msg;
+  g_last_error = full;
+  throw Error(full);
+}
+
+#ifdef OSHB_EMU
+
+void init_ctx(int) {
+  Ctx& c = g_ctx;
+  if (c.ready) return;
+  c.device = 0;
+  c.pinned = malloc(4096);
+  c.dscratch_bytes = 1 << 20;
+  c.dscratch = malloc(c.dscratch_bytes);
+  c.ready = true;
+}
+void sync_stream() {}
+void* dev_alloc(size_t bytes) {
+  Ctx& c = g_ctx;
+  c.alloc_bytes += bytes;
+  if (c.alloc_bytes > c.peak_bytes) c.peak_bytes = c.alloc_bytes;
+  void* p = malloc(bytes ? bytes : 1);
+  memset(p, 0xCD, bytes);  // poison so reads of unwritten entries show up
+  return p;
+}
+void dev_free(void* p, size_t bytes) {
+  g_ctx.alloc_bytes -= bytes;
+  free(p);
+}
+void h2d(void* dst, void const* src, size_t bytes) { memcpy(dst, src, bytes); }
+void d2h(void* dst, void const* src, size_t bytes) {
+  memcpy(dst, src, bytes);
+  g_ctx.syncs++;
+}
+void d2d(void* dst, void const* src, size_t bytes) { memcpy(dst, src, bytes); }
+void dev_memset(void* dst, int byte, size_t bytes) { memset(dst, byte, bytes); }
+
+#else
+
+void init_ctx(int device) {
+  Ctx& c = g_ctx;
+  if (c.ready) return;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fail(__FILE__, __LINE__,
+        std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+            "); this library has no CPU path");
+  }
+  if (device < 0) device = 0;
+  OSHB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  OSHB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    fail(__FILE__, __LINE__, "this library is built for sm_100a only; device is sm_" +
+                                 std::to_string(prop.major) + std::to_string(prop.minor));
+  }
+  c.device = device;
+  c.sms = prop.multiProcessorCount;
+  OSHB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  // keep freed blocks in the pool: temporaries of one pass are reused by the next
+  cudaMemPool_t pool;
+  OSHB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t threshold = UINT64_MAX;
+  OSHB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  OSHB_CUDA(cudaMallocHost(&c.pinned, 4096));
+  c.dscratch_bytes = 8 << 20;
+  OSHB_CUDA(cudaMalloc(&c.dscratch, c.dscratch_bytes));
+  c.ready = true;
+}
+
+void sync_stream() { OSHB_CUDA(cudaStreamSynchronize(g_ctx.stream)); }
+
+void* dev_alloc(size_t bytes) {
+  Ctx& c = g_ctx;
+  if (!c.ready) init_ctx(-1);
+  void* p = nullptr;
+  OSHB_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, c.stream));
+  c.alloc_bytes += bytes;
+  if (c.alloc_bytes > c.peak_bytes) c.peak_bytes = c.alloc_bytes;
+  return p;
+}
+
+void dev_free(void* p, size_t bytes) {
+  Ctx& c = g_ctx;
+  c.alloc_bytes -= bytes;
+  cudaFreeAsync(p, c.stream);
+}
+
+void h2d(void* dst, void const* src, size_t bytes) {
+  Ctx& c = g_ctx;
+  if (!c.ready) init_ctx(-1);
+  OSHB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
+  // pageable sources are staged by the driver before the call returns; pinned ones
+  // must stay alive until the stream reaches the copy -- callers that pass pinned
+  // memory synchronise themselves (see capi.cu)
+}
+
+void d2h(void* dst, void const* src, size_t bytes) {
+  Ctx& c = g_ctx;
+  if (bytes <= 4096) {
+    OSHB_CUDA(cudaMemcpyAsync(c.pinned, src, bytes, cudaMemcpyDeviceToHost, c.stream));
+    OSHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(dst, c.pinned, bytes);
+  } else {
+    OSHB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
+    OSHB_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  c.syncs++;
+}
+
+void d2d(void* dst, void const* src, size_t bytes) {
+  OSHB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_ctx.stream));
+}
+
+void dev_memset(void* dst, int byte, size_t bytes) {
+  OSHB_CUDA(cudaMemsetAsync(dst, byte, bytes, g_ctx.stream));
+}
+
+#endif
+
+}  // namespace oshb

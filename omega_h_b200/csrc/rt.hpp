@@ -1,0 +1,215 @@
+// Runtime layer of the B200 refine path: device arrays, the launch helper every
+// entity-parallel kernel goes through, atomics, scalar read-back.
+//
+// Replaces the reference's array runtime + execution backends for this path
+// (Read/Write: src/Omega_h_array.hpp:23-228; parallel_for: src/Omega_h_for.hpp:20-101;
+//  atomics: src/Omega_h_atomics.hpp:12-37). One process drives one GPU; all work is
+// enqueued on one stream; device memory comes from the stream-ordered pool
+// (cudaMallocAsync) so temporaries cost no cudaMalloc and no implicit sync.
+//
+// OSHB_EMU: a TEST-ONLY build mode (tests/emu/) that compiles the very same kernel
+// bodies as serial host loops so the mesh logic can be checked against the oracle on a
+// machine without a GPU. The product library is always built by nvcc without OSHB_EMU
+// and contains no host execution path for kernels.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifndef OSHB_EMU
+#include <cuda_runtime.h>
+#endif
+
+namespace oshb {
+
+typedef int8_t I8;
+typedef int32_t LO;
+typedef int64_t GO;
+typedef double Real;
+
+#ifdef OSHB_EMU
+#define OSHB_HD inline
+#define OSHB_LAMBDA [=]
+#define OSHB_CONSTANT static const
+#else
+#define OSHB_HD __host__ __device__ __forceinline__
+#define OSHB_LAMBDA [=] __device__
+#define OSHB_CONSTANT __constant__ const
+#endif
+
+struct Error : public std::runtime_error {
+  explicit Error(std::string const& s) : std::runtime_error(s) {}
+};
+
+[[noreturn]] void fail(char const* file, int line, std::string const& msg);
+#define OSHB_CHECK(cond)                                            \
+  do {                                                              \
+    if (!(cond)) ::oshb::fail(__FILE__, __LINE__, "check failed: " #cond); \
+  } while (0)
+
+#ifndef OSHB_EMU
+#define OSHB_CUDA(call)                                                       \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess)                                                    \
+      ::oshb::fail(__FILE__, __LINE__, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+#endif
+
+struct Ctx {
+#ifndef OSHB_EMU
+  cudaStream_t stream = nullptr;
+#endif
+  int device = -1;
+  int sms = 148;
+  bool ready = false;
+  uint64_t launches = 0;    // kernels launched by this library (bench.py "gpu_launches")
+  uint64_t syncs = 0;       // blocking scalar read-backs
+  uint64_t alloc_bytes = 0; // live device bytes handed out
+  uint64_t peak_bytes = 0;
+  void* pinned = nullptr;   // 4 KB pinned staging for scalar read-backs
+  void* dscratch = nullptr; // device scratch (scan tile descriptors, reduction cells)
+  size_t dscratch_bytes = 0;
+};
+Ctx& ctx();
+void init_ctx(int device);  // idempotent; fails loudly when no CUDA device is usable
+void sync_stream();
+
+void* dev_alloc(size_t bytes);
+void dev_free(void* p, size_t bytes);
+void h2d(void* dst, void const* src, size_t bytes);
+void d2h(void* dst, void const* src, size_t bytes);  // blocking
+void d2d(void* dst, void const* src, size_t bytes);
+void dev_memset(void* dst, int byte, size_t bytes);
+
+// reference-counted device array, the counterpart of Read<T>/Write<T>
+template <class T>
+class DArr {
+  struct Storage {
+    T* p;
+    int64_t n;
+    bool owned;
+    Storage(int64_t n_) : p(nullptr), n(n_), owned(true) {
+      if (n > 0) p = static_cast<T*>(dev_alloc(size_t(n) * sizeof(T)));
+    }
+    Storage(T* p_, int64_t n_) : p(p_), n(n_), owned(false) {}
+    ~Storage() {
+      if (p && owned) dev_free(p, size_t(n) * sizeof(T));
+    }
+  };
+  std::shared_ptr<Storage> s_;
+
+ public:
+  DArr() {}
+  explicit DArr(int64_t n) : s_(std::make_shared<Storage>(n)) {}
+  bool exists() const { return bool(s_); }
+  int64_t size() const { return s_ ? s_->n : 0; }
+  T* data() const { return s_ ? s_->p : nullptr; }
+  void reset() { s_.reset(); }
+  std::vector<T> to_host() const {
+    std::vector<T> h(static_cast<size_t>(size()));
+    if (size()) d2h(h.data(), data(), size_t(size()) * sizeof(T));
+    return h;
+  }
+  // non-owning view of caller-provided device memory (C-ABI primitives)
+  static DArr view(T const* p, int64_t n) {
+    DArr a;
+    a.s_ = std::make_shared<Storage>(const_cast<T*>(p), n);
+    return a;
+  }
+  static DArr from_host(T const* h, int64_t n) {
+    DArr a(n);
+    if (n) h2d(a.data(), h, size_t(n) * sizeof(T));
+    return a;
+  }
+};
+
+typedef DArr<I8> Bytes;
+typedef DArr<LO> LOs;
+typedef DArr<GO> GOs;
+typedef DArr<Real> Reals;
+
+// blocking read of one device scalar (the analogue of Read<T>::get/last,
+// src/Omega_h_array.cpp:92-119) -- counted, these are the pass's only sync points
+template <class T>
+T read_scalar(T const* dptr) {
+  T v;
+  d2h(&v, dptr, sizeof(T));
+  return v;
+}
+
+#ifdef OSHB_EMU
+template <class F>
+void parallel_for(int64_t n, F f, char const* = nullptr) {
+  for (int64_t i = 0; i < n; ++i) f(LO(i));
+  ctx().launches++;
+}
+OSHB_HD LO atomic_add(LO* p, LO v) {
+  LO old = *p;
+  *p += v;
+  return old;
+}
+OSHB_HD void atomic_max_i32(int* p, int v) {
+  if (v > *p) *p = v;
+}
+OSHB_HD void atomic_or_i32(int* p, int v) { *p |= v; }
+#else
+template <class F>
+__global__ void __launch_bounds__(256) k_for(int64_t n, F f) {
+  int64_t stride = int64_t(gridDim.x) * 256;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) f(LO(i));
+}
+// one thread per entity, grid-stride, grid capped at 16 resident CTAs per SM worth of
+// blocks (a multiple of the SM count) so large launches run as a persistent wave
+template <class F>
+void parallel_for(int64_t n, F f, char const* name = nullptr) {
+  (void)name;
+  if (n <= 0) return;
+  Ctx& c = ctx();
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = int64_t(c.sms) * 16;
+  if (blocks > cap) blocks = cap;
+  k_for<<<unsigned(blocks), 256, 0, c.stream>>>(n, f);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(__FILE__, __LINE__, std::string("kernel launch: ") + cudaGetErrorString(e));
+  c.launches++;
+}
+__device__ __forceinline__ LO atomic_add(LO* p, LO v) { return atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_max_i32(int* p, int v) { atomicMax(p, v); }
+__device__ __forceinline__ void atomic_or_i32(int* p, int v) { atomicOr(p, v); }
+#endif
+
+// ---- cooperative primitives (prims.cu) -------------------------------------------
+// exclusive offset scan, out has n+1 entries, out[0]=0 (src/Omega_h_int_scan.cpp:10-19)
+void scan_offsets(I8 const* in, int64_t n, LO* out);
+void scan_offsets(LO const* in, int64_t n, LO* out);
+void scan_offsets(LO const* in, int64_t n, GO* out);
+void scan_offsets(GO const* in, int64_t n, GO* out);
+int max_i8(I8 const* in, int64_t n);                 // get_max, src/Omega_h_array_ops.cpp:47-68
+void minmax_f64(Real const* in, int64_t n, Real* mn, Real* mx);
+// stable sort of n keys of `width` words each; writes the permutation (sorted -> original)
+void sort_by_keys(LO const* keys, int64_t n, int width, LO* perm);  // src/Omega_h_sort.cpp:57-92
+void sort_by_keys(GO const* keys, int64_t n, int width, LO* perm);
+
+// ---- small helpers built on parallel_for ------------------------------------------
+template <class T>
+void fill(T* p, int64_t n, T v) {
+  parallel_for(n, OSHB_LAMBDA(LO i) { p[i] = v; }, "fill");
+}
+template <class T>
+DArr<T> filled(int64_t n, T v) {
+  DArr<T> a(n);
+  fill(a.data(), n, v);
+  return a;
+}
+template <class T>
+void fill_linear(T* p, int64_t n, T offset, T stride) {
+  parallel_for(n, OSHB_LAMBDA(LO i) { p[i] = offset + stride * T(i); }, "fill_linear");
+}
+
+}  // namespace oshb

@@ -1,6 +1,8 @@
 """Reader for the flat "OSHD1" record files written by oracle/ref_driver.cpp and by
 the package's own dump helper. Test infrastructure."""
+import gzip
 import struct
+
 import numpy as np
 
 _DT = {0: np.int8, 1: np.int32, 2: np.int64, 3: np.float64}
@@ -8,7 +10,8 @@ _DT = {0: np.int8, 1: np.int32, 2: np.int64, 3: np.float64}
 
 def read_oshd(path):
     out = {}
-    with open(path, "rb") as f:
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rb") as f:
         magic = f.read(6)
         assert magic == b"OSHD1\n", magic
         while True:

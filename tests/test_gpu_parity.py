@@ -1,0 +1,124 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against
+ (1) the committed golden fixtures of the reference,
+ (2) fixtures produced on the spot by the unmodified reference (oracle/_ref/ref_driver),
+ (3) numpy for the array primitives.
+Integers bit-exact; reals within 1e-12 relative (isotropic) -- see DESIGN.md for the
+anisotropic libm caveat."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity
+from conftest import golden_files
+
+pytestmark = pytest.mark.gpu
+
+# anisotropic fixtures go through log/exp/acos/cos/cbrt of CUDA's libdevice, which differ
+# from glibc by <=1-2 ulp; the reference itself amplifies that to ~1e-8
+ANISO_RTOL = 1e-7
+
+
+def rtol_of(fx):
+    return parity.RTOL if int(fx["metric_kind"][0]) in (0, 3) else ANISO_RTOL
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p).split(".")[0])
+def test_golden_pass(gpu_lib, path):
+    fx = parity.load(path)
+    rep, _ = parity.check_pass(fx, gpu_lib, rtol=rtol_of(fx))
+    rep.assert_ok()
+
+
+@pytest.mark.parametrize("dim,n,kind", [(3, 12, 0), (3, 8, 2), (2, 24, 0), (2, 16, 1), (3, 6, 3)])
+def test_live_reference_loop(gpu_lib, ref_driver, tmp_path, dim, n, kind):
+    """Whole refine loop on meshes the reference builds and refines right here."""
+    args = [ref_driver, "refine", str(dim), str(n), str(kind), "-1", str(tmp_path / "r")]
+    if kind == 3:
+        args.append("0.47")
+    subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
+    files = sorted(glob.glob(str(tmp_path / "r_pass*.oshd")), key=lambda s: int(s.split("_pass")[1].split(".")[0]))
+    assert files
+    for f in files:
+        fx = parity.load(f)
+        rep, _ = parity.check_pass(fx, gpu_lib, rtol=rtol_of(fx))
+        rep.assert_ok()
+
+
+def test_chained_loop_matches_reference(gpu_lib, ref_driver, tmp_path):
+    """Our own loop (each pass consuming OUR previous output) ends bit-identical to the reference's."""
+    from omega_h_b200 import AdaptOpts, refine_by_size
+    subprocess.run([ref_driver, "refine", "3", "8", "0", "-1", str(tmp_path / "r")], check=True, stdout=subprocess.DEVNULL)
+    files = sorted(glob.glob(str(tmp_path / "r_pass*.oshd")), key=lambda s: int(s.split("_pass")[1].split(".")[0]))
+    m = parity.mesh_from_fixture(parity.load(files[0]), gpu_lib)
+    opts = AdaptOpts(m)
+    last = None
+    for f in files:
+        fx = parity.load(f)
+        did = refine_by_size(m, opts)
+        assert int(did) == int(fx["did"][0])
+        if did:
+            last = fx
+    rep = parity.Report()
+    parity.compare_mesh(rep, m, last, "out:")
+    rep.assert_ok()
+
+
+# ---- array primitives against numpy -----------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 31, 4096, 4097, 1_000_003, 20_000_000])
+@pytest.mark.parametrize("dtype", [np.int8, np.int32])
+def test_offset_scan(gpu_lib, n, dtype):
+    import ctypes as C
+    rng = np.random.default_rng(n + 1)
+    a = rng.integers(0, 3, size=n).astype(dtype)
+    d_in = gpu_lib.to_device(a)
+    d_out = gpu_lib.empty_device(n + 1, np.int32)
+    fn = gpu_lib.c.oshb_offset_scan_i8 if dtype == np.int8 else gpu_lib.c.oshb_offset_scan_i32
+    gpu_lib.check(fn(d_in.ptr, C.c_int64(n), d_out.ptr))
+    got = d_out.to_host()
+    want = np.concatenate([[0], np.cumsum(a.astype(np.int64))]).astype(np.int32)
+    assert np.array_equal(got, want)
+
+
+def test_offset_scan_i64(gpu_lib):
+    import ctypes as C
+    n = 3_000_001
+    a = np.full(n, 2_000, dtype=np.int32)  # sum 6e9 overflows int32
+    d_in = gpu_lib.to_device(a)
+    d_out = gpu_lib.empty_device(n + 1, np.int64)
+    gpu_lib.check(gpu_lib.c.oshb_offset_scan_i32_i64(d_in.ptr, C.c_int64(n), d_out.ptr))
+    got = d_out.to_host()
+    assert np.array_equal(got, np.concatenate([[0], np.cumsum(a.astype(np.int64))]))
+
+
+@pytest.mark.parametrize("n", [1, 1000, 2_000_003])
+def test_collect_marked(gpu_lib, n):
+    import ctypes as C
+    rng = np.random.default_rng(n)
+    m = (rng.random(n) < 0.3).astype(np.int8)
+    d_in = gpu_lib.to_device(m)
+    d_out = gpu_lib.empty_device(n, np.int32)
+    cnt = C.c_int32()
+    gpu_lib.check(gpu_lib.c.oshb_collect_marked(d_in.ptr, C.c_int64(n), d_out.ptr, C.byref(cnt)))
+    want = np.nonzero(m)[0].astype(np.int32)
+    assert cnt.value == want.size
+    assert np.array_equal(d_out.to_host(cnt.value), want)
+
+
+@pytest.mark.parametrize("width,dtype,n", [(1, np.int32, 1000), (2, np.int32, 100_003), (3, np.int32, 1_000_000),
+                                           (3, np.int64, 300_001), (1, np.int64, 5)])
+def test_sort_by_keys(gpu_lib, width, dtype, n):
+    """stable lexicographic sort; known answers of unit_array_algs.cpp:36-57 are in test_known_answers"""
+    import ctypes as C
+    rng = np.random.default_rng(7)
+    hi = 50 if dtype == np.int32 else (1 << 40)
+    keys = rng.integers(0, hi, size=(n, width)).astype(dtype)
+    d_k = gpu_lib.to_device(keys.reshape(-1))
+    d_p = gpu_lib.empty_device(n, np.int32)
+    fn = gpu_lib.c.oshb_sort_by_keys_i32 if dtype == np.int32 else gpu_lib.c.oshb_sort_by_keys_i64
+    gpu_lib.check(fn(d_k.ptr, C.c_int64(n), C.c_int(width), d_p.ptr))
+    got = d_p.to_host()
+    want = np.lexsort([keys[:, k] for k in range(width - 1, -1, -1)]).astype(np.int32)  # lexsort is stable
+    assert np.array_equal(got, want)
