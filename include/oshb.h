@@ -126,6 +126,12 @@ int oshb_mesh_ask_star(oshb_mesh* m, int ent_dim, int64_t* nentries, int32_t* a2
 int oshb_mesh_ask_lengths(oshb_mesh* m);
 int oshb_mesh_ask_qualities(oshb_mesh* m);
 
+/* build_box(comm, OMEGA_H_SIMPLEX, x, y, z, nx, ny, nz, symmetric=false),
+ * src/Omega_h_build.cpp:136-149: nz==0 builds a 2-D triangle mesh. The mesh is built on the
+ * device and is identical, entity for entity, to the reference's (Hilbert-ordered, box
+ * classification, identity globals). */
+int oshb_build_box(double x, double y, double z, int32_t nx, int32_t ny, int32_t nz, oshb_mesh** out);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* AdaptOpts, src/Omega_h_adapt.hpp:50-82; defaults from oshb_adapt_opts_init(dim),
  * src/Omega_h_adapt.cpp:52-85 */

@@ -474,3 +474,15 @@ int oshb_last_pass_stats(oshb_pass_stats* out) {
 }
 
 }  // extern "C"
+
+namespace oshb {
+Mesh build_box(int dim, Real x, Real y, Real z, LO nx, LO ny, LO nz);
+}
+extern "C" int oshb_build_box(double x, double y, double z, int32_t nx, int32_t ny, int32_t nz, oshb_mesh** out) {
+  OSHB_TRY
+  init_ctx(-1);
+  auto* h = new oshb_mesh();
+  h->m = oshb::build_box(nz > 0 ? 3 : 2, x, y, z, nx, ny, nz);
+  *out = h;
+  OSHB_CATCH
+}

@@ -225,6 +225,17 @@ class Mesh:
         return out
 
 
+def build_box(x, y, z, nx, ny, nz, lib=None):
+    """build_box(world, OMEGA_H_SIMPLEX, x, y, z, nx, ny, nz) on the device
+    (src/Omega_h_build.cpp:136-149); nz == 0 gives a 2-D triangle mesh."""
+    lib = lib or _lib.default_lib()
+    lib.init()
+    h = C.c_void_p()
+    lib.check(lib.c.oshb_build_box(C.c_double(x), C.c_double(y), C.c_double(z), C.c_int32(nx), C.c_int32(ny),
+                                   C.c_int32(nz), C.byref(h)))
+    return Mesh(3 if nz else 2, lib, h)
+
+
 def refine_by_size(mesh, opts=None):
     """One metric-driven refine pass; returns False if the mesh was not modified
     (src/Omega_h_refine.cpp:92-100)."""
