@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py -- new tets/s of the metric-driven refine loop (BASELINE.json metric).
+
+One "step" = the whole `while (refine_by_size(&mesh, opts))` loop on one freshly built box
+mesh: config[1] of BASELINE.json, `build_box 64^3 (x6 tets)` with the uniform isotropic
+metric h = 1/(2n) (4 doubling passes, 1,572,864 -> 25,165,824 tets, 23,592,960 new tets).
+
+  value : new tets / device time of the loops, input mesh resident in HBM (CUDA events on the
+          library's stream, max over ranks)
+  e2e   : the same loop driven through the public host-buffer API: every step uploads the
+          input mesh from pinned host arrays (Mesh.set_ents/add_tag), runs the loop and reads
+          the whole refined mesh back into pinned host arrays
+  roofline : the dominant kernel, timed live with CUDA events inside the timed region,
+          algorithmic bytes declared by its call site / measured HBM peak
+  cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref, OpenMP build) on the
+          box's host cores, bounded sample of the same workload
+
+N > 1 (round 1): every rank refines its own box (independent replicas, no ghost exchange yet
+-- see DESIGN.md "multi-GPU"); value = sum of new tets / max time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "new tets/sec, adapt() refine pass"
+UNIT = "tets/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=64, help="box cells per axis (config[1] = 64)")
+    ap.add_argument("--profile", action="store_true", help="print a per-kernel time table to stderr and exit")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(n):
+    return {
+        "workload": "3D tet unit cube build_box %d^3 (x6 tets), uniform isotropic metric h=1/(2n), "
+                    "while(refine_by_size) loop (4 doubling passes, x16 elements)" % n,
+        "box_n": n,
+        "metric": "isotropic ncomps=1",
+        "l2": "inputs larger than L2 (%.0f MB input mesh, GB-scale outputs); no explicit flush" % (n ** 3 * 6 * 145 / 1e6),
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm_sorted = sorted(sm)
+        # "under load": the upper half of the samples (the loop is short, idle samples drag the median)
+        load = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference on the host cores
+# ---------------------------------------------------------------------------------------------
+def run_reference(n, maxpasses, omp=True):
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver_omp" if omp else "ref_driver")
+    if not os.path.exists(exe):
+        return None
+    env = dict(os.environ)
+    cores = os.cpu_count() or 1
+    env["OMP_NUM_THREADS"] = str(cores)
+    env["OMP_PROC_BIND"] = "false"
+    out = subprocess.run([exe, "time", "3", str(n), "0", str(maxpasses)], capture_output=True, text=True, env=env)
+    if out.returncode != 0:
+        return None
+    for ln in out.stdout.splitlines():
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return None
+
+
+def reference_sample(n):
+    """bounded sample: the first two passes of the same loop on the same box (the remaining two
+    passes repeat the same work on 4x and 8x the entities)."""
+    r = run_reference(n, 2, omp=True)
+    if r is None:
+        return None
+    new = r["nelems_after"] - r["nelems_before"]
+    return {"value": new / r["seconds"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+            "sample": "passes 0-1 of the %d^3 loop (%d -> %d tets) in %.2f s, OpenMP build of the unmodified "
+                      "reference (oracle/_ref), %d threads" % (n, r["nelems_before"], r["nelems_after"], r["seconds"],
+                                                               r["threads"]),
+            "seconds": r["seconds"]}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    last = None
+    t0 = time.time()
+    for i in range(args.warmup + args.steps):
+        # keep the whole arm within a few minutes whatever K/W the driver passes
+        if i >= 1 and time.time() - t0 > 150:
+            break
+        s = reference_sample(args.n)
+        if s is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_omp missing or failed"}))
+            return 0
+        last = s
+        if i >= min(args.warmup, 1):
+            vals.append(s)
+    if not vals:
+        vals = [last]
+    secs = sum(v["seconds"] for v in vals) / len(vals)
+    value = sum(v["value"] for v in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": secs * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.n),
+        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    line["cpu_baseline"]["value"] = value
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def build_input(n, lib):
+    import numpy as np
+    from omega_h_b200 import VERT, build_box
+    m = build_box(1.0, 1.0, 1.0, n, n, n, lib=lib)
+    h = 1.0 / n / 2.0
+    m.add_tag(VERT, "metric", 1, np.full(m.nverts(), 1.0 / (h * h)))
+    m.ask_lengths()
+    m.ask_qualities()
+    lib.sync()
+    return m
+
+
+def run_loop(m, opts):
+    from omega_h_b200 import refine_by_size
+    passes = 0
+    while refine_by_size(m, opts):
+        passes += 1
+    return passes
+
+
+def host_copy_of(m, lib):
+    """Pinned host image of a mesh: what a caller that keeps its mesh on the host hands over."""
+    dim = m.dim()
+    img = {"dim": dim, "nverts": m.nverts(), "down": {}, "tags": {}}
+    nbytes = 0
+    for d in range(1, dim + 1):
+        ab2b, codes = m.ask_down(d, d - 1)
+        pa = lib.pinned_empty(ab2b.size, ab2b.dtype)
+        pa[:] = ab2b
+        pc = None
+        if codes is not None:
+            pc = lib.pinned_empty(codes.size, codes.dtype)
+            pc[:] = codes
+            nbytes += pc.nbytes
+        img["down"][d] = (pa, pc)
+        nbytes += pa.nbytes
+    for d in range(dim + 1):
+        for name, _, nc in m.tags(d):
+            a = m.get_array(d, name)
+            pa = lib.pinned_empty(a.size, a.dtype)
+            pa[:] = a
+            img["tags"][(d, name)] = (nc, pa)
+            nbytes += pa.nbytes
+    img["nbytes"] = nbytes
+    return img
+
+
+def upload(img, lib):
+    from omega_h_b200 import Mesh
+    m = Mesh(img["dim"], lib=lib)
+    m.set_verts(img["nverts"])
+    for d, (pa, pc) in img["down"].items():
+        m.set_ents(d, pa, pc)
+    for (d, name), (nc, pa) in img["tags"].items():
+        m.add_tag(d, name, nc, pa, internal=True)
+    return m
+
+
+class Download:
+    """Reads the whole refined mesh (downward adjacencies + every tag) into reusable pinned buffers."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.bufs = {}
+
+    def buf(self, key, n, dtype):
+        b = self.bufs.get(key)
+        if b is None or b.size < n:
+            b = self.lib.pinned_empty(int(n * 1.05) + 16, dtype)
+            self.bufs[key] = b
+        return b
+
+    def __call__(self, m):
+        import numpy as np
+        from omega_h_b200 import simplex_degree
+        from omega_h_b200._lib import NP_OF
+        nbytes = 0
+        dim = m.dim()
+        for d in range(1, dim + 1):
+            n = m.nents(d) * simplex_degree(d, d - 1)
+            ob = self.buf(("down", d), n, np.int32)
+            oc = self.buf(("codes", d), n, np.int8) if d > 1 else None
+            m.ask_down(d, d - 1, out=ob, out_codes=oc)
+            nbytes += n * 4 + (n if d > 1 else 0)
+        for d in range(dim + 1):
+            for name, t, nc in m.tags(d):
+                n = m.nents(d) * nc
+                ob = self.buf(("tag", d, name), n, NP_OF[t])
+                m.get_array(d, name, out=ob)
+                nbytes += n * np.dtype(NP_OF[t]).itemsize
+        return nbytes
+
+
+def summarize_profile(recs):
+    agg = {}
+    for name, ms in recs:
+        parts = name.split("\t")
+        nm = parts[0]
+        b = int(parts[1]) if len(parts) > 1 else 0
+        a = agg.setdefault(nm, [0, 0.0, 0])
+        a[0] += 1
+        a[1] += ms
+        a[2] += b
+    return agg
+
+
+def main_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from omega_h_b200 import AdaptOpts, Lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = Lib(device=local_rank).init()
+    if lib.is_emulation:
+        raise SystemExit("bench.py refuses to run on the emulation build")
+
+    def barrier():
+        lib.sync()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    base = build_input(args.n, lib)
+    opts = AdaptOpts(base)
+    nelems0 = base.nelems()
+
+    if args.profile:
+        for _ in range(2):
+            m = base.copy()
+            run_loop(m, opts)
+        lib.sync()
+        m = base.copy()
+        lib.profile_begin(None)
+        lib.timer_start()
+        run_loop(m, opts)
+        total = lib.timer_stop()
+        agg = summarize_profile(lib.profile_end())
+        ksum = sum(v[1] for v in agg.values())
+        print("loop %.3f ms (profiled), kernels %.3f ms, %d launches" % (total, ksum, sum(v[0] for v in agg.values())),
+              file=sys.stderr)
+        for nm, (cnt, ms, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            gbs = (b / 1e9) / (ms / 1e3) if b and ms > 0 else 0.0
+            print("%-36s n=%4d %9.3f ms %5.1f%% %8.1f GB/s(algo)" % (nm, cnt, ms, 100 * ms / ksum, gbs), file=sys.stderr)
+        return 0
+
+    # ---- pick the dominant kernel (outside the timed region) --------------------------------
+    for _ in range(max(args.warmup, 3)):
+        m = base.copy()
+        run_loop(m, opts)
+    lib.sync()
+    m = base.copy()
+    lib.profile_begin(None)
+    run_loop(m, opts)
+    agg = summarize_profile(lib.profile_end())
+    top = max(agg.items(), key=lambda kv: kv[1][1])[0]
+    del m
+
+    # ---- timed region: device-resident input -----------------------------------------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.launch_count()
+    lib.profile_begin(top)
+    new_tets = 0
+    dev_ms = 0.0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        m = base.copy()
+        lib.timer_start()
+        npasses = run_loop(m, opts)
+        dev_ms += lib.timer_stop()
+        new_tets += m.nelems() - nelems0
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    top_recs = lib.profile_end()
+    launches = lib.launch_count() - launches0
+    clocks = sampler.stop()
+    nelems1 = m.nelems()
+    del m
+
+    if world > 1:
+        t = torch.tensor([dev_ms, float(new_tets)], device="cuda", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms_max = float(tmax[0])
+        total_new = float(tsum[1])
+    else:
+        dev_ms_max, total_new = dev_ms, float(new_tets)
+    value = total_new / (dev_ms_max / 1e3)
+
+    # roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    tagg = summarize_profile(top_recs)
+    cnt, tms, tbytes = tagg.get(top, (0, 0.0, 0))
+    achieved = (tbytes / 1e9) / (tms / 1e3) if tms > 0 and tbytes else None
+    roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "launches": cnt, "avg_ms": (tms / cnt) if cnt else None,
+                "share_of_step": (tms / dev_ms) if dev_ms > 0 else None,
+                "algorithmic_bytes_per_launch": (tbytes / cnt) if cnt else None}
+
+    # ---- end to end: host buffers in, host buffers out ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        img = host_copy_of(base, lib)
+        down = Download(lib)
+        for _ in range(2):
+            m = upload(img, lib)
+            run_loop(m, opts)
+            d2h_bytes = down(m)
+            del m
+        barrier()
+        t0 = time.perf_counter()
+        e_new = 0
+        for _ in range(args.steps):
+            m = upload(img, lib)
+            run_loop(m, opts)
+            d2h_bytes = down(m)
+            e_new += m.nelems() - nelems0
+            del m
+        barrier()
+        e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_s = float(t[0])
+            t2 = torch.tensor([float(e_new)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+            e_new = float(t2[0])
+        e2e = {"value": e_new / e_s, "unit": UNIT, "h2d_bytes_per_step": int(img["nbytes"]),
+               "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e_s * 1e3 / args.steps,
+               "timing": "wall clock around upload + loop + download, stream synchronised, max over ranks"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        s = reference_sample(args.n)
+        if s:
+            cpu = {k: s[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        cfg = workload_config(args.n)
+        cfg["parallelism"] = "1 GPU" if world == 1 else "%d independent replicas (one box per GPU, no ghost exchange yet)" % world
+        cfg["passes_per_step"] = npasses
+        cfg["tets_per_step"] = "%d -> %d" % (nelems0, nelems1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "wall_ms_per_step": wall_ms / args.steps, "syncs_per_step": None,
+            "peak_device_bytes": lib.peak_bytes(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -164,6 +164,20 @@ typedef struct oshb_pass_stats {
 } oshb_pass_stats;
 int oshb_last_pass_stats(oshb_pass_stats* out);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------
+ * CUDA-event timer and per-kernel event timing on the library's own stream
+ * (the reference's counterpart is the --osh-time call tree, src/Omega_h_profile.hpp:185-232). */
+int oshb_timer_start(void);
+int oshb_timer_stop(double* ms);
+/* filter NULL/"" = every named kernel, otherwise exactly that kernel name */
+int oshb_profile_begin(const char* filter);
+/* stops profiling and writes one "name\tms\n" line per launch, in launch order; call with
+ * buf=NULL to learn the size */
+int oshb_profile_end(char* buf, uint64_t cap, uint64_t* needed);
+/* pinned host buffers for callers that keep the mesh on the host (end-to-end path) */
+int oshb_host_alloc(uint64_t bytes, void** h_out);
+int oshb_host_free(void* h_ptr);
+
 #ifdef __cplusplus
 }
 #endif

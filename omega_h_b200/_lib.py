@@ -57,6 +57,8 @@ SYMBOLS = [
     "oshb_mesh_ask_lengths", "oshb_mesh_ask_qualities", "oshb_build_box",
     "oshb_adapt_opts_init", "oshb_refine_qualities", "oshb_mident_metrics", "oshb_find_indset",
     "oshb_rep_vertex2md_order", "oshb_refine_by_size", "oshb_last_pass_stats",
+    "oshb_timer_start", "oshb_timer_stop", "oshb_profile_begin", "oshb_profile_end", "oshb_host_alloc",
+    "oshb_host_free",
 ]
 
 
@@ -103,6 +105,42 @@ class Lib:
     def sync(self):
         self.check(self.c.oshb_sync())
 
+    # ---- measurement hooks --------------------------------------------------------------
+    def timer_start(self):
+        self.check(self.c.oshb_timer_start())
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self.check(self.c.oshb_timer_stop(C.byref(ms)))
+        return ms.value
+
+    def profile_begin(self, kernel_name=None):
+        self.check(self.c.oshb_profile_begin(kernel_name.encode() if kernel_name else None))
+
+    def profile_end(self):
+        """[(kernel name, milliseconds)] for every profiled launch, in launch order."""
+        need = C.c_uint64()
+        self.check(self.c.oshb_profile_end(None, C.c_uint64(0), C.byref(need)))
+        buf = C.create_string_buffer(int(need.value) + 16)
+        self.check(self.c.oshb_profile_end(buf, C.c_uint64(len(buf)), C.byref(need)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, ms = line.rsplit("\t", 1)
+            out.append((name, float(ms)))
+        return out
+
+    def pinned_empty(self, n, dtype):
+        """numpy array over cudaHostAlloc'd memory (kept alive by the returned array's base)."""
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n) * dtype.itemsize, 1)
+        p = C.c_void_p()
+        self.check(self.c.oshb_host_alloc(C.c_uint64(nbytes), C.byref(p)))
+        raw = (C.c_char * nbytes).from_address(p.value)
+        holder = _PinnedHolder(self, p, raw)
+        arr = np.frombuffer(raw, dtype=dtype, count=int(n))
+        _PINNED[id(arr)] = holder
+        return arr
+
     # ---- raw device buffers (used by the primitive-level tests) -------------------------
     def to_device(self, a):
         a = np.ascontiguousarray(a)
@@ -118,6 +156,16 @@ class Lib:
         nbytes = int(n) * dtype.itemsize
         self.check(self.c.oshb_dev_alloc(C.c_uint64(max(nbytes, 1)), C.byref(p)))
         return DevBuf(self, p, nbytes, dtype, int(n))
+
+
+_PINNED = {}
+
+
+class _PinnedHolder:
+    """Keeps a pinned allocation alive for the life of the process (bench buffers are few)."""
+
+    def __init__(self, lib, ptr, raw):
+        self.lib, self.ptr, self.raw = lib, ptr, raw
 
 
 class DevBuf:

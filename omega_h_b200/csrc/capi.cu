@@ -486,3 +486,86 @@ extern "C" int oshb_build_box(double x, double y, double z, int32_t nx, int32_t 
   *out = h;
   OSHB_CATCH
 }
+
+// ---- timing / profiling hooks for bench.py ------------------------------------------------------
+namespace oshb {
+void prof_set(bool on, char const* filter);
+void prof_clear();
+size_t prof_collect(std::vector<std::string>* names, std::vector<float>* ms);
+}
+#ifndef OSHB_EMU
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+#endif
+extern "C" {
+/* CUDA-event timer on the library's stream */
+int oshb_timer_start(void) {
+  OSHB_TRY
+#ifndef OSHB_EMU
+  init_ctx(-1);
+  if (!g_t0) {
+    OSHB_CUDA(cudaEventCreate(&g_t0));
+    OSHB_CUDA(cudaEventCreate(&g_t1));
+  }
+  OSHB_CUDA(cudaEventRecord(g_t0, ctx().stream));
+#endif
+  OSHB_CATCH
+}
+int oshb_timer_stop(double* ms) {
+  OSHB_TRY
+  *ms = 0;
+#ifndef OSHB_EMU
+  OSHB_CUDA(cudaEventRecord(g_t1, ctx().stream));
+  OSHB_CUDA(cudaEventSynchronize(g_t1));
+  float t = 0;
+  OSHB_CUDA(cudaEventElapsedTime(&t, g_t0, g_t1));
+  *ms = t;
+#endif
+  OSHB_CATCH
+}
+/* filter: NULL/"" = every named kernel, otherwise exactly that kernel name */
+int oshb_profile_begin(const char* filter) {
+  OSHB_TRY
+  prof_clear();
+  prof_set(true, filter);
+  OSHB_CATCH
+}
+/* stops profiling; writes "name\tms\n" lines (one per launch, launch order) into buf */
+int oshb_profile_end(char* buf, uint64_t cap, uint64_t* needed) {
+  OSHB_TRY
+  prof_set(false, nullptr);
+  std::vector<std::string> names;
+  std::vector<float> ms;
+  prof_collect(&names, &ms);
+  std::string out;
+  char tmp[64];
+  for (size_t i = 0; i < names.size(); ++i) {
+    snprintf(tmp, sizeof(tmp), "\t%.6f\n", double(ms[i]));
+    out += names[i];
+    out += tmp;
+  }
+  if (needed) *needed = out.size() + 1;
+  if (buf && cap > out.size()) memcpy(buf, out.c_str(), out.size() + 1);
+  if (buf && cap > out.size()) prof_clear();
+  OSHB_CATCH
+}
+/* pinned host memory for the end-to-end path (cudaHostAlloc) */
+int oshb_host_alloc(uint64_t bytes, void** h_out) {
+  OSHB_TRY
+#ifdef OSHB_EMU
+  *h_out = malloc(bytes ? bytes : 1);
+#else
+  init_ctx(-1);
+  OSHB_CUDA(cudaHostAlloc(h_out, bytes ? bytes : 1, cudaHostAllocDefault));
+#endif
+  OSHB_CATCH
+}
+int oshb_host_free(void* h_ptr) {
+  OSHB_TRY
+#ifdef OSHB_EMU
+  free(h_ptr);
+#else
+  OSHB_CUDA(cudaFreeHost(h_ptr));
+#endif
+  OSHB_CATCH
+}
+}

@@ -190,8 +190,10 @@ static void scan_launch(Tin const* in, int64_t n, Tacc* out) {
   dev_memset(static_cast<char*>(c.dscratch) + 4096, 0, size_t(ntiles) * 8);
   unsigned* ticket = static_cast<unsigned*>(c.dscratch);
   unsigned long long* desc = reinterpret_cast<unsigned long long*>(static_cast<char*>(c.dscratch) + 4096);
+  if (c.prof_on) prof_begin("offset_scan");
   k_scan<Tin, Tacc><<<unsigned(ntiles), SCAN_T, 0, c.stream>>>(in, out, n, desc, ticket);
   OSHB_CUDA(cudaGetLastError());
+  if (c.prof_on) prof_end("offset_scan");
   c.launches++;
 }
 

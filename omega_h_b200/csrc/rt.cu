@@ -16,6 +16,78 @@ std::string& last_error_string() { return g_last_error; }
   throw Error(full);
 }
 
+// ---- per-kernel event timing ------------------------------------------------------------
+struct ProfRec {
+  std::string name;
+#ifndef OSHB_EMU
+  cudaEvent_t a, b;
+#endif
+};
+static std::vector<ProfRec> g_prof;
+static std::string g_prof_filter;
+static std::vector<void*> g_event_pool;
+
+void prof_set(bool on, char const* filter) {
+  g_ctx.prof_on = on;
+  g_prof_filter = filter ? filter : "";
+}
+void prof_clear() {
+#ifndef OSHB_EMU
+  for (auto& r : g_prof) {
+    g_event_pool.push_back(r.a);
+    g_event_pool.push_back(r.b);
+  }
+#endif
+  g_prof.clear();
+}
+#ifdef OSHB_EMU
+void prof_begin(char const*) {}
+void prof_end(char const*) {}
+size_t prof_collect(std::vector<std::string>*, std::vector<float>*) { return 0; }
+#else
+static bool prof_match(char const* name) {
+  if (!name) return false;
+  return g_prof_filter.empty() || g_prof_filter == name;
+}
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = static_cast<cudaEvent_t>(g_event_pool.back());
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  OSHB_CUDA(cudaEventCreate(&e));
+  return e;
+}
+void prof_begin(char const* name) {
+  if (!prof_match(name)) {
+    g_ctx.next_bytes = 0;
+    return;
+  }
+  ProfRec r;
+  r.name = std::string(name) + "\t" + std::to_string(g_ctx.next_bytes);
+  g_ctx.next_bytes = 0;
+  r.a = get_event();
+  r.b = get_event();
+  OSHB_CUDA(cudaEventRecord(r.a, g_ctx.stream));
+  g_prof.push_back(r);
+}
+void prof_end(char const* name) {
+  if (!prof_match(name)) return;
+  OSHB_CUDA(cudaEventRecord(g_prof.back().b, g_ctx.stream));
+}
+size_t prof_collect(std::vector<std::string>* names, std::vector<float>* ms) {
+  OSHB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  for (auto& r : g_prof) {
+    float t = 0;
+    OSHB_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    names->push_back(r.name);
+    ms->push_back(t);
+  }
+  return g_prof.size();
+}
+#endif
+
 #ifdef OSHB_EMU
 
 void init_ctx(int) {

@@ -68,7 +68,9 @@ struct Ctx {
   int device = -1;
   int sms = 148;
   bool ready = false;
-  uint64_t launches = 0;    // kernels launched by this library (bench.py "gpu_launches")
+  bool prof_on = false;
+  int64_t next_bytes = 0;   // algorithmic bytes of the next launch (set by algo_bytes())
+  uint64_t launches = 0;   // kernels launched by this library (bench.py "gpu_launches")
   uint64_t syncs = 0;       // blocking scalar read-backs
   uint64_t alloc_bytes = 0; // live device bytes handed out
   uint64_t peak_bytes = 0;
@@ -77,6 +79,16 @@ struct Ctx {
   size_t dscratch_bytes = 0;
 };
 Ctx& ctx();
+// per-kernel timing with CUDA events on the launching stream (bench.py roofline leg):
+// prof_begin/prof_end bracket a launch when profiling is on and the name matches the filter
+void prof_begin(char const* name);
+void prof_end(char const* name);
+// declares the ALGORITHMIC bytes (compulsory reads + writes) of the next launch so
+// the profiler can report achieved GB/s per kernel; a no-op unless profiling is on
+inline void algo_bytes(int64_t bytes);
+inline void algo_bytes(int64_t bytes) {
+  if (ctx().prof_on) ctx().next_bytes = bytes;
+}
 void init_ctx(int device);  // idempotent; fails loudly when no CUDA device is usable
 void sync_stream();
 
@@ -174,9 +186,11 @@ void parallel_for(int64_t n, F f, char const* name = nullptr) {
   int64_t blocks = (n + 255) / 256;
   int64_t cap = int64_t(c.sms) * 16;
   if (blocks > cap) blocks = cap;
+  if (c.prof_on) prof_begin(name);
   k_for<<<unsigned(blocks), 256, 0, c.stream>>>(n, f);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) fail(__FILE__, __LINE__, std::string("kernel launch: ") + cudaGetErrorString(e));
+  if (c.prof_on) prof_end(name);
   c.launches++;
 }
 __device__ __forceinline__ LO atomic_add(LO* p, LO v) { return atomicAdd(p, v); }

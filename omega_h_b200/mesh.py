@@ -143,10 +143,16 @@ class Mesh:
     def has_tag(self, ent_dim, name):
         return any(t[0] == name for t in self.tags(ent_dim))
 
-    def get_array(self, ent_dim, name):
+    def get_array(self, ent_dim, name, out=None):
+        """Mesh::get_array; `out` may be a preallocated (e.g. pinned) host buffer of at least the tag's size."""
         for tname, ttype, nc in self.tags(ent_dim):
             if tname == name:
-                out = np.empty(self.nents(ent_dim) * nc, dtype=NP_OF[ttype])
+                n = self.nents(ent_dim) * nc
+                if out is None:
+                    out = np.empty(n, dtype=NP_OF[ttype])
+                else:
+                    assert out.dtype == NP_OF[ttype] and out.size >= n
+                    out = out[:n]
                 self.lib.check(self.lib.c.oshb_mesh_get_tag(self.h, C.c_int(ent_dim), name.encode(), _ptr(out), C.c_int(1)))
                 return out
         raise OshbError("get_array(%d, %s): doesn't exist" % (ent_dim, name))
@@ -158,10 +164,13 @@ class Mesh:
         return self.get_array(ent_dim, "global")
 
     # ---- adjacencies -----------------------------------------------------------------------
-    def ask_down(self, from_dim, to_dim):
+    def ask_down(self, from_dim, to_dim, out=None, out_codes=None):
         deg = simplex_degree(from_dim, to_dim)
-        ab2b = np.empty(self.nents(from_dim) * deg, dtype=np.int32)
-        codes = np.empty(ab2b.size, dtype=np.int8) if to_dim > 0 else None
+        n = self.nents(from_dim) * deg
+        ab2b = np.empty(n, dtype=np.int32) if out is None else out[:n]
+        codes = None
+        if to_dim > 0:
+            codes = np.empty(n, dtype=np.int8) if out_codes is None else out_codes[:n]
         self.lib.check(self.lib.c.oshb_mesh_ask_down(self.h, C.c_int(from_dim), C.c_int(to_dim), _ptr(ab2b),
                                                      _ptr(codes) if codes is not None else None, C.c_int(1)))
         return ab2b, codes
