@@ -323,6 +323,25 @@ def main_b200(args):
             m = base.copy()
             run_loop(m, opts)
         lib.sync()
+        import ctypes as C
+
+        def host_stats():
+            a, f, s_, n = C.c_double(), C.c_double(), C.c_double(), C.c_uint64()
+            lib.c.oshb_host_time_stats(C.byref(a), C.byref(f), C.byref(s_), C.byref(n))
+            return a.value, f.value, s_.value, n.value, lib.sync_count(), lib.launch_count()
+        # un-profiled loop with host-side accounting
+        m = base.copy()
+        h0 = host_stats()
+        t0 = time.perf_counter()
+        lib.timer_start()
+        run_loop(m, opts)
+        tot = lib.timer_stop()
+        t1 = time.perf_counter()
+        h1 = host_stats()
+        print("plain loop: %.3f ms device, %.3f ms wall; host time in alloc %.3f ms (%d allocs), free %.3f ms, "
+              "blocking read-backs %.3f ms (%d), launches %d" %
+              (tot, (t1 - t0) * 1e3, (h1[0] - h0[0]) * 1e3, h1[3] - h0[3], (h1[1] - h0[1]) * 1e3,
+               (h1[2] - h0[2]) * 1e3, h1[4] - h0[4], h1[5] - h0[5]), file=sys.stderr)
         m = base.copy()
         lib.profile_begin(None)
         lib.timer_start()

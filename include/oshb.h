@@ -175,6 +175,8 @@ int oshb_profile_begin(const char* filter);
  * buf=NULL to learn the size */
 int oshb_profile_end(char* buf, uint64_t cap, uint64_t* needed);
 /* pinned host buffers for callers that keep the mesh on the host (end-to-end path) */
+/* host seconds spent in cudaMallocAsync / cudaFreeAsync / blocking read-backs, allocation count */
+int oshb_host_time_stats(double* alloc_s, double* free_s, double* sync_s, uint64_t* nalloc);
 int oshb_host_alloc(uint64_t bytes, void** h_out);
 int oshb_host_free(void* h_ptr);
 

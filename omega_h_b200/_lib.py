@@ -58,7 +58,7 @@ SYMBOLS = [
     "oshb_adapt_opts_init", "oshb_refine_qualities", "oshb_mident_metrics", "oshb_find_indset",
     "oshb_rep_vertex2md_order", "oshb_refine_by_size", "oshb_last_pass_stats",
     "oshb_timer_start", "oshb_timer_stop", "oshb_profile_begin", "oshb_profile_end", "oshb_host_alloc",
-    "oshb_host_free",
+    "oshb_host_free", "oshb_host_time_stats",
 ]
 
 

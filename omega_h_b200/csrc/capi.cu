@@ -569,3 +569,13 @@ int oshb_host_free(void* h_ptr) {
   OSHB_CATCH
 }
 }
+
+/* host seconds spent inside cudaMallocAsync / cudaFreeAsync / blocking read-backs, and the
+ * number of allocations, since oshb_init (diagnostics for bench.py --profile) */
+extern "C" int oshb_host_time_stats(double* alloc_s, double* free_s, double* sync_s, uint64_t* nalloc) {
+  *alloc_s = ctx().host_s_alloc;
+  *free_s = ctx().host_s_free;
+  *sync_s = ctx().host_s_sync;
+  *nalloc = ctx().n_alloc;
+  return 0;
+}

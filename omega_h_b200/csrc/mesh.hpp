@@ -144,8 +144,6 @@ Reals refine_qualities(Mesh* mesh, LOs cands2edges);                // src/Omega
 // ---- refine pass (refine.cu) ------------------------------------------------------------
 Bytes find_indset(Mesh* mesh, int ent_dim, Reals quality, Bytes candidates, int* nrounds = nullptr);  // src/Omega_h_indset.cpp:27-34
 LOs get_rep2md_order_adapt(Mesh* mesh, int key_dim, int rep_dim, Bytes kds_are_keys);  // src/Omega_h_modify.cpp:269-281
-void refine_products(Mesh* mesh, int ent_dim, LOs keys2edges, LOs keys2midverts, LOs old_verts2new_verts,
-    LOs& keys2prods, LOs& prod_verts2verts);                        // src/Omega_h_refine_topology.cpp:186-203
 bool refine_by_size(Mesh* mesh, AdaptOpts const& opts);             // src/Omega_h_refine.cpp:92-100
 
 struct PassStats {

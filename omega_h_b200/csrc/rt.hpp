@@ -74,6 +74,8 @@ struct Ctx {
   uint64_t syncs = 0;       // blocking scalar read-backs
   uint64_t alloc_bytes = 0; // live device bytes handed out
   uint64_t peak_bytes = 0;
+  double host_s_alloc = 0, host_s_free = 0, host_s_sync = 0;  // host seconds spent in those calls
+  uint64_t n_alloc = 0;
   void* pinned = nullptr;   // 4 KB pinned staging for scalar read-backs
   void* dscratch = nullptr; // device scratch (scan tile descriptors, reduction cells)
   size_t dscratch_bytes = 0;

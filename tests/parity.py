@@ -160,7 +160,16 @@ def check_pass(fx, lib, rtol=RTOL, derived=True, stages=True):
     rep.eq("did", int(did), int(fx["did"][0]))
     if did and int(fx["did"][0]):
         compare_mesh(rep, m, fx, "out:", rtol)
+        check_seeded_adjacencies(rep, m, fx, lib)
     return rep, m
+
+
+def check_seeded_adjacencies(rep, m, fx, lib):
+    """The refine pass seeds entity->vertex tables of the new mesh instead of deriving them;
+    they must equal what a fresh mesh holding the REFERENCE's output derives by transit."""
+    fresh = mesh_from_fixture(fx, lib, prefix="out:")
+    for d in range(2, m.dim() + 1):
+        rep.eq("seeded verts_of%d" % d, m.ask_verts_of(d), fresh.ask_verts_of(d))
 
 
 def load(path):

@@ -32,3 +32,44 @@ def test_corner_trace(emu_lib, ref_driver, tmp_path):
         if int(fx["did"][0]):
             nkeys.append(last_pass_stats(emu_lib)["nkeys"])
     assert nkeys == [63, 195, 123, 184, 441, 261, 414, 813, 93]
+
+
+def test_chained_loop_from_build_box(emu_lib, ref_driver, tmp_path):
+    """build_box + our own loop (every pass consumes OUR previous output, including the seeded
+    adjacency cache) ends bit-identical to the reference's final mesh."""
+    import glob
+    import subprocess
+    import numpy as np
+    from omega_h_b200 import VERT, AdaptOpts, build_box, refine_by_size
+    n = 6
+    subprocess.run([ref_driver, "refine", "3", str(n), "0", "-1", str(tmp_path / "r")], check=True,
+                   stdout=subprocess.DEVNULL)
+    files = sorted(glob.glob(str(tmp_path / "r_pass*.oshd")), key=lambda s: int(s.split("_pass")[1].split(".")[0]))
+    m = build_box(1.0, 1.0, 1.0, n, n, n, lib=emu_lib)
+    h = 1.0 / n / 2.0
+    m.add_tag(VERT, "metric", 1, np.full(m.nverts(), 1.0 / (h * h)))
+    m.ask_lengths()
+    m.ask_qualities()
+    rep = parity.Report()
+    parity.compare_mesh(rep, m, parity.load(files[0]), "in:")
+    opts = AdaptOpts(m)
+    npass = 0
+    while refine_by_size(m, opts):
+        npass += 1
+    assert npass == len(files) - 1
+    parity.compare_mesh(rep, m, parity.load(files[-2]), "out:")
+    rep.assert_ok()
+
+
+@pytest.mark.parametrize("dim,n", [(2, 5), (3, 3)])
+def test_build_box_matches_reference(emu_lib, ref_driver, tmp_path, dim, n):
+    import subprocess
+    from omega_h_b200 import build_box
+    out = str(tmp_path / "box.oshd")
+    subprocess.run([ref_driver, "box", str(dim), str(n), out], check=True, stdout=subprocess.DEVNULL)
+    fx = parity.load(out)
+    m = build_box(1.0, 1.0, 1.0 if dim == 3 else 0.0, n, n, n if dim == 3 else 0, lib=emu_lib)
+    rep = parity.Report()
+    parity.compare_mesh(rep, m, fx, "in:")
+    parity.compare_derived(rep, m, fx)
+    rep.assert_ok()

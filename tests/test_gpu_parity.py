@@ -66,6 +66,66 @@ def test_chained_loop_matches_reference(gpu_lib, ref_driver, tmp_path):
     rep.assert_ok()
 
 
+@pytest.mark.parametrize("dim,n", [(2, 33), (3, 12)])
+def test_build_box_matches_reference(gpu_lib, ref_driver, tmp_path, dim, n):
+    """device build_box (find_unique -> radix sort_by_keys, reflect_down, Hilbert sort) vs the reference's"""
+    from omega_h_b200 import build_box
+    out = str(tmp_path / "box.oshd")
+    subprocess.run([ref_driver, "box", str(dim), str(n), out], check=True, stdout=subprocess.DEVNULL)
+    fx = parity.load(out)
+    m = build_box(1.0, 1.0, 1.0 if dim == 3 else 0.0, n, n, n if dim == 3 else 0, lib=gpu_lib)
+    rep = parity.Report()
+    parity.compare_mesh(rep, m, fx, "in:")
+    parity.compare_derived(rep, m, fx)
+    rep.assert_ok()
+
+
+def test_full_size_loop_properties(gpu_lib):
+    """BASELINE config[1] at full size (64^3): size-independent properties of the result --
+    exact doubling per pass, identity globals, Euler characteristic of a ball, every tet
+    positively oriented with quality in (0,1], downward adjacency consistent with vertices."""
+    import numpy as np
+    from omega_h_b200 import VERT, AdaptOpts, build_box, last_pass_stats, refine_by_size
+    n = 64
+    m = build_box(1.0, 1.0, 1.0, n, n, n, lib=gpu_lib)
+    h = 1.0 / n / 2.0
+    m.add_tag(VERT, "metric", 1, np.full(m.nverts(), 1.0 / (h * h)))
+    m.ask_lengths()
+    m.ask_qualities()
+    opts = AdaptOpts(m)
+    keys = []
+    counts = [m.nelems()]
+    while refine_by_size(m, opts):
+        keys.append(last_pass_stats(gpu_lib)["nkeys"])
+        counts.append(m.nelems())
+    assert keys == [262144, 798720, 811200, 2097152]  # SURVEY.md section 8 table, measured on the reference
+    assert counts == [1572864 * 2 ** i for i in range(5)]
+    nv, ne, nf, nr = (m.nents(d) for d in range(4))
+    assert (nv, ne, nf, nr) == (4243841, 29507968, 50429952, 25165824)
+    assert nv - ne + nf - nr == 1
+    for d in range(4):
+        assert np.array_equal(m.globals(d), np.arange(m.nents(d), dtype=np.int64))
+    q = m.get_array(3, "quality")
+    assert q.min() > 0.2 and q.max() <= 1.0 + 1e-12
+    lengths = m.get_array(1, "length")
+    assert lengths.max() <= np.sqrt(2.0) * (1 + 1e-12)
+    # volumes: positive orientation and total volume of the unit cube
+    rv = m.ask_verts_of(3).reshape(-1, 4)
+    x = m.coords().reshape(-1, 3)
+    b = x[rv[:, 1:]] - x[rv[:, :1]]
+    vol = np.einsum("ij,ij->i", np.cross(b[:, 0], b[:, 1]), b[:, 2]) / 6.0
+    assert vol.min() > 0
+    assert abs(vol.sum() - 1.0) < 1e-9
+    # every stored face of a tet is made of that tet's vertices
+    rf, _ = m.ask_down(3, 2)
+    fv = m.ask_verts_of(2).reshape(-1, 3)
+    tet_sets = np.sort(rv, axis=1)
+    for k in range(4):
+        fset = np.sort(fv[rf.reshape(-1, 4)[:, k]], axis=1)
+        inside = (fset[:, :, None] == tet_sets[:, None, :]).any(axis=2).all(axis=1)
+        assert inside.all()
+
+
 # ---- array primitives against numpy -----------------------------------------------------------
 @pytest.mark.parametrize("n", [0, 1, 31, 4096, 4097, 1_000_003, 20_000_000])
 @pytest.mark.parametrize("dtype", [np.int8, np.int32])
