@@ -1,0 +1,741 @@
+// The rebuild half of a refine pass: product topology, new numbering, new connectivity,
+// new globals, field transfer (src/Omega_h_refine.cpp:43-82, Omega_h_refine_topology.cpp,
+// Omega_h_modify.cpp:20-70,141-243,347-517, Omega_h_transfer.cpp:150-428;
+// SURVEY.md section 8a rows a19-a24).
+//
+// Device-first restructuring relative to the reference (results identical, checked
+// bit-for-bit against fixtures of the reference):
+//  * numbering first: for every dimension one scan of the representative counts gives
+//    old->new for surviving entities and, per key, the new index / new global of its first
+//    product (assign_new_numbering, modify.cpp:347-404);
+//  * ONE FUSED STREAMING KERNEL PER DIMENSION over the OLD entities copies everything a
+//    surviving entity keeps: remapped downward row, codes, entity->vertex row, global id and
+//    every transferable tag (no compaction into "same" index lists, no per-tag launches);
+//  * PRODUCTS ARE BUILT PER CAVITY DOMAIN: one thread per key edge (midpoint vertex + the two
+//    halves), one per (key, adjacent triangle) (cut edge + two pair triangles) and one per
+//    (key, adjacent tet) (cut triangle + two pair tets). Each derives analytically
+//      - vertices              (refine_domains_to_pairs/_cuts, refine_topology.cpp:13-203)
+//      - downward entities AND alignment codes: every bounding entity of a product is either
+//        another product of the same key or an old entity of the split domain, so the
+//        reference's reflect_down search (form_uses + find_matches, 58 % of its time) becomes
+//        index arithmetic on the key's cavity
+//      - new local index, new global id, inherited classification
+//    so pairs/cuts/combine temporaries, use lists, hash or sort joins never exist;
+//  * the new mesh's entity->vertex tables (F->V, R->V) are written by the same kernels and
+//    seeded into its adjacency cache (they equal what transit would derive).
+#include "mesh.hpp"
+
+namespace oshb {
+
+// ---------------------------------------------------------------------------------------
+// tag tables handed to the fused kernels
+// ---------------------------------------------------------------------------------------
+struct TagCopy {
+  void const* src;     // old array of this dimension
+  void const* src_up;  // old array of the next dimension (inheritance source of cuts)
+  void* dst;           // new array of this dimension
+  int bytes;           // bytes per entity (element size * ncomps)
+};
+struct TagTable {
+  int n;
+  TagCopy t[8];
+};
+
+OSHB_HD void copy_ent(void* dst, int64_t di, void const* src, int64_t si, int bytes) {
+  if (bytes == 1) {
+    static_cast<I8*>(dst)[di] = static_cast<I8 const*>(src)[si];
+  } else if (bytes == 4) {
+    static_cast<LO*>(dst)[di] = static_cast<LO const*>(src)[si];
+  } else if (bytes == 8) {
+    static_cast<GO*>(dst)[di] = static_cast<GO const*>(src)[si];
+  } else if ((bytes & 7) == 0) {
+    int n = bytes >> 3;
+    for (int k = 0; k < n; ++k) static_cast<GO*>(dst)[di * n + k] = static_cast<GO const*>(src)[si * n + k];
+  } else if ((bytes & 3) == 0) {
+    int n = bytes >> 2;
+    for (int k = 0; k < n; ++k) static_cast<LO*>(dst)[di * n + k] = static_cast<LO const*>(src)[si * n + k];
+  } else {
+    for (int k = 0; k < bytes; ++k) static_cast<I8*>(dst)[di * bytes + k] = static_cast<I8 const*>(src)[si * bytes + k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-key cavity view used by the product kernels (plain pointers, captured by value)
+// ---------------------------------------------------------------------------------------
+struct Topo {
+  int dim;
+  LO const* k2e;
+  LO const* ev2v;
+  LO const* ef_off;  // E->F upward
+  LO const* ef_ents;
+  I8 const* ef_codes;
+  LO const* er_off;  // E->R upward (3-D)
+  LO const* er_ents;
+  I8 const* er_codes;
+  LO const* fe2e;  // stored F->E
+  I8 const* fe_codes;
+  LO const* fv2v;
+  LO const* rf2f;  // stored R->F (3-D)
+  I8 const* rf_codes;
+  LO const* rv2v;
+  LO const* re2e;  // derived R->E (3-D)
+  I8 const* re_codes;
+  LO const* o2n[4];    // old entity -> new entity (-1 dead), per dimension
+  LO const* pbase[4];  // key -> new index of its first product, per dimension
+  GO const* gbase[4];  // key -> new global of its first product, per dimension
+  // outputs
+  LO* nd[4];   // new downward rows
+  I8* nc[4];   // new codes
+  LO* nvo[4];  // new entity -> vertices (dims 2, 3)
+  GO* ng[4];   // new globals
+};
+
+OSHB_HD int find_in_row(LO const* row, LO n, LO what) {
+  for (LO i = 0; i < n; ++i)
+    if (row[i] == what) return int(i);
+  return -1;
+}
+
+// one product TRIANGLE: t < 2*nf: pair (face t/2, endpoint t%2 removed); else cut of tet t-2*nf.
+// Emits vertices and the three bounding edges with codes.
+OSHB_HD void product_tri(Topo const& tp, LO key, LO t, LO* verts, LO* lows, I8* codes) {
+  LO e = tp.k2e[key];
+  LO M = tp.pbase[0][key];
+  LO fb = tp.ef_off[e];
+  LO nf = tp.ef_off[e + 1] - fb;
+  LO pb1 = tp.pbase[1][key];
+  LO const* ov2nv = tp.o2n[0];
+  LO const* oe2ne = tp.o2n[1];
+  if (t < 2 * nf) {
+    int i = int(t >> 1), eev = int(t & 1);
+    LO f = tp.ef_ents[fb + i];
+    I8 code = tp.ef_codes[fb + i];
+    int dde = code_which_down(code);
+    int rot = code_rotation(code);
+    int dev = eev ^ rot;
+    int ddv = simplex_down_template(2, EDGE, dde, dev);  // face-local index of the removed key endpoint
+    int dds = simplex_opposite_template(2, VERT, ddv);   // face-local edge that survives
+    int l0 = dds, l1 = (dds + 1) % 3;
+    verts[0] = ov2nv[tp.fv2v[int64_t(f) * 3 + l0]];
+    verts[1] = ov2nv[tp.fv2v[int64_t(f) * 3 + l1]];
+    verts[2] = M;
+    int tipl = simplex_opposite_template(2, EDGE, dde);
+    bool x0_is_tip = (l0 == tipl);
+    lows[0] = oe2ne[tp.fe2e[int64_t(f) * 3 + dds]];
+    codes[0] = tp.fe_codes[int64_t(f) * 3 + dds];
+    LO cut = pb1 + 2 + i;
+    LO half = pb1 + (eev == 0 ? 1 : 0);  // the half of the key that keeps the other endpoint
+    if (!x0_is_tip) {
+      // e1 = (tip, M) is the cut edge stored (tip, M); e2 = (M, K)
+      lows[1] = cut;
+      codes[1] = make_code(false, 0, 0);
+      lows[2] = half;
+      codes[2] = make_code(false, (eev == 1) ? 1 : 0, 0);
+    } else {
+      // e1 = (K, M); e2 = (M, tip)
+      lows[1] = half;
+      codes[1] = make_code(false, (eev == 1) ? 0 : 1, 0);
+      lows[2] = cut;
+      codes[2] = make_code(false, 1, 0);
+    }
+  } else {
+    LO j = t - 2 * nf;
+    LO er = tp.er_off[e] + j;
+    LO r = tp.er_ents[er];
+    int rre = code_which_down(tp.er_codes[er]);
+    int ddt = simplex_opposite_template(3, EDGE, rre);  // the tip edge
+    int pl = simplex_down_template(3, EDGE, ddt, 0);
+    int ql = simplex_down_template(3, EDGE, ddt, 1);
+    verts[0] = ov2nv[tp.rv2v[int64_t(r) * 4 + pl]];
+    verts[1] = ov2nv[tp.rv2v[int64_t(r) * 4 + ql]];
+    verts[2] = M;
+    lows[0] = oe2ne[tp.re2e[int64_t(r) * 6 + ddt]];
+    codes[0] = tp.re_codes[int64_t(r) * 6 + ddt];
+    // the face through (key, q) is the tet face opposite p, and vice versa
+    LO Fq = tp.rf2f[int64_t(r) * 4 + simplex_opposite_template(3, VERT, pl)];
+    LO Fp = tp.rf2f[int64_t(r) * 4 + simplex_opposite_template(3, VERT, ql)];
+    int iq = find_in_row(tp.ef_ents + fb, nf, Fq);
+    int ip = find_in_row(tp.ef_ents + fb, nf, Fp);
+    lows[1] = pb1 + 2 + iq;  // (q, M) against stored (q, M)
+    codes[1] = make_code(false, 0, 0);
+    lows[2] = pb1 + 2 + ip;  // (M, p) against stored (p, M)
+    codes[2] = make_code(false, 1, 0);
+  }
+}
+
+// one product TET: pair (tet j, endpoint eev removed). Emits vertices and the four bounding
+// triangles with codes.
+OSHB_HD void product_tet(Topo const& tp, LO key, int j, int eev, LO* verts, LO* lows, I8* codes) {
+  LO e = tp.k2e[key];
+  LO M = tp.pbase[0][key];
+  LO fb = tp.ef_off[e];
+  LO nf = tp.ef_off[e + 1] - fb;
+  LO pb2 = tp.pbase[2][key];
+  LO const* ov2nv = tp.o2n[0];
+  LO er = tp.er_off[e] + j;
+  LO r = tp.er_ents[er];
+  I8 code = tp.er_codes[er];
+  int rre = code_which_down(code);
+  int rot = code_rotation(code);
+  int dev = eev ^ rot;
+  int ddv = simplex_down_template(3, EDGE, rre, dev);     // tet-local index of the removed endpoint
+  int Kl = simplex_down_template(3, EDGE, rre, 1 - dev);  // tet-local index of the kept endpoint
+  int dds = simplex_opposite_template(3, VERT, ddv);      // the old face that survives
+  int l[3];
+  LO x[3];
+  for (int k = 0; k < 3; ++k) {
+    l[k] = simplex_down_template(3, FACE, dds, k);
+    x[k] = tp.rv2v[int64_t(r) * 4 + l[k]];
+  }
+  // flip_new_elem: (x0, x1, x2, M) -> (x0, x2, x1, M)
+  verts[0] = ov2nv[x[0]];
+  verts[1] = ov2nv[x[2]];
+  verts[2] = ov2nv[x[1]];
+  verts[3] = M;
+  // face 0 of the new tet = (y0,y2,y1) = (x0,x1,x2): the old face, same use order as before
+  lows[0] = tp.o2n[2][tp.rf2f[int64_t(r) * 4 + dds]];
+  codes[0] = tp.rf_codes[int64_t(r) * 4 + dds];
+  int ddt = simplex_opposite_template(3, EDGE, rre);
+  int pl = simplex_down_template(3, EDGE, ddt, 0);
+  int ql = simplex_down_template(3, EDGE, ddt, 1);
+  // faces 1..3 in template order: (y0,y1,M) (y1,y2,M) (y2,y0,M) with y = (x0,x2,x1)
+  int const ya[3] = {0, 2, 1};
+  for (int k = 0; k < 3; ++k) {
+    int la = l[ya[k]];
+    int lb = l[ya[(k + 1) % 3]];
+    LO ua = x[ya[k]];  // old id of the use's first vertex
+    if (la != Kl && lb != Kl) {
+      // the tip edge + M: the cut triangle of this tet, stored (p, q, M)
+      lows[1 + k] = pb2 + 2 * nf + j;
+      codes[1 + k] = (la == pl) ? make_code(false, 0, 0) : make_code(true, 2, 0);
+    } else {
+      int tl = (la == Kl) ? lb : la;     // the tip in this face
+      int other = (tl == pl) ? ql : pl;  // the other tip
+      LO F = tp.rf2f[int64_t(r) * 4 + simplex_opposite_template(3, VERT, other)];
+      int i = find_in_row(tp.ef_ents + fb, nf, F);
+      lows[1 + k] = pb2 + 2 * i + eev;
+      // stored vertices of that pair triangle: surviving edge of face i in face order, then M
+      I8 fcode = tp.ef_codes[fb + i];
+      int fdev = eev ^ code_rotation(fcode);
+      int fddv = simplex_down_template(2, EDGE, code_which_down(fcode), fdev);
+      int fdds = simplex_opposite_template(2, VERT, fddv);
+      LO s0 = tp.fv2v[int64_t(F) * 3 + fdds];
+      codes[1 + k] = (s0 == ua) ? make_code(false, 0, 0) : make_code(true, 2, 0);
+    }
+  }
+}
+
+// should_inherit (src/Omega_h_transfer.cpp:20-34): class_id / class_dim present with the
+// same type and width on every dimension
+static bool should_inherit(Mesh* mesh, Tag const& tag) {
+  if (!(tag.name == "class_id" || tag.name == "class_dim" || tag.name == "momentum_velocity_fixed")) return false;
+  for (int i = 0; i <= mesh->dim(); ++i) {
+    Tag const* t = mesh->find_tag(i, tag.name);
+    if (!t || t->type != tag.type || t->ncomps != tag.ncomps) return false;
+  }
+  return true;
+}
+
+static Tag alloc_like(Tag const& tag, int64_t nents) {
+  Tag nt;
+  nt.name = tag.name;
+  nt.type = tag.type;
+  nt.ncomps = tag.ncomps;
+  int64_t n = nents * tag.ncomps;
+  switch (tag.type) {
+    case TAG_I8:
+      nt.i8 = Bytes(n);
+      break;
+    case TAG_I32:
+      nt.i32 = LOs(n);
+      break;
+    case TAG_I64:
+      nt.i64 = GOs(n);
+      break;
+    default:
+      nt.f64 = Reals(n);
+      break;
+  }
+  return nt;
+}
+
+template <class T>
+static void scatter_by(T const* data, T* new_data, LO const* index, LO n, int ncomps) {
+  parallel_for(int64_t(n) * ncomps, OSHB_LAMBDA(LO i) {
+    LO p = i / ncomps;
+    int c = i - p * ncomps;
+    new_data[int64_t(index[p]) * ncomps + c] = data[i];
+  }, "transfer(prods)");
+}
+
+// pair index -> key: count the keys whose range starts at each pair, prefix sum
+static LOs pair2key(LOs k_off, LO nkeys, LO npairs) {
+  LO const* ko = k_off.data();
+  // a key without pairs (cannot happen for faces; boundary-free for tets) would share its
+  // offset with the next key: count every key whose range starts here
+  LOs cnt = filled<LO>(npairs + 1, 0);
+  LO* cp = cnt.data();
+  parallel_for(nkeys, OSHB_LAMBDA(LO key) { atomic_add(&cp[ko[key]], 1); }, "pair2key(heads)");
+  LOs map(npairs + 2);
+  scan_offsets(cnt.data(), npairs + 1, map.data());
+  return map;  // key of pair p = map[p + 1] - 1
+}
+
+// ---------------------------------------------------------------------------------------
+// refine_element_based
+// ---------------------------------------------------------------------------------------
+void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_order, PassStats* stats) {
+  int const dim = mesh->dim();
+  LO const nkeys = LO(keys2edges.size());
+  LO const* k2e = keys2edges.data();
+  Mesh new_mesh = mesh->copy_meta();
+  LOs ev2v_old = mesh->ask_verts_of(EDGE);
+  LO const* ev2v = ev2v_old.data();
+  Adj e2f = mesh->ask_up(EDGE, FACE);
+  Adj e2r;
+  Adj f2e = mesh->ask_down(FACE, EDGE);
+  LOs fv2v = mesh->ask_verts_of(FACE);
+  Adj r2f, r2e;
+  LOs rv2v;
+  if (dim == 3) {
+    e2r = mesh->ask_up(EDGE, REGION);
+    r2f = mesh->ask_down(REGION, FACE);
+    r2e = mesh->ask_down(REGION, EDGE);
+    rv2v = mesh->ask_verts_of(REGION);
+  }
+  Topo tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.dim = dim;
+  tp.k2e = k2e;
+  tp.ev2v = ev2v;
+  tp.ef_off = e2f.a2ab.data();
+  tp.ef_ents = e2f.ab2b.data();
+  tp.ef_codes = e2f.codes.data();
+  tp.fe2e = f2e.ab2b.data();
+  tp.fe_codes = f2e.codes.data();
+  tp.fv2v = fv2v.data();
+  if (dim == 3) {
+    tp.er_off = e2r.a2ab.data();
+    tp.er_ents = e2r.ab2b.data();
+    tp.er_codes = e2r.codes.data();
+    tp.rf2f = r2f.ab2b.data();
+    tp.rf_codes = r2f.codes.data();
+    tp.rv2v = rv2v.data();
+    tp.re2e = r2e.ab2b.data();
+    tp.re_codes = r2e.codes.data();
+  }
+  LO const* ef_off = tp.ef_off;
+  LO const* er_off = tp.er_off;
+
+  // ---- key -> (key, face) and (key, tet) pair ranges --------------------------------------
+  LOs kf_off(nkeys + 1), kr_off;
+  {
+    LOs nf(nkeys);
+    LO* p = nf.data();
+    parallel_for(nkeys, OSHB_LAMBDA(LO key) { p[key] = ef_off[k2e[key] + 1] - ef_off[k2e[key]]; }, "key_degrees");
+    scan_offsets(nf.data(), nkeys, kf_off.data());
+    if (dim == 3) {
+      kr_off = LOs(nkeys + 1);
+      parallel_for(nkeys, OSHB_LAMBDA(LO key) { p[key] = er_off[k2e[key] + 1] - er_off[k2e[key]]; }, "key_degrees");
+      scan_offsets(nf.data(), nkeys, kr_off.data());
+    }
+  }
+  LO const nkf = last_of(kf_off);
+  LO const nkr = (dim == 3) ? last_of(kr_off) : 0;
+  LO const* kfo = kf_off.data();
+  LO const* kro = (dim == 3) ? kr_off.data() : nullptr;
+  LOs kf2key = pair2key(kf_off, nkeys, nkf);
+  LOs kr2key;
+  if (dim == 3) kr2key = pair2key(kr_off, nkeys, nkr);
+
+  // ---- numbering of every dimension ---------------------------------------------------------
+  LOs old2new[4], pbase[4], offsets_keep[4];
+  GOs gbase[4], new_globals[4], lin_globals_keep[4];
+  LO nnew[4] = {0, 0, 0, 0};
+  for (int ent_dim = 0; ent_dim <= dim; ++ent_dim) {
+    LO const nold = mesh->nents(ent_dim);
+    // representative counts: 1 for surviving entities, the key's product count on each key's
+    // representative (get_mods2reps / get_rep_counts, src/Omega_h_modify.cpp:141-243)
+    LOs rep_counts(nold);
+    LO* rc = rep_counts.data();
+    Adj const& e2d = (ent_dim == FACE) ? e2f : e2r;  // EDGE -> ent_dim upward (ent_dim >= 2)
+    LO const* d_off = (ent_dim >= FACE) ? e2d.a2ab.data() : nullptr;
+    LO const* d_ents = (ent_dim >= FACE) ? e2d.ab2b.data() : nullptr;
+    Bytes dead;
+    if (ent_dim >= EDGE) dead = Bytes(nold);
+    I8* dd = dead.exists() ? dead.data() : nullptr;
+    parallel_for(nold, OSHB_LAMBDA(LO i) {
+      rc[i] = 1;
+      if (dd) dd[i] = 0;
+    }, "rep_counts(init)");
+    if (ent_dim == VERT) {
+      parallel_for(nkeys, OSHB_LAMBDA(LO key) { atomic_add(&rc[ev2v[int64_t(k2e[key]) * 2]], 1); }, "rep_counts(vert)");
+    } else if (ent_dim == EDGE) {
+      parallel_for(nkeys, OSHB_LAMBDA(LO key) {
+        LO e = k2e[key];
+        rc[e] = 2 + (ef_off[e + 1] - ef_off[e]);
+        dd[e] = 1;
+      }, "rep_counts(edge)");
+    } else {
+      // all entities around a key die; the first one represents the key's products.
+      // two launches so that the dead representative ends with nprods, not 0.
+      parallel_for(nkeys, OSHB_LAMBDA(LO key) {
+        LO e = k2e[key];
+        for (LO ed = d_off[e]; ed < d_off[e + 1]; ++ed) {
+          rc[d_ents[ed]] = 0;
+          dd[d_ents[ed]] = 1;
+        }
+      }, "rep_counts(dead)");
+      parallel_for(nkeys, OSHB_LAMBDA(LO key) {
+        LO e = k2e[key];
+        LO nf = ef_off[e + 1] - ef_off[e];
+        LO nr = er_off ? (er_off[e + 1] - er_off[e]) : 0;
+        rc[d_ents[d_off[e]]] = (ent_dim == FACE) ? (2 * nf + nr) : (2 * nr);
+      }, "rep_counts(rep)");
+    }
+    LOs offsets = offset_scan(rep_counts);
+    rep_counts.reset();
+    LO const* off = offsets.data();
+    nnew[ent_dim] = last_of(offsets);
+    old2new[ent_dim] = LOs(nold);
+    LO* o2n = old2new[ent_dim].data();
+    // globals of the old entities on the linear partition (modify_globals,
+    // src/Omega_h_modify.cpp:406-444); one rank: exchange = identity, rescan = exclusive scan
+    GOs old_globals = mesh->globals(ent_dim);
+    GO const* og = old_globals.data();
+    GOs lin_globals(int64_t(nold) + 1);
+    {
+      LOs lin_counts(nold);
+      LO* lc = lin_counts.data();
+      parallel_for(nold, OSHB_LAMBDA(LO e) {
+        o2n[e] = (dd && dd[e]) ? -1 : off[e];
+        lc[og[e]] = off[e + 1] - off[e];
+      }, "old2new+to_lin");
+      scan_offsets(lin_counts.data(), nold, lin_globals.data());
+    }
+    GO const* lg = lin_globals.data();
+    pbase[ent_dim] = LOs(nkeys);
+    gbase[ent_dim] = GOs(nkeys);
+    LO* pb = pbase[ent_dim].data();
+    GO* gb = gbase[ent_dim].data();
+    LO const* kord = keys_order.data();
+    LO const* eord = edge_order.data();
+    parallel_for(nkeys, OSHB_LAMBDA(LO key) {
+      LO e = k2e[key];
+      if (ent_dim == VERT) {
+        LO rep = ev2v[int64_t(e) * 2];
+        pb[key] = off[rep] + kord[key] + 1;
+        gb[key] = lg[og[rep]] + eord[e] + 1;
+      } else {
+        LO rep = (ent_dim == EDGE) ? e : d_ents[d_off[e]];
+        pb[key] = off[rep];
+        gb[key] = lg[og[rep]];
+      }
+    }, "prod_bases");
+    new_globals[ent_dim] = GOs(nnew[ent_dim]);
+    lin_globals_keep[ent_dim] = lin_globals;
+    tp.o2n[ent_dim] = o2n;
+    tp.pbase[ent_dim] = pb;
+    tp.gbase[ent_dim] = gb;
+    tp.ng[ent_dim] = new_globals[ent_dim].data();
+    stats->nents_after[ent_dim] = nnew[ent_dim];
+  }
+  new_mesh.set_verts(nnew[0]);
+
+  // ---- new arrays + tag tables ----------------------------------------------------------------
+  LOs new_down[4], new_vo[4];
+  Bytes new_codes[4];
+  std::vector<Tag> new_tags[4];
+  TagTable same_tab[4], inh_tab[4];
+  struct Special {
+    int kind;  // 1 coords-like, 2 metric, 3 length, 4 quality
+    Tag old_tag;
+    size_t new_index;
+  };
+  std::vector<Special> specials[4];
+  std::vector<std::pair<Tag, size_t>> overflow[4];  // tags that did not fit the fused table
+  for (int d = 0; d <= dim; ++d) {
+    same_tab[d].n = 0;
+    inh_tab[d].n = 0;
+    if (d >= 1) {
+      int deg = simplex_degree(d, d - 1);
+      new_down[d] = LOs(int64_t(nnew[d]) * deg);
+      tp.nd[d] = new_down[d].data();
+      if (d >= 2) {
+        new_codes[d] = Bytes(int64_t(nnew[d]) * deg);
+        tp.nc[d] = new_codes[d].data();
+        new_vo[d] = LOs(int64_t(nnew[d]) * (d + 1));
+        tp.nvo[d] = new_vo[d].data();
+      }
+    }
+    for (auto const& tag : mesh->tags_[d]) {
+      int kind = -1;
+      bool inherit = should_inherit(mesh, tag);
+      if (inherit) kind = 0;
+      else if (d == VERT && tag.type == TAG_F64 && (tag.name == "coordinates" || tag.name == "warp")) kind = 1;
+      else if (d == VERT && tag.type == TAG_F64 && (tag.name == "metric" || tag.name == "target_metric") &&
+               (tag.ncomps == 1 || tag.ncomps == (dim * (dim + 1)) / 2)) kind = 2;
+      else if (d == EDGE && tag.type == TAG_F64 && tag.name == "length" && tag.ncomps == 1) kind = 3;
+      else if (d == dim && tag.type == TAG_F64 && tag.name == "quality" && tag.ncomps == 1) kind = 4;
+      if (kind < 0) continue;  // "global" is rebuilt; tags without a transfer rule are dropped
+      Tag nt = alloc_like(tag, nnew[d]);
+      new_tags[d].push_back(nt);
+      TagCopy tc;
+      tc.src = tag.data();
+      tc.src_up = nullptr;
+      tc.dst = nt.data();
+      tc.bytes = Tag::elem_bytes(tag.type) * tag.ncomps;
+      if (inherit && d < dim) tc.src_up = mesh->find_tag(d + 1, tag.name)->data();
+      if (same_tab[d].n < 8) {
+        same_tab[d].t[same_tab[d].n++] = tc;
+      } else {
+        overflow[d].push_back(std::make_pair(tag, new_tags[d].size() - 1));
+      }
+      if (inherit) {
+        OSHB_CHECK(inh_tab[d].n < 8);
+        inh_tab[d].t[inh_tab[d].n++] = tc;
+      } else {
+        Special s;
+        s.kind = kind;
+        s.old_tag = tag;
+        s.new_index = new_tags[d].size() - 1;
+        specials[d].push_back(s);
+      }
+    }
+  }
+
+  // ---- surviving entities: one fused streaming kernel per dimension ----------------------------
+  for (int d = 0; d <= dim; ++d) {
+    LO const nold = mesh->nents(d);
+    int const deg = (d >= 1) ? simplex_degree(d, d - 1) : 0;
+    int const nv = d + 1;
+    Adj old_down;
+    if (d >= 1) old_down = mesh->ask_down(d, d - 1);
+    LO const* od = (d >= 1) ? old_down.ab2b.data() : nullptr;
+    I8 const* oc = (d >= 2) ? old_down.codes.data() : nullptr;
+    LO const* ovo = (d == FACE) ? tp.fv2v : ((d == REGION) ? tp.rv2v : nullptr);
+    LO const* o2n = tp.o2n[d];
+    LO const* ol2nl = (d >= 1) ? tp.o2n[d - 1] : nullptr;
+    LO const* ov2nv = tp.o2n[0];
+    LO* nd = tp.nd[d];
+    I8* nc = tp.nc[d];
+    LO* nvo = tp.nvo[d];
+    GO* ng = tp.ng[d];
+    GO const* og = mesh->globals(d).data();
+    GOs lgk = lin_globals_keep[d];
+    GO const* lg = lgk.data();
+    TagTable const tab = same_tab[d];
+    int64_t tag_bytes = 0;
+    for (int k = 0; k < tab.n; ++k) tag_bytes += tab.t[k].bytes;
+    algo_bytes(int64_t(nold) * (4 + 16 + deg * 8 + (d >= 2 ? deg * 2 + nv * 8 : 0) + 2 * tag_bytes));
+    parallel_for(nold, OSHB_LAMBDA(LO e) {
+      LO ne = o2n[e];
+      if (ne < 0) return;
+      ng[ne] = lg[og[e]];
+      for (int k = 0; k < deg; ++k) {
+        nd[int64_t(ne) * deg + k] = ol2nl[od[int64_t(e) * deg + k]];
+        if (nc) nc[int64_t(ne) * deg + k] = oc[int64_t(e) * deg + k];
+      }
+      if (nvo)
+        for (int k = 0; k < nv; ++k) nvo[int64_t(ne) * nv + k] = ov2nv[ovo[int64_t(e) * nv + k]];
+      for (int k = 0; k < tab.n; ++k) copy_ent(tab.t[k].dst, ne, tab.t[k].src, e, tab.t[k].bytes);
+    }, "same_entities");
+    for (auto const& ov : overflow[d]) {
+      Tag const& ot = ov.first;
+      Tag& nt = new_tags[d][ov.second];
+      void const* src = ot.data();
+      void* dst = nt.data();
+      int bytes = Tag::elem_bytes(ot.type) * ot.ncomps;
+      parallel_for(nold, OSHB_LAMBDA(LO e) {
+        LO ne = o2n[e];
+        if (ne >= 0) copy_ent(dst, ne, src, e, bytes);
+      }, "same_entities(overflow)");
+    }
+  }
+
+  // ---- products ------------------------------------------------------------------------------------
+  Topo const t2 = tp;
+  TagTable const it0 = inh_tab[0], it1 = inh_tab[1], it2 = inh_tab[2], it3 = inh_tab[3];
+  // per key: midpoint vertex + the two halves of the key edge
+  parallel_for(nkeys, OSHB_LAMBDA(LO key) {
+    LO e = t2.k2e[key];
+    LO M = t2.pbase[0][key];
+    t2.ng[0][M] = t2.gbase[0][key];
+    for (int k = 0; k < it0.n; ++k) copy_ent(it0.t[k].dst, M, it0.t[k].src_up, e, it0.t[k].bytes);
+    LO pb1 = t2.pbase[1][key];
+    GO gb1 = t2.gbase[1][key];
+    t2.nd[1][int64_t(pb1) * 2 + 0] = t2.o2n[0][t2.ev2v[int64_t(e) * 2 + 0]];
+    t2.nd[1][int64_t(pb1) * 2 + 1] = M;
+    t2.nd[1][int64_t(pb1) * 2 + 2] = M;
+    t2.nd[1][int64_t(pb1) * 2 + 3] = t2.o2n[0][t2.ev2v[int64_t(e) * 2 + 1]];
+    t2.ng[1][pb1] = gb1;
+    t2.ng[1][pb1 + 1] = gb1 + 1;
+    for (int k = 0; k < it1.n; ++k) {
+      copy_ent(it1.t[k].dst, pb1, it1.t[k].src, e, it1.t[k].bytes);
+      copy_ent(it1.t[k].dst, pb1 + 1, it1.t[k].src, e, it1.t[k].bytes);
+    }
+  }, "products(key)");
+  // per (key, adjacent triangle): the cut edge + the two pair triangles
+  {
+    LO const* map = kf2key.data();
+    parallel_for(nkf, OSHB_LAMBDA(LO kf) {
+      LO key = map[kf + 1] - 1;
+      LO i = kf - kfo[key];
+      LO e = t2.k2e[key];
+      LO M = t2.pbase[0][key];
+      LO ef = t2.ef_off[e] + i;
+      LO f = t2.ef_ents[ef];
+      // cut edge (tip', M) (refine_domains_to_cuts(dim 2), refine_topology.cpp:121-166)
+      int dde = code_which_down(t2.ef_codes[ef]);
+      int tipl = simplex_opposite_template(2, EDGE, dde);
+      LO ne1 = t2.pbase[1][key] + 2 + i;
+      t2.nd[1][int64_t(ne1) * 2 + 0] = t2.o2n[0][t2.fv2v[int64_t(f) * 3 + tipl]];
+      t2.nd[1][int64_t(ne1) * 2 + 1] = M;
+      t2.ng[1][ne1] = t2.gbase[1][key] + 2 + i;
+      for (int k = 0; k < it1.n; ++k) copy_ent(it1.t[k].dst, ne1, it1.t[k].src_up, f, it1.t[k].bytes);
+      // pair triangles
+      for (int eev = 0; eev < 2; ++eev) {
+        LO t = 2 * i + eev;
+        LO ne2 = t2.pbase[2][key] + t;
+        LO verts[3];
+        LO lows[3];
+        I8 codes[3];
+        product_tri(t2, key, t, verts, lows, codes);
+        for (int k = 0; k < 3; ++k) {
+          t2.nd[2][int64_t(ne2) * 3 + k] = lows[k];
+          t2.nc[2][int64_t(ne2) * 3 + k] = codes[k];
+          t2.nvo[2][int64_t(ne2) * 3 + k] = verts[k];
+        }
+        t2.ng[2][ne2] = t2.gbase[2][key] + t;
+        for (int k = 0; k < it2.n; ++k) copy_ent(it2.t[k].dst, ne2, it2.t[k].src, f, it2.t[k].bytes);
+      }
+    }, "products(key,face)");
+  }
+  // per (key, adjacent tet): the cut triangle + the two pair tets
+  if (dim == 3) {
+    LO const* map = kr2key.data();
+    parallel_for(nkr, OSHB_LAMBDA(LO kr) {
+      LO key = map[kr + 1] - 1;
+      LO j = kr - kro[key];
+      LO e = t2.k2e[key];
+      LO nf = t2.ef_off[e + 1] - t2.ef_off[e];
+      LO r = t2.er_ents[t2.er_off[e] + j];
+      {
+        LO t = 2 * nf + j;
+        LO ne2 = t2.pbase[2][key] + t;
+        LO verts[3];
+        LO lows[3];
+        I8 codes[3];
+        product_tri(t2, key, t, verts, lows, codes);
+        for (int k = 0; k < 3; ++k) {
+          t2.nd[2][int64_t(ne2) * 3 + k] = lows[k];
+          t2.nc[2][int64_t(ne2) * 3 + k] = codes[k];
+          t2.nvo[2][int64_t(ne2) * 3 + k] = verts[k];
+        }
+        t2.ng[2][ne2] = t2.gbase[2][key] + t;
+        for (int k = 0; k < it2.n; ++k) copy_ent(it2.t[k].dst, ne2, it2.t[k].src_up, r, it2.t[k].bytes);
+      }
+      for (int eev = 0; eev < 2; ++eev) {
+        LO t = 2 * j + eev;
+        LO ne3 = t2.pbase[3][key] + t;
+        LO verts[4];
+        LO lows[4];
+        I8 codes[4];
+        product_tet(t2, key, int(j), eev, verts, lows, codes);
+        for (int k = 0; k < 4; ++k) {
+          t2.nd[3][int64_t(ne3) * 4 + k] = lows[k];
+          t2.nc[3][int64_t(ne3) * 4 + k] = codes[k];
+          t2.nvo[3][int64_t(ne3) * 4 + k] = verts[k];
+        }
+        t2.ng[3][ne3] = t2.gbase[3][key] + t;
+        for (int k = 0; k < it3.n; ++k) copy_ent(it3.t[k].dst, ne3, it3.t[k].src, r, it3.t[k].bytes);
+      }
+    }, "products(key,tet)");
+  }
+
+  // ---- assemble the new mesh ----------------------------------------------------------------------
+  for (int d = 1; d <= dim; ++d) {
+    Adj a;
+    a.ab2b = new_down[d];
+    a.codes = new_codes[d];
+    new_mesh.set_ents(d, a);
+    if (d >= 2) {
+      // equal to transit(new ent->low, new low->vert); seeded so the new mesh never derives it
+      Adj vo;
+      vo.ab2b = new_vo[d];
+      new_mesh.add_adj(d, VERT, vo);
+    }
+  }
+  for (int d = 0; d <= dim; ++d) {
+    new_mesh.add_tag(d, "global", 1, new_globals[d], true);
+    for (auto const& nt : new_tags[d]) new_mesh.add_tag(d, nt, true);
+  }
+
+  // ---- transfers that need product data computed from the new mesh ----------------------------------
+  LO const* pb0 = tp.pbase[0];
+  for (auto const& s : specials[VERT]) {
+    Tag& nt = new_tags[VERT][s.new_index];
+    int const ncp = nt.ncomps;
+    if (s.kind == 1) {
+      // transfer_linear_interp / average_field (src/Omega_h_transfer.cpp:182-196,
+      // src/Omega_h_mesh.cpp:822-844): comp = 0; comp += x0; comp += x1; comp /= 2
+      Real const* odp = s.old_tag.f64.data();
+      Real* ndp = nt.f64.data();
+      parallel_for(int64_t(nkeys) * ncp, OSHB_LAMBDA(LO i) {
+        LO key = i / ncp;
+        int c = i - key * ncp;
+        LO e = k2e[key];
+        Real comp = 0;
+        comp += odp[int64_t(ev2v[int64_t(e) * 2 + 0]) * ncp + c];
+        comp += odp[int64_t(ev2v[int64_t(e) * 2 + 1]) * ncp + c];
+        comp /= 2;
+        ndp[int64_t(pb0[key]) * ncp + c] = comp;
+      }, "transfer_linear_interp");
+    } else if (s.kind == 2) {
+      // transfer_metric (src/Omega_h_transfer.cpp:198-210)
+      Reals prod = get_mident_metrics(mesh, EDGE, keys2edges, s.old_tag.f64);
+      scatter_by<Real>(prod.data(), nt.f64.data(), pb0, nkeys, ncp);
+    }
+  }
+  for (auto const& s : specials[EDGE]) {
+    if (s.kind != 3) continue;
+    // transfer_length (src/Omega_h_transfer.cpp:337-348): re-measure the product edges
+    LO const n1 = 2 * nkeys + nkf;
+    LOs list(n1);
+    LO* lp = list.data();
+    LO const* pb1 = tp.pbase[1];
+    LO const* map = kf2key.data();
+    parallel_for(n1, OSHB_LAMBDA(LO i) {
+      if (i < 2 * nkeys) {
+        lp[i] = pb1[i >> 1] + (i & 1);
+      } else {
+        LO kf = i - 2 * nkeys;
+        LO key = map[kf + 1] - 1;
+        lp[i] = pb1[key] + 2 + (kf - kfo[key]);
+      }
+    }, "product_list(edges)");
+    Reals prod = measure_edges_metric(&new_mesh, list, new_mesh.get_reals(VERT, "metric"));
+    scatter_by<Real>(prod.data(), new_tags[EDGE][s.new_index].f64.data(), lp, n1, 1);
+  }
+  for (auto const& s : specials[dim]) {
+    if (s.kind != 4) continue;
+    // transfer_quality (src/Omega_h_transfer.cpp:350-362)
+    LO const npairs = (dim == 3) ? nkr : nkf;
+    LO const nq = 2 * npairs;
+    LOs list(nq);
+    LO* lp = list.data();
+    LO const* pbd = tp.pbase[dim];
+    LO const* map = (dim == 3) ? kr2key.data() : kf2key.data();
+    LO const* ko = (dim == 3) ? kro : kfo;
+    parallel_for(nq, OSHB_LAMBDA(LO i) {
+      LO pr = i >> 1;
+      LO key = map[pr + 1] - 1;
+      lp[i] = pbd[key] + 2 * (pr - ko[key]) + (i & 1);
+    }, "product_list(elems)");
+    Reals prod = measure_qualities(&new_mesh, list, new_mesh.get_reals(VERT, "metric"));
+    scatter_by<Real>(prod.data(), new_tags[dim][s.new_index].f64.data(), lp, nq, 1);
+  }
+  *mesh = new_mesh;
+}
+
+}  // namespace oshb

@@ -107,3 +107,30 @@ def test_find_unique_known_answers(lib):
         return d_o.to_host(n.value * (ld + 1)).tolist()
     # 5 unique edges sorted by canonical tuple; each run keeps its LAST use's orientation
     assert fu([0, 1, 2, 2, 3, 0], 2, 1) == [0, 1, 0, 2, 3, 0, 1, 2, 2, 3]
+
+
+@pytest.mark.parametrize("seed,nlow,maxdeg", [(1, 50, 3), (2, 200, 8), (3, 300, 16), (4, 100, 40), (5, 4000, 12)])
+def test_invert_adj_random_rows(lib, seed, nlow, maxdeg):
+    """rows of every length class (<=8 register network, <=16 network, longer insertion sort)
+    against a stable numpy sort; rows must come out sorted by high index with the right codes"""
+    rng = np.random.default_rng(seed)
+    deg = 3
+    nhigh = (nlow * maxdeg) // (2 * deg) + 7
+    # each high picks `deg` distinct lows, skewed so some rows are long
+    w = rng.random(nlow) ** 3 + 1e-3
+    w /= w.sum()
+    hl2l = np.stack([rng.choice(nlow, size=deg, replace=False, p=w) for _ in range(nhigh)]).astype(np.int32).reshape(-1)
+    codes = rng.integers(0, 6, size=hl2l.size).astype(np.int8)  # rotation/flip bits of a down code
+    d_in, d_c = lib.to_device(hl2l), lib.to_device(codes)
+    d_off = lib.empty_device(nlow + 1, np.int32)
+    d_ab = lib.empty_device(hl2l.size, np.int32)
+    d_oc = lib.empty_device(hl2l.size, np.int8)
+    lib.check(lib.c.oshb_invert_adj(d_in.ptr, d_c.ptr, C.c_int64(nhigh), C.c_int(deg), C.c_int32(nlow), d_off.ptr,
+                                    d_ab.ptr, d_oc.ptr))
+    order = np.argsort(hl2l, kind="stable")  # uses sorted by low, then by use index (= by high)
+    want_off = np.concatenate([[0], np.cumsum(np.bincount(hl2l, minlength=nlow))]).astype(np.int32)
+    want_h = (order // deg).astype(np.int32)
+    want_c = (((order % deg) << 3) | (codes[order] & 7)).astype(np.int8)
+    assert np.array_equal(d_off.to_host(), want_off)
+    assert np.array_equal(d_ab.to_host(), want_h)
+    assert np.array_equal(d_oc.to_host(), want_c)
