@@ -146,6 +146,16 @@ Bytes find_indset(Mesh* mesh, int ent_dim, Reals quality, Bytes candidates, int*
 LOs get_rep2md_order_adapt(Mesh* mesh, int key_dim, int rep_dim, Bytes kds_are_keys);  // src/Omega_h_modify.cpp:269-281
 bool refine_by_size(Mesh* mesh, AdaptOpts const& opts);             // src/Omega_h_refine.cpp:92-100
 
+// ordering of the key edges that share a first vertex (get_rep2md_order, src/Omega_h_modify.cpp:283-338)
+struct KeyOrder {
+  LOs edge_order;     // rep_vertex2md_order: per edge, -1 or the key's rank at its first vertex
+  LOs keys_order;     // the same rank, per key
+  LOs vert2keys_off;  // CSR first vertex -> keys (nverts + 1)
+  LOs vert_keys;      // keys of each first vertex in increasing rank
+};
+struct PassStats;
+void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassStats* stats);  // rebuild.cu
+
 struct PassStats {
   LO ncands = 0, nkeys = 0, indset_rounds = 0;
   LO nents_before[4] = {0, 0, 0, 0};

@@ -8,12 +8,14 @@
 //  * numbering first: for every dimension one scan of the representative counts gives
 //    old->new for surviving entities and, per key, the new index / new global of its first
 //    product (assign_new_numbering, modify.cpp:347-404);
-//  * ONE FUSED STREAMING KERNEL PER DIMENSION over the OLD entities copies everything a
-//    surviving entity keeps: remapped downward row, codes, entity->vertex row, global id and
-//    every transferable tag (no compaction into "same" index lists, no per-tag launches);
-//  * PRODUCTS ARE BUILT PER CAVITY DOMAIN: one thread per key edge (midpoint vertex + the two
-//    halves), one per (key, adjacent triangle) (cut edge + two pair triangles) and one per
-//    (key, adjacent tet) (cut triangle + two pair tets). Each derives analytically
+//  * GATHER FORMULATION: ONE THREAD PER NEW ENTITY, one fused kernel per dimension. The thread
+//    finds (binary search in the scanned counts) the old entity that represents its slot; it is
+//    either that surviving entity -- then it copies the remapped downward row, codes,
+//    entity->vertex row, global id and every transferable tag -- or product number t of a key
+//    edge. Every new array is therefore written exactly once, in index order, in full
+//    sectors (ncu showed the scatter formulation paying 2.5x its algorithmic DRAM bytes in
+//    read-modify-write of partially written sectors, profiles/ncu_r1a_summary.md).
+//  * a product derives analytically, from the key's upward rows (E->F, E->R),
 //      - vertices              (refine_domains_to_pairs/_cuts, refine_topology.cpp:13-203)
 //      - downward entities AND alignment codes: every bounding entity of a product is either
 //        another product of the same key or an old entity of the split domain, so the
@@ -268,23 +270,31 @@ static void scatter_by(T const* data, T* new_data, LO const* index, LO n, int nc
   }, "transfer(prods)");
 }
 
-// pair index -> key: count the keys whose range starts at each pair, prefix sum
-static LOs pair2key(LOs k_off, LO nkeys, LO npairs) {
-  LO const* ko = k_off.data();
-  // a key without pairs (cannot happen for faces; boundary-free for tets) would share its
-  // offset with the next key: count every key whose range starts here
-  LOs cnt = filled<LO>(npairs + 1, 0);
-  LO* cp = cnt.data();
-  parallel_for(nkeys, OSHB_LAMBDA(LO key) { atomic_add(&cp[ko[key]], 1); }, "pair2key(heads)");
-  LOs map(npairs + 2);
-  scan_offsets(cnt.data(), npairs + 1, map.data());
-  return map;  // key of pair p = map[p + 1] - 1
+// first index in [0, n] with off[idx] > x (off is nondecreasing, n entries)
+OSHB_HD LO upper_bound(LO const* off, LO n, LO x) {
+  LO lo = 0, hi = n;
+  while (lo < hi) {
+    LO mid = lo + ((hi - lo) >> 1);
+    if (off[mid] <= x) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+OSHB_HD LO key_nprods(Topo const& tp, int ent_dim, LO key) {
+  LO e = tp.k2e[key];
+  LO nf = tp.ef_off[e + 1] - tp.ef_off[e];
+  LO nr = tp.er_off ? (tp.er_off[e + 1] - tp.er_off[e]) : 0;
+  if (ent_dim == VERT) return 1;
+  if (ent_dim == EDGE) return 2 + nf;
+  if (ent_dim == FACE) return 2 * nf + nr;
+  return 2 * nr;
 }
 
 // ---------------------------------------------------------------------------------------
 // refine_element_based
 // ---------------------------------------------------------------------------------------
-void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_order, PassStats* stats) {
+void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassStats* stats) {
   int const dim = mesh->dim();
   LO const nkeys = LO(keys2edges.size());
   LO const* k2e = keys2edges.data();
@@ -324,102 +334,78 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_o
     tp.re2e = r2e.ab2b.data();
     tp.re_codes = r2e.codes.data();
   }
-  LO const* ef_off = tp.ef_off;
-  LO const* er_off = tp.er_off;
-
-  // ---- key -> (key, face) and (key, tet) pair ranges --------------------------------------
-  LOs kf_off(nkeys + 1), kr_off;
-  {
-    LOs nf(nkeys);
-    LO* p = nf.data();
-    parallel_for(nkeys, OSHB_LAMBDA(LO key) { p[key] = ef_off[k2e[key] + 1] - ef_off[k2e[key]]; }, "key_degrees");
-    scan_offsets(nf.data(), nkeys, kf_off.data());
-    if (dim == 3) {
-      kr_off = LOs(nkeys + 1);
-      parallel_for(nkeys, OSHB_LAMBDA(LO key) { p[key] = er_off[k2e[key] + 1] - er_off[k2e[key]]; }, "key_degrees");
-      scan_offsets(nf.data(), nkeys, kr_off.data());
-    }
-  }
-  LO const nkf = last_of(kf_off);
-  LO const nkr = (dim == 3) ? last_of(kr_off) : 0;
-  LO const* kfo = kf_off.data();
-  LO const* kro = (dim == 3) ? kr_off.data() : nullptr;
-  LOs kf2key = pair2key(kf_off, nkeys, nkf);
-  LOs kr2key;
-  if (dim == 3) kr2key = pair2key(kr_off, nkeys, nkr);
+  LO const* voff = ko.vert2keys_off.data();
+  LO const* vkeys = ko.vert_keys.data();
 
   // ---- numbering of every dimension ---------------------------------------------------------
-  LOs old2new[4], pbase[4], offsets_keep[4];
-  GOs gbase[4], new_globals[4], lin_globals_keep[4];
+  // status[e]: -1 the entity survives, -2 it dies, k >= 0 it dies and represents key k
+  // (get_mods2reps, src/Omega_h_modify.cpp:141-176: the key itself for edges, the first upward
+  //  adjacent entity for triangles / tets; for vertices the key's first vertex, which survives)
+  LOs old2new[4], pbase[4], offsets[4], status[4];
+  GOs gbase[4], new_globals[4], lin_globals[4];
   LO nnew[4] = {0, 0, 0, 0};
   for (int ent_dim = 0; ent_dim <= dim; ++ent_dim) {
     LO const nold = mesh->nents(ent_dim);
-    // representative counts: 1 for surviving entities, the key's product count on each key's
-    // representative (get_mods2reps / get_rep_counts, src/Omega_h_modify.cpp:141-243)
+    Topo const t1 = tp;
+    LO* st = nullptr;
+    if (ent_dim >= EDGE) {
+      status[ent_dim] = filled<LO>(nold, -1);
+      st = status[ent_dim].data();
+      if (ent_dim == EDGE) {
+        parallel_for(nkeys, OSHB_LAMBDA(LO key) { st[k2e[key]] = key; }, "status(edge)");
+      } else {
+        Adj const& e2d = (ent_dim == FACE) ? e2f : e2r;
+        LO const* d_off = e2d.a2ab.data();
+        LO const* d_ents = e2d.ab2b.data();
+        // two launches so that the representative ends with its key, not with -2
+        parallel_for(nkeys, OSHB_LAMBDA(LO key) {
+          LO e = k2e[key];
+          for (LO ed = d_off[e]; ed < d_off[e + 1]; ++ed) st[d_ents[ed]] = -2;
+        }, "status(dead)");
+        parallel_for(nkeys, OSHB_LAMBDA(LO key) { st[d_ents[d_off[k2e[key]]]] = key; }, "status(rep)");
+      }
+    }
+    // representative counts (get_rep_counts, src/Omega_h_modify.cpp:178-243)
     LOs rep_counts(nold);
     LO* rc = rep_counts.data();
-    Adj const& e2d = (ent_dim == FACE) ? e2f : e2r;  // EDGE -> ent_dim upward (ent_dim >= 2)
-    LO const* d_off = (ent_dim >= FACE) ? e2d.a2ab.data() : nullptr;
-    LO const* d_ents = (ent_dim >= FACE) ? e2d.ab2b.data() : nullptr;
-    Bytes dead;
-    if (ent_dim >= EDGE) dead = Bytes(nold);
-    I8* dd = dead.exists() ? dead.data() : nullptr;
-    parallel_for(nold, OSHB_LAMBDA(LO i) {
-      rc[i] = 1;
-      if (dd) dd[i] = 0;
-    }, "rep_counts(init)");
-    if (ent_dim == VERT) {
-      parallel_for(nkeys, OSHB_LAMBDA(LO key) { atomic_add(&rc[ev2v[int64_t(k2e[key]) * 2]], 1); }, "rep_counts(vert)");
-    } else if (ent_dim == EDGE) {
-      parallel_for(nkeys, OSHB_LAMBDA(LO key) {
-        LO e = k2e[key];
-        rc[e] = 2 + (ef_off[e + 1] - ef_off[e]);
-        dd[e] = 1;
-      }, "rep_counts(edge)");
-    } else {
-      // all entities around a key die; the first one represents the key's products.
-      // two launches so that the dead representative ends with nprods, not 0.
-      parallel_for(nkeys, OSHB_LAMBDA(LO key) {
-        LO e = k2e[key];
-        for (LO ed = d_off[e]; ed < d_off[e + 1]; ++ed) {
-          rc[d_ents[ed]] = 0;
-          dd[d_ents[ed]] = 1;
-        }
-      }, "rep_counts(dead)");
-      parallel_for(nkeys, OSHB_LAMBDA(LO key) {
-        LO e = k2e[key];
-        LO nf = ef_off[e + 1] - ef_off[e];
-        LO nr = er_off ? (er_off[e + 1] - er_off[e]) : 0;
-        rc[d_ents[d_off[e]]] = (ent_dim == FACE) ? (2 * nf + nr) : (2 * nr);
-      }, "rep_counts(rep)");
-    }
-    LOs offsets = offset_scan(rep_counts);
+    parallel_for(nold, OSHB_LAMBDA(LO e) {
+      if (ent_dim == VERT) {
+        rc[e] = 1 + (voff[e + 1] - voff[e]);
+      } else {
+        LO s = st[e];
+        rc[e] = (s == -1) ? 1 : ((s == -2) ? 0 : key_nprods(t1, ent_dim, s));
+      }
+    }, "rep_counts");
+    offsets[ent_dim] = offset_scan(rep_counts);
     rep_counts.reset();
-    LO const* off = offsets.data();
-    nnew[ent_dim] = last_of(offsets);
+    LO const* off = offsets[ent_dim].data();
+    nnew[ent_dim] = last_of(offsets[ent_dim]);
     old2new[ent_dim] = LOs(nold);
     LO* o2n = old2new[ent_dim].data();
     // globals of the old entities on the linear partition (modify_globals,
     // src/Omega_h_modify.cpp:406-444); one rank: exchange = identity, rescan = exclusive scan
     GOs old_globals = mesh->globals(ent_dim);
     GO const* og = old_globals.data();
-    GOs lin_globals(int64_t(nold) + 1);
+    lin_globals[ent_dim] = GOs(int64_t(nold) + 1);
     {
       LOs lin_counts(nold);
       LO* lc = lin_counts.data();
       parallel_for(nold, OSHB_LAMBDA(LO e) {
-        o2n[e] = (dd && dd[e]) ? -1 : off[e];
+        o2n[e] = (st && st[e] != -1) ? -1 : off[e];
         lc[og[e]] = off[e + 1] - off[e];
       }, "old2new+to_lin");
-      scan_offsets(lin_counts.data(), nold, lin_globals.data());
+      scan_offsets(lin_counts.data(), nold, lin_globals[ent_dim].data());
     }
-    GO const* lg = lin_globals.data();
+    GO const* lg = lin_globals[ent_dim].data();
     pbase[ent_dim] = LOs(nkeys);
     gbase[ent_dim] = GOs(nkeys);
     LO* pb = pbase[ent_dim].data();
     GO* gb = gbase[ent_dim].data();
-    LO const* kord = keys_order.data();
-    LO const* eord = edge_order.data();
+    LO const* kord = ko.keys_order.data();
+    LO const* eord = ko.edge_order.data();
+    Adj const& e2d = (ent_dim == FACE) ? e2f : e2r;
+    LO const* d_off = (ent_dim >= FACE) ? e2d.a2ab.data() : nullptr;
+    LO const* d_ents = (ent_dim >= FACE) ? e2d.ab2b.data() : nullptr;
     parallel_for(nkeys, OSHB_LAMBDA(LO key) {
       LO e = k2e[key];
       if (ent_dim == VERT) {
@@ -433,7 +419,6 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_o
       }
     }, "prod_bases");
     new_globals[ent_dim] = GOs(nnew[ent_dim]);
-    lin_globals_keep[ent_dim] = lin_globals;
     tp.o2n[ent_dim] = o2n;
     tp.pbase[ent_dim] = pb;
     tp.gbase[ent_dim] = gb;
@@ -444,7 +429,7 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_o
 
   // ---- new arrays + tag tables ----------------------------------------------------------------
   LOs new_down[4], new_vo[4];
-  Bytes new_codes[4];
+  Bytes new_codes[4], prod_marks[4];
   std::vector<Tag> new_tags[4];
   TagTable same_tab[4], inh_tab[4];
   struct Special {
@@ -500,11 +485,12 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_o
         s.old_tag = tag;
         s.new_index = new_tags[d].size() - 1;
         specials[d].push_back(s);
+        if (kind == 3 || kind == 4) prod_marks[d] = Bytes(nnew[d]);
       }
     }
   }
 
-  // ---- surviving entities: one fused streaming kernel per dimension ----------------------------
+  // ---- one gather kernel per dimension: thread per NEW entity -----------------------------------
   for (int d = 0; d <= dim; ++d) {
     LO const nold = mesh->nents(d);
     int const deg = (d >= 1) ? simplex_degree(d, d - 1) : 0;
@@ -514,32 +500,108 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_o
     LO const* od = (d >= 1) ? old_down.ab2b.data() : nullptr;
     I8 const* oc = (d >= 2) ? old_down.codes.data() : nullptr;
     LO const* ovo = (d == FACE) ? tp.fv2v : ((d == REGION) ? tp.rv2v : nullptr);
-    LO const* o2n = tp.o2n[d];
+    LO const* off = offsets[d].data();
+    LO const* st = (d >= 1) ? status[d].data() : nullptr;
     LO const* ol2nl = (d >= 1) ? tp.o2n[d - 1] : nullptr;
     LO const* ov2nv = tp.o2n[0];
     LO* nd = tp.nd[d];
     I8* nc = tp.nc[d];
     LO* nvo = tp.nvo[d];
     GO* ng = tp.ng[d];
-    GO const* og = mesh->globals(d).data();
-    GOs lgk = lin_globals_keep[d];
-    GO const* lg = lgk.data();
-    TagTable const tab = same_tab[d];
+    GOs ogs = mesh->globals(d);
+    GO const* og = ogs.data();
+    GO const* lg = lin_globals[d].data();
+    I8* pm = prod_marks[d].exists() ? prod_marks[d].data() : nullptr;
+    TagTable const stab = same_tab[d];
+    TagTable const itab = inh_tab[d];
+    Topo const t2 = tp;
     int64_t tag_bytes = 0;
-    for (int k = 0; k < tab.n; ++k) tag_bytes += tab.t[k].bytes;
-    algo_bytes(int64_t(nold) * (4 + 16 + deg * 8 + (d >= 2 ? deg * 2 + nv * 8 : 0) + 2 * tag_bytes));
-    parallel_for(nold, OSHB_LAMBDA(LO e) {
-      LO ne = o2n[e];
-      if (ne < 0) return;
-      ng[ne] = lg[og[e]];
-      for (int k = 0; k < deg; ++k) {
-        nd[int64_t(ne) * deg + k] = ol2nl[od[int64_t(e) * deg + k]];
-        if (nc) nc[int64_t(ne) * deg + k] = oc[int64_t(e) * deg + k];
+    for (int k = 0; k < stab.n; ++k) tag_bytes += stab.t[k].bytes;
+    // algorithmic bytes: every new array written once + the old arrays read once
+    algo_bytes(int64_t(nnew[d]) * (8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes) +
+               int64_t(nold) * (4 + 4 + 8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes));
+    parallel_for(nnew[d], OSHB_LAMBDA(LO ne) {
+      LO e = upper_bound(off, nold + 1, ne) - 1;  // the old entity that represents this slot
+      LO local = ne - off[e];
+      LO s = st ? st[e] : -1;
+      if (s == -1 && local == 0) {
+        // a surviving entity keeps its place: remapped row, codes, vertices, global, tags
+        // (modify_conn / transfer_common2, src/Omega_h_modify.cpp:20-70, Omega_h_transfer.cpp:160-170)
+        ng[ne] = lg[og[e]];
+        for (int k = 0; k < deg; ++k) {
+          nd[int64_t(ne) * deg + k] = ol2nl[od[int64_t(e) * deg + k]];
+          if (nc) nc[int64_t(ne) * deg + k] = oc[int64_t(e) * deg + k];
+        }
+        if (nvo)
+          for (int k = 0; k < nv; ++k) nvo[int64_t(ne) * nv + k] = ov2nv[ovo[int64_t(e) * nv + k]];
+        for (int k = 0; k < stab.n; ++k) copy_ent(stab.t[k].dst, ne, stab.t[k].src, e, stab.t[k].bytes);
+        if (pm) pm[ne] = 0;
+        return;
       }
-      if (nvo)
-        for (int k = 0; k < nv; ++k) nvo[int64_t(ne) * nv + k] = ov2nv[ovo[int64_t(e) * nv + k]];
-      for (int k = 0; k < tab.n; ++k) copy_ent(tab.t[k].dst, ne, tab.t[k].src, e, tab.t[k].bytes);
-    }, "same_entities");
+      if (pm) pm[ne] = 1;
+      if (d == VERT) {
+        // midpoint vertex of the (local-1)-th key whose first vertex is e
+        LO key = vkeys[voff[e] + local - 1];
+        LO ke = t2.k2e[key];
+        ng[ne] = t2.gbase[0][key];
+        for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src_up, ke, itab.t[k].bytes);
+        return;
+      }
+      LO key = s;
+      LO t = local;
+      LO ke = t2.k2e[key];
+      ng[ne] = t2.gbase[d][key] + t;
+      LO fb = t2.ef_off[ke];
+      LO nf = t2.ef_off[ke + 1] - fb;
+      if (d == EDGE) {
+        LO M = t2.pbase[0][key];
+        if (t < 2) {
+          // halves of the key: (A', M), (M, B')  (refine_edges_to_pairs, refine_topology.cpp:13-34)
+          LO end = ov2nv[t2.ev2v[int64_t(ke) * 2 + t]];
+          nd[int64_t(ne) * 2 + 0] = (t == 0) ? end : M;
+          nd[int64_t(ne) * 2 + 1] = (t == 0) ? M : end;
+          for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src, ke, itab.t[k].bytes);
+        } else {
+          // cut edge of face t-2: (tip', M)  (refine_domains_to_cuts(dim 2), :121-166)
+          LO f = t2.ef_ents[fb + t - 2];
+          int dde = code_which_down(t2.ef_codes[fb + t - 2]);
+          int tipl = simplex_opposite_template(2, EDGE, dde);
+          nd[int64_t(ne) * 2 + 0] = ov2nv[t2.fv2v[int64_t(f) * 3 + tipl]];
+          nd[int64_t(ne) * 2 + 1] = M;
+          for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src_up, f, itab.t[k].bytes);
+        }
+      } else if (d == FACE) {
+        LO verts[3];
+        LO lows[3];
+        I8 codes[3];
+        product_tri(t2, key, t, verts, lows, codes);
+        for (int k = 0; k < 3; ++k) {
+          nd[int64_t(ne) * 3 + k] = lows[k];
+          nc[int64_t(ne) * 3 + k] = codes[k];
+          nvo[int64_t(ne) * 3 + k] = verts[k];
+        }
+        if (t < 2 * nf) {
+          LO f = t2.ef_ents[fb + (t >> 1)];
+          for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src, f, itab.t[k].bytes);
+        } else {
+          LO r = t2.er_ents[t2.er_off[ke] + (t - 2 * nf)];
+          for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src_up, r, itab.t[k].bytes);
+        }
+      } else {
+        LO verts[4];
+        LO lows[4];
+        I8 codes[4];
+        product_tet(t2, key, int(t >> 1), int(t & 1), verts, lows, codes);
+        for (int k = 0; k < 4; ++k) {
+          nd[int64_t(ne) * 4 + k] = lows[k];
+          nc[int64_t(ne) * 4 + k] = codes[k];
+          nvo[int64_t(ne) * 4 + k] = verts[k];
+        }
+        LO r = t2.er_ents[t2.er_off[ke] + (t >> 1)];
+        for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src, r, itab.t[k].bytes);
+      }
+    }, "rebuild(gather)");
+    LO const* o2n = tp.o2n[d];
     for (auto const& ov : overflow[d]) {
       Tag const& ot = ov.first;
       Tag& nt = new_tags[d][ov.second];
@@ -551,106 +613,6 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_o
         if (ne >= 0) copy_ent(dst, ne, src, e, bytes);
       }, "same_entities(overflow)");
     }
-  }
-
-  // ---- products ------------------------------------------------------------------------------------
-  Topo const t2 = tp;
-  TagTable const it0 = inh_tab[0], it1 = inh_tab[1], it2 = inh_tab[2], it3 = inh_tab[3];
-  // per key: midpoint vertex + the two halves of the key edge
-  parallel_for(nkeys, OSHB_LAMBDA(LO key) {
-    LO e = t2.k2e[key];
-    LO M = t2.pbase[0][key];
-    t2.ng[0][M] = t2.gbase[0][key];
-    for (int k = 0; k < it0.n; ++k) copy_ent(it0.t[k].dst, M, it0.t[k].src_up, e, it0.t[k].bytes);
-    LO pb1 = t2.pbase[1][key];
-    GO gb1 = t2.gbase[1][key];
-    t2.nd[1][int64_t(pb1) * 2 + 0] = t2.o2n[0][t2.ev2v[int64_t(e) * 2 + 0]];
-    t2.nd[1][int64_t(pb1) * 2 + 1] = M;
-    t2.nd[1][int64_t(pb1) * 2 + 2] = M;
-    t2.nd[1][int64_t(pb1) * 2 + 3] = t2.o2n[0][t2.ev2v[int64_t(e) * 2 + 1]];
-    t2.ng[1][pb1] = gb1;
-    t2.ng[1][pb1 + 1] = gb1 + 1;
-    for (int k = 0; k < it1.n; ++k) {
-      copy_ent(it1.t[k].dst, pb1, it1.t[k].src, e, it1.t[k].bytes);
-      copy_ent(it1.t[k].dst, pb1 + 1, it1.t[k].src, e, it1.t[k].bytes);
-    }
-  }, "products(key)");
-  // per (key, adjacent triangle): the cut edge + the two pair triangles
-  {
-    LO const* map = kf2key.data();
-    parallel_for(nkf, OSHB_LAMBDA(LO kf) {
-      LO key = map[kf + 1] - 1;
-      LO i = kf - kfo[key];
-      LO e = t2.k2e[key];
-      LO M = t2.pbase[0][key];
-      LO ef = t2.ef_off[e] + i;
-      LO f = t2.ef_ents[ef];
-      // cut edge (tip', M) (refine_domains_to_cuts(dim 2), refine_topology.cpp:121-166)
-      int dde = code_which_down(t2.ef_codes[ef]);
-      int tipl = simplex_opposite_template(2, EDGE, dde);
-      LO ne1 = t2.pbase[1][key] + 2 + i;
-      t2.nd[1][int64_t(ne1) * 2 + 0] = t2.o2n[0][t2.fv2v[int64_t(f) * 3 + tipl]];
-      t2.nd[1][int64_t(ne1) * 2 + 1] = M;
-      t2.ng[1][ne1] = t2.gbase[1][key] + 2 + i;
-      for (int k = 0; k < it1.n; ++k) copy_ent(it1.t[k].dst, ne1, it1.t[k].src_up, f, it1.t[k].bytes);
-      // pair triangles
-      for (int eev = 0; eev < 2; ++eev) {
-        LO t = 2 * i + eev;
-        LO ne2 = t2.pbase[2][key] + t;
-        LO verts[3];
-        LO lows[3];
-        I8 codes[3];
-        product_tri(t2, key, t, verts, lows, codes);
-        for (int k = 0; k < 3; ++k) {
-          t2.nd[2][int64_t(ne2) * 3 + k] = lows[k];
-          t2.nc[2][int64_t(ne2) * 3 + k] = codes[k];
-          t2.nvo[2][int64_t(ne2) * 3 + k] = verts[k];
-        }
-        t2.ng[2][ne2] = t2.gbase[2][key] + t;
-        for (int k = 0; k < it2.n; ++k) copy_ent(it2.t[k].dst, ne2, it2.t[k].src, f, it2.t[k].bytes);
-      }
-    }, "products(key,face)");
-  }
-  // per (key, adjacent tet): the cut triangle + the two pair tets
-  if (dim == 3) {
-    LO const* map = kr2key.data();
-    parallel_for(nkr, OSHB_LAMBDA(LO kr) {
-      LO key = map[kr + 1] - 1;
-      LO j = kr - kro[key];
-      LO e = t2.k2e[key];
-      LO nf = t2.ef_off[e + 1] - t2.ef_off[e];
-      LO r = t2.er_ents[t2.er_off[e] + j];
-      {
-        LO t = 2 * nf + j;
-        LO ne2 = t2.pbase[2][key] + t;
-        LO verts[3];
-        LO lows[3];
-        I8 codes[3];
-        product_tri(t2, key, t, verts, lows, codes);
-        for (int k = 0; k < 3; ++k) {
-          t2.nd[2][int64_t(ne2) * 3 + k] = lows[k];
-          t2.nc[2][int64_t(ne2) * 3 + k] = codes[k];
-          t2.nvo[2][int64_t(ne2) * 3 + k] = verts[k];
-        }
-        t2.ng[2][ne2] = t2.gbase[2][key] + t;
-        for (int k = 0; k < it2.n; ++k) copy_ent(it2.t[k].dst, ne2, it2.t[k].src_up, r, it2.t[k].bytes);
-      }
-      for (int eev = 0; eev < 2; ++eev) {
-        LO t = 2 * j + eev;
-        LO ne3 = t2.pbase[3][key] + t;
-        LO verts[4];
-        LO lows[4];
-        I8 codes[4];
-        product_tet(t2, key, int(j), eev, verts, lows, codes);
-        for (int k = 0; k < 4; ++k) {
-          t2.nd[3][int64_t(ne3) * 4 + k] = lows[k];
-          t2.nc[3][int64_t(ne3) * 4 + k] = codes[k];
-          t2.nvo[3][int64_t(ne3) * 4 + k] = verts[k];
-        }
-        t2.ng[3][ne3] = t2.gbase[3][key] + t;
-        for (int k = 0; k < it3.n; ++k) copy_ent(it3.t[k].dst, ne3, it3.t[k].src, r, it3.t[k].bytes);
-      }
-    }, "products(key,tet)");
   }
 
   // ---- assemble the new mesh ----------------------------------------------------------------------
@@ -700,40 +662,16 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_o
   for (auto const& s : specials[EDGE]) {
     if (s.kind != 3) continue;
     // transfer_length (src/Omega_h_transfer.cpp:337-348): re-measure the product edges
-    LO const n1 = 2 * nkeys + nkf;
-    LOs list(n1);
-    LO* lp = list.data();
-    LO const* pb1 = tp.pbase[1];
-    LO const* map = kf2key.data();
-    parallel_for(n1, OSHB_LAMBDA(LO i) {
-      if (i < 2 * nkeys) {
-        lp[i] = pb1[i >> 1] + (i & 1);
-      } else {
-        LO kf = i - 2 * nkeys;
-        LO key = map[kf + 1] - 1;
-        lp[i] = pb1[key] + 2 + (kf - kfo[key]);
-      }
-    }, "product_list(edges)");
+    LOs list = collect_marked(prod_marks[EDGE]);
     Reals prod = measure_edges_metric(&new_mesh, list, new_mesh.get_reals(VERT, "metric"));
-    scatter_by<Real>(prod.data(), new_tags[EDGE][s.new_index].f64.data(), lp, n1, 1);
+    scatter_by<Real>(prod.data(), new_tags[EDGE][s.new_index].f64.data(), list.data(), LO(list.size()), 1);
   }
   for (auto const& s : specials[dim]) {
     if (s.kind != 4) continue;
     // transfer_quality (src/Omega_h_transfer.cpp:350-362)
-    LO const npairs = (dim == 3) ? nkr : nkf;
-    LO const nq = 2 * npairs;
-    LOs list(nq);
-    LO* lp = list.data();
-    LO const* pbd = tp.pbase[dim];
-    LO const* map = (dim == 3) ? kr2key.data() : kf2key.data();
-    LO const* ko = (dim == 3) ? kro : kfo;
-    parallel_for(nq, OSHB_LAMBDA(LO i) {
-      LO pr = i >> 1;
-      LO key = map[pr + 1] - 1;
-      lp[i] = pbd[key] + 2 * (pr - ko[key]) + (i & 1);
-    }, "product_list(elems)");
+    LOs list = collect_marked(prod_marks[dim]);
     Reals prod = measure_qualities(&new_mesh, list, new_mesh.get_reals(VERT, "metric"));
-    scatter_by<Real>(prod.data(), new_tags[dim][s.new_index].f64.data(), lp, nq, 1);
+    scatter_by<Real>(prod.data(), new_tags[dim][s.new_index].f64.data(), list.data(), LO(list.size()), 1);
   }
   *mesh = new_mesh;
 }

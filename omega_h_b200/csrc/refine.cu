@@ -7,7 +7,6 @@
 
 namespace oshb {
 
-void refine_element_based(Mesh* mesh, LOs keys2edges, LOs edge_order, LOs keys_order, PassStats* stats);
 
 static PassStats g_stats;
 PassStats const& last_pass_stats() { return g_stats; }
@@ -108,7 +107,8 @@ Bytes find_indset(Mesh* mesh, int ent_dim, Reals quality, Bytes candidates, int*
 // among the key edges whose FIRST vertex is v, their rank in increasing edge index.
 // Built from the keys alone: CSR (first vertex -> keys) by atomics, rank by counting.
 // ---------------------------------------------------------------------------------------
-LOs rep_vertex_order_from_keys(LOs ev2v_a, LO nverts, LO nedges, LOs keys2edges, LOs* keys_order_out) {
+LOs rep_vertex_order_from_keys(LOs ev2v_a, LO nverts, LO nedges, LOs keys2edges, LOs* keys_order_out,
+    LOs* vert2keys_off_out, LOs* vert_keys_out) {
   LO const nkeys = LO(keys2edges.size());
   LOs order = filled<LO>(nedges, -1);
   LOs counts = filled<LO>(nverts, 0);
@@ -126,8 +126,10 @@ LOs rep_vertex_order_from_keys(LOs ev2v_a, LO nverts, LO nedges, LOs keys2edges,
     rw[off[v] + j - 1] = k;
   }, "rep_order(fill)");
   LOs korder(nkeys);
+  LOs sorted_rows(nkeys);  // per first vertex, its keys in increasing key (= edge) index
   LO* ko = korder.data();
   LO* ord = order.data();
+  LO* sr = sorted_rows.data();
   parallel_for(nkeys, OSHB_LAMBDA(LO k) {
     LO v = ev2v[int64_t(k2e[k]) * 2];
     LO r = 0;
@@ -135,15 +137,19 @@ LOs rep_vertex_order_from_keys(LOs ev2v_a, LO nverts, LO nedges, LOs keys2edges,
       if (rw[s] < k) ++r;
     ko[k] = r;
     ord[k2e[k]] = r;
+    sr[off[v] + r] = k;
   }, "rep_order(rank)");
   if (keys_order_out) *keys_order_out = korder;
+  if (vert2keys_off_out) *vert2keys_off_out = offsets;
+  if (vert_keys_out) *vert_keys_out = sorted_rows;
   return order;
 }
 
 LOs get_rep2md_order_adapt(Mesh* mesh, int key_dim, int rep_dim, Bytes kds_are_keys) {
   OSHB_CHECK(key_dim == EDGE && rep_dim == VERT);
   LOs keys2edges = collect_marked(kds_are_keys);
-  return rep_vertex_order_from_keys(mesh->ask_verts_of(EDGE), mesh->nverts(), mesh->nedges(), keys2edges, nullptr);
+  return rep_vertex_order_from_keys(
+      mesh->ask_verts_of(EDGE), mesh->nverts(), mesh->nedges(), keys2edges, nullptr, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -198,9 +204,10 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
   LO nkeys = 0;
   LOs keys2edges = collect_marked(state, &nkeys);
   g_stats.nkeys = nkeys;
-  LOs keys_order;
-  LOs edge_order = rep_vertex_order_from_keys(mesh->ask_verts_of(EDGE), mesh->nverts(), nedges, keys2edges, &keys_order);
-  refine_element_based(mesh, keys2edges, edge_order, keys_order, &g_stats);
+  KeyOrder ko;
+  ko.edge_order = rep_vertex_order_from_keys(mesh->ask_verts_of(EDGE), mesh->nverts(), nedges, keys2edges,
+      &ko.keys_order, &ko.vert2keys_off, &ko.vert_keys);
+  refine_element_based(mesh, keys2edges, ko, &g_stats);
   device_error_check("refine_element_based");
   return true;
 }
