@@ -520,8 +520,22 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassSt
     // algorithmic bytes: every new array written once + the old arrays read once
     algo_bytes(int64_t(nnew[d]) * (8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes) +
                int64_t(nold) * (4 + 4 + 8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes));
+    // coarse[i] = old entity representing new slot 256*i: the per-thread search below then
+    // only bisects the (cache-resident) stretch of offsets between two coarse samples
+    LO const ncoarse = nnew[d] / 256 + 2;
+    LOs coarse(ncoarse);
+    LO* cs = coarse.data();
+    LO const nnew_d = nnew[d];
+    parallel_for(ncoarse, OSHB_LAMBDA(LO i) {
+      int64_t slot = int64_t(i) * 256;
+      if (slot > nnew_d - 1) slot = nnew_d - 1;
+      cs[i] = upper_bound(off, nold + 1, LO(slot)) - 1;
+    }, "rebuild(coarse)");
     parallel_for(nnew[d], OSHB_LAMBDA(LO ne) {
-      LO e = upper_bound(off, nold + 1, ne) - 1;  // the old entity that represents this slot
+      // the old entity that represents this slot: last e with off[e] <= ne
+      LO lo = cs[ne >> 8];
+      LO hi = cs[(ne >> 8) + 1];
+      LO e = lo + upper_bound(off + lo + 1, hi - lo, ne);
       LO local = ne - off[e];
       LO s = st ? st[e] : -1;
       if (s == -1 && local == 0) {
