@@ -517,9 +517,6 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassSt
     Topo const t2 = tp;
     int64_t tag_bytes = 0;
     for (int k = 0; k < stab.n; ++k) tag_bytes += stab.t[k].bytes;
-    // algorithmic bytes: every new array written once + the old arrays read once
-    algo_bytes(int64_t(nnew[d]) * (8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes) +
-               int64_t(nold) * (4 + 4 + 8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes));
     // coarse[i] = old entity representing new slot 256*i: the per-thread search below then
     // only bisects the (cache-resident) stretch of offsets between two coarse samples
     LO const ncoarse = nnew[d] / 256 + 2;
@@ -531,6 +528,9 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassSt
       if (slot > nnew_d - 1) slot = nnew_d - 1;
       cs[i] = upper_bound(off, nold + 1, LO(slot)) - 1;
     }, "rebuild(coarse)");
+    // algorithmic bytes: every new array written once + the old arrays read once
+    algo_bytes(int64_t(nnew[d]) * (8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes) +
+               int64_t(nold) * (4 + 4 + 8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes));
     parallel_for(nnew[d], OSHB_LAMBDA(LO ne) {
       // the old entity that represents this slot: last e with off[e] <= ne
       LO lo = cs[ne >> 8];
