@@ -174,3 +174,87 @@ def check_seeded_adjacencies(rep, m, fx, lib):
 
 def load(path):
     return read_oshd(path)
+
+
+def random_case(seed, dim, n, aniso):
+    """Seeded irregular input for oracle-vs-CUDA parity: a reference-built box fixture whose
+    coordinates are jittered and whose metric is a random graded field (isotropic or SPD)."""
+    rng = np.random.default_rng(seed)
+    return rng
+
+
+def jittered_input(fx, seed, aniso):
+    """copy of a fixture's input mesh with seeded jitter on interior coordinates and a random metric"""
+    rng = np.random.default_rng(seed)
+    out = {k: v.copy() for k, v in fx.items() if k.startswith("in:") or k.startswith("opts:") or k in ("metric_kind", "box_n")}
+    dim = int(fx["in:dim"][0])
+    nv = int(fx["in:nents0"][0])
+    n = int(fx["box_n"][0])
+    x = out["in:tag0:coordinates"].reshape(nv, dim)
+    interior = ((x > 1e-9) & (x < 1 - 1e-9)).all(axis=1)
+    x[interior] += (rng.random((int(interior.sum()), dim)) - 0.5) * (0.3 / n)
+    out["in:tag0:coordinates"] = x.reshape(-1)
+    h = (0.35 + 0.5 * rng.random(nv)) / n
+    if not aniso:
+        out["in:tag0:metric"] = 1.0 / h ** 2
+        out["in:tag0:metric:ncomps"] = np.array([1], dtype=np.int64)
+    else:
+        # random SPD tensors: R diag(1/h_i^2) R^T with distinct h_i
+        ms = []
+        for v in range(nv):
+            a = rng.standard_normal((dim, dim))
+            q, _ = np.linalg.qr(a)
+            hh = h[v] * (1.0 + np.arange(dim) * 0.6 + 0.2 * rng.random(dim))
+            m = q @ np.diag(1.0 / hh ** 2) @ q.T
+            m = 0.5 * (m + m.T)
+            ms.append([m[0, 0], m[1, 1], m[0, 1]] if dim == 2 else [m[0, 0], m[1, 1], m[2, 2], m[0, 1], m[1, 2], m[0, 2]])
+        out["in:tag0:metric"] = np.array(ms).reshape(-1)
+        out["in:tag0:metric:ncomps"] = np.array([3 if dim == 2 else 6], dtype=np.int64)
+    for k in list(out):
+        if k.startswith("in:tag1:length") or k.startswith("in:tag%d:quality" % dim):
+            del out[k]
+    return out
+
+
+def check_against_oracle(fx_in, lib, rtol=RTOL, npasses=3):
+    """CUDA (or emulation) path vs oracle/oracle_np.py on the same seeded input, pass after pass."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_np as onp
+    from omega_h_b200 import AdaptOpts, refine_by_size
+    rep = Report()
+    m = mesh_from_fixture(fx_in, lib)
+    om = onp.mesh_from_fixture(fx_in)
+    opts = AdaptOpts(m)
+    m.ask_lengths()
+    m.ask_qualities()
+    dim = om.dim
+    om.add_tag(1, "length", 1, onp.measure_edges_metric(om, np.arange(om.nents[1], dtype=np.int32)))
+    om.add_tag(dim, "quality", 1, onp.measure_qualities(om, np.arange(om.nents[dim], dtype=np.int32)))
+    rep.close("length", m.get_array(1, "length"), om.get(1, "length"), rtol)
+    rep.close("quality", m.get_array(dim, "quality"), om.get(dim, "quality"), rtol)
+    for p in range(npasses):
+        did = refine_by_size(m, opts)
+        new, info = onp.refine_by_size(om, opts.max_length_desired, opts.min_quality_allowed)
+        rep.eq("pass%d did" % p, int(did), int(new is not None))
+        if not did or new is None:
+            break
+        om = new
+        for d in range(dim + 1):
+            rep.eq("pass%d nents%d" % (p, d), m.nents(d), om.nents[d])
+        if rep.fail:
+            break
+        for d in range(1, dim + 1):
+            ab2b, codes = m.ask_down(d, d - 1)
+            rep.eq("pass%d down%d" % (p, d), ab2b, om.down[d][0])
+            if d > 1:
+                rep.eq("pass%d codes%d" % (p, d), codes, om.down[d][1])
+        for d in range(dim + 1):
+            for name, (nc, arr) in om.tags[d].items():
+                a = m.get_array(d, name)
+                if arr.dtype == np.float64:
+                    rep.close("pass%d tag%d:%s" % (p, d, name), a, arr, rtol)
+                else:
+                    rep.eq("pass%d tag%d:%s" % (p, d, name), a, arr)
+    return rep

@@ -73,3 +73,13 @@ def test_build_box_matches_reference(emu_lib, ref_driver, tmp_path, dim, n):
     parity.compare_mesh(rep, m, fx, "in:")
     parity.compare_derived(rep, m, fx)
     rep.assert_ok()
+
+
+@pytest.mark.parametrize("fixture,seed,aniso", [("d3n3m0_pass0", 11, False), ("d3n4m2_pass0", 12, True),
+                                               ("d2n6m1_pass0", 13, True), ("d2n6m2_pass0", 14, False)])
+def test_against_oracle_on_jittered_inputs(emu_lib, fixture, seed, aniso):
+    """irregular seeded inputs (jittered coordinates, random graded metric): kernel bodies vs the
+    numpy/C oracle, three passes chained"""
+    fx = parity.load(os.path.join(parity.HERE, "golden", fixture + ".oshd.gz"))
+    rep = parity.check_against_oracle(parity.jittered_input(fx, seed, aniso), emu_lib)
+    rep.assert_ok()

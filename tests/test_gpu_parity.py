@@ -126,6 +126,18 @@ def test_full_size_loop_properties(gpu_lib):
         assert inside.all()
 
 
+@pytest.mark.parametrize("fixture,seed,aniso", [("d3n3m0_pass0", 21, False), ("d3n4m2_pass0", 22, True),
+                                               ("d2n6m1_pass0", 23, True), ("d2n6m2_pass0", 24, False),
+                                               ("d3n4m3_pass0", 25, False)])
+def test_against_oracle_on_jittered_inputs(gpu_lib, fixture, seed, aniso):
+    """irregular seeded inputs (jittered coordinates, random graded metric): CUDA path vs the
+    numpy/C oracle (oracle/oracle_np.py), three passes chained"""
+    fx = parity.load(os.path.join(parity.HERE, "golden", fixture + ".oshd.gz"))
+    rep = parity.check_against_oracle(parity.jittered_input(fx, seed, aniso), gpu_lib,
+                                      rtol=ANISO_RTOL if aniso else parity.RTOL)
+    rep.assert_ok()
+
+
 # ---- array primitives against numpy -----------------------------------------------------------
 @pytest.mark.parametrize("n", [0, 1, 31, 4096, 4097, 1_000_003, 20_000_000])
 @pytest.mark.parametrize("dtype", [np.int8, np.int32])
