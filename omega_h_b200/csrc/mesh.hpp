@@ -153,8 +153,20 @@ struct KeyOrder {
   LOs vert2keys_off;  // CSR first vertex -> keys (nverts + 1)
   LOs vert_keys;      // keys of each first vertex in increasing rank
 };
+// everything the selection half hands to the rebuild half
+struct Selection {
+  LOs keys2edges;
+  KeyOrder order;
+  Adj key_faces;   // key -> triangles around it: the key edge's E->F row (sorted, with upward codes)
+  Adj key_tets;    // key -> tets around it: the key edge's E->R row (3-D only)
+  LOs face2key;    // per triangle: the key whose cavity contains it, or -1
+  LOs tet2key;     // per tet (3-D only)
+  Reals edge_mid_metrics;  // log-Euclidean midpoint metric per EDGE, valid on candidate edges
+};
 struct PassStats;
-void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassStats* stats);  // rebuild.cu
+void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats);  // rebuild.cu
+LOs rep_vertex_order_from_keys(LOs ev2v, LO nverts, LO nedges, LOs keys2edges, LOs* keys_order_out,
+    LOs* vert2keys_off_out, LOs* vert_keys_out);  // refine.cu
 
 struct PassStats {
   LO ncands = 0, nkeys = 0, indset_rounds = 0;

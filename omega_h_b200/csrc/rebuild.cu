@@ -101,10 +101,9 @@ OSHB_HD int find_in_row(LO const* row, LO n, LO what) {
 // one product TRIANGLE: t < 2*nf: pair (face t/2, endpoint t%2 removed); else cut of tet t-2*nf.
 // Emits vertices and the three bounding edges with codes.
 OSHB_HD void product_tri(Topo const& tp, LO key, LO t, LO* verts, LO* lows, I8* codes) {
-  LO e = tp.k2e[key];
   LO M = tp.pbase[0][key];
-  LO fb = tp.ef_off[e];
-  LO nf = tp.ef_off[e + 1] - fb;
+  LO fb = tp.ef_off[key];
+  LO nf = tp.ef_off[key + 1] - fb;
   LO pb1 = tp.pbase[1][key];
   LO const* ov2nv = tp.o2n[0];
   LO const* oe2ne = tp.o2n[1];
@@ -142,7 +141,7 @@ OSHB_HD void product_tri(Topo const& tp, LO key, LO t, LO* verts, LO* lows, I8* 
     }
   } else {
     LO j = t - 2 * nf;
-    LO er = tp.er_off[e] + j;
+    LO er = tp.er_off[key] + j;
     LO r = tp.er_ents[er];
     int rre = code_which_down(tp.er_codes[er]);
     int ddt = simplex_opposite_template(3, EDGE, rre);  // the tip edge
@@ -168,13 +167,12 @@ OSHB_HD void product_tri(Topo const& tp, LO key, LO t, LO* verts, LO* lows, I8* 
 // one product TET: pair (tet j, endpoint eev removed). Emits vertices and the four bounding
 // triangles with codes.
 OSHB_HD void product_tet(Topo const& tp, LO key, int j, int eev, LO* verts, LO* lows, I8* codes) {
-  LO e = tp.k2e[key];
   LO M = tp.pbase[0][key];
-  LO fb = tp.ef_off[e];
-  LO nf = tp.ef_off[e + 1] - fb;
+  LO fb = tp.ef_off[key];
+  LO nf = tp.ef_off[key + 1] - fb;
   LO pb2 = tp.pbase[2][key];
   LO const* ov2nv = tp.o2n[0];
-  LO er = tp.er_off[e] + j;
+  LO er = tp.er_off[key] + j;
   LO r = tp.er_ents[er];
   I8 code = tp.er_codes[er];
   int rre = code_which_down(code);
@@ -282,9 +280,8 @@ OSHB_HD LO upper_bound(LO const* off, LO n, LO x) {
 }
 
 OSHB_HD LO key_nprods(Topo const& tp, int ent_dim, LO key) {
-  LO e = tp.k2e[key];
-  LO nf = tp.ef_off[e + 1] - tp.ef_off[e];
-  LO nr = tp.er_off ? (tp.er_off[e + 1] - tp.er_off[e]) : 0;
+  LO nf = tp.ef_off[key + 1] - tp.ef_off[key];
+  LO nr = tp.er_off ? (tp.er_off[key + 1] - tp.er_off[key]) : 0;
   if (ent_dim == VERT) return 1;
   if (ent_dim == EDGE) return 2 + nf;
   if (ent_dim == FACE) return 2 * nf + nr;
@@ -294,21 +291,24 @@ OSHB_HD LO key_nprods(Topo const& tp, int ent_dim, LO key) {
 // ---------------------------------------------------------------------------------------
 // refine_element_based
 // ---------------------------------------------------------------------------------------
-void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassStats* stats) {
+void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
+  LOs keys2edges = sel.keys2edges;
+  KeyOrder const& ko = sel.order;
   int const dim = mesh->dim();
   LO const nkeys = LO(keys2edges.size());
   LO const* k2e = keys2edges.data();
   Mesh new_mesh = mesh->copy_meta();
   LOs ev2v_old = mesh->ask_verts_of(EDGE);
   LO const* ev2v = ev2v_old.data();
-  Adj e2f = mesh->ask_up(EDGE, FACE);
+  // key-indexed cavity rows (the key edges' E->F / E->R rows), built by the selection half
+  Adj e2f = sel.key_faces;
   Adj e2r;
   Adj f2e = mesh->ask_down(FACE, EDGE);
   LOs fv2v = mesh->ask_verts_of(FACE);
   Adj r2f, r2e;
   LOs rv2v;
   if (dim == 3) {
-    e2r = mesh->ask_up(EDGE, REGION);
+    e2r = sel.key_tets;
     r2f = mesh->ask_down(REGION, FACE);
     r2e = mesh->ask_down(REGION, EDGE);
     rv2v = mesh->ask_verts_of(REGION);
@@ -354,15 +354,15 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassSt
       if (ent_dim == EDGE) {
         parallel_for(nkeys, OSHB_LAMBDA(LO key) { st[k2e[key]] = key; }, "status(edge)");
       } else {
+        // every entity of a key's cavity dies; the first of the key's (sorted) row represents it
         Adj const& e2d = (ent_dim == FACE) ? e2f : e2r;
         LO const* d_off = e2d.a2ab.data();
         LO const* d_ents = e2d.ab2b.data();
-        // two launches so that the representative ends with its key, not with -2
-        parallel_for(nkeys, OSHB_LAMBDA(LO key) {
-          LO e = k2e[key];
-          for (LO ed = d_off[e]; ed < d_off[e + 1]; ++ed) st[d_ents[ed]] = -2;
-        }, "status(dead)");
-        parallel_for(nkeys, OSHB_LAMBDA(LO key) { st[d_ents[d_off[k2e[key]]]] = key; }, "status(rep)");
+        LO const* ent2key = (ent_dim == FACE) ? sel.face2key.data() : sel.tet2key.data();
+        parallel_for(nold, OSHB_LAMBDA(LO e) {
+          LO key = ent2key[e];
+          if (key >= 0) st[e] = (d_ents[d_off[key]] == e) ? key : -2;
+        }, "status(cavity)");
       }
     }
     // representative counts (get_rep_counts, src/Omega_h_modify.cpp:178-243)
@@ -413,7 +413,7 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassSt
         pb[key] = off[rep] + kord[key] + 1;
         gb[key] = lg[og[rep]] + eord[e] + 1;
       } else {
-        LO rep = (ent_dim == EDGE) ? e : d_ents[d_off[e]];
+        LO rep = (ent_dim == EDGE) ? e : d_ents[d_off[key]];
         pb[key] = off[rep];
         gb[key] = lg[og[rep]];
       }
@@ -565,8 +565,8 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassSt
       LO t = local;
       LO ke = t2.k2e[key];
       ng[ne] = t2.gbase[d][key] + t;
-      LO fb = t2.ef_off[ke];
-      LO nf = t2.ef_off[ke + 1] - fb;
+      LO fb = t2.ef_off[key];
+      LO nf = t2.ef_off[key + 1] - fb;
       if (d == EDGE) {
         LO M = t2.pbase[0][key];
         if (t < 2) {
@@ -598,7 +598,7 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassSt
           LO f = t2.ef_ents[fb + (t >> 1)];
           for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src, f, itab.t[k].bytes);
         } else {
-          LO r = t2.er_ents[t2.er_off[ke] + (t - 2 * nf)];
+          LO r = t2.er_ents[t2.er_off[key] + (t - 2 * nf)];
           for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src_up, r, itab.t[k].bytes);
         }
       } else {
@@ -611,7 +611,7 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassSt
           nc[int64_t(ne) * 4 + k] = codes[k];
           nvo[int64_t(ne) * 4 + k] = verts[k];
         }
-        LO r = t2.er_ents[t2.er_off[ke] + (t >> 1)];
+        LO r = t2.er_ents[t2.er_off[key] + (t >> 1)];
         for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src, r, itab.t[k].bytes);
       }
     }, "rebuild(gather)");
@@ -669,8 +669,19 @@ void refine_element_based(Mesh* mesh, LOs keys2edges, KeyOrder const& ko, PassSt
       }, "transfer_linear_interp");
     } else if (s.kind == 2) {
       // transfer_metric (src/Omega_h_transfer.cpp:198-210)
-      Reals prod = get_mident_metrics(mesh, EDGE, keys2edges, s.old_tag.f64);
-      scatter_by<Real>(prod.data(), nt.f64.data(), pb0, nkeys, ncp);
+      if (s.old_tag.name == "metric" && sel.edge_mid_metrics.exists()) {
+        // the midpoint metrics of the key edges were already computed for the cavity qualities
+        Real const* em = sel.edge_mid_metrics.data();
+        Real* ndp = nt.f64.data();
+        parallel_for(int64_t(nkeys) * ncp, OSHB_LAMBDA(LO i) {
+          LO key = i / ncp;
+          int c = i - key * ncp;
+          ndp[int64_t(pb0[key]) * ncp + c] = em[int64_t(k2e[key]) * ncp + c];
+        }, "transfer_metric(reuse)");
+      } else {
+        Reals prod = get_mident_metrics(mesh, EDGE, keys2edges, s.old_tag.f64);
+        scatter_by<Real>(prod.data(), nt.f64.data(), pb0, nkeys, ncp);
+      }
     }
   }
   for (auto const& s : specials[EDGE]) {

@@ -1,15 +1,11 @@
-// refine_by_size and the selection half of the pass: candidates, cavity qualities,
-// independent set, key ordering (src/Omega_h_refine.cpp:17-41,92-100,
+// Stand-alone selection primitives of the ABI: per-edge find_indset and the key ordering
+// (src/Omega_h_refine.cpp:17-41,
 // src/Omega_h_indset*.{hpp,cpp}, src/Omega_h_modify.cpp:269-338; SURVEY.md 8a rows a4,a16,a17).
-// The rebuild half (products, numbering, connectivity, globals, transfer) is rebuild.cu.
+// The pass itself (fused element-centric selection) is select.cu; the rebuild half is rebuild.cu.
 #include "mesh.hpp"
 #include "smallmath.hpp"
 
 namespace oshb {
-
-
-static PassStats g_stats;
-PassStats const& last_pass_stats() { return g_stats; }
 
 enum { NOT_IN = 0, IN = 1, UNKNOWN = 2 };
 
@@ -150,66 +146,6 @@ LOs get_rep2md_order_adapt(Mesh* mesh, int key_dim, int rep_dim, Bytes kds_are_k
   LOs keys2edges = collect_marked(kds_are_keys);
   return rep_vertex_order_from_keys(
       mesh->ask_verts_of(EDGE), mesh->nverts(), mesh->nedges(), keys2edges, nullptr, nullptr, nullptr);
-}
-
-// ---------------------------------------------------------------------------------------
-// refine_by_size (src/Omega_h_refine.cpp:92-100) -> refine_ghosted (:17-41, one rank)
-// -> refine_element_based (rebuild.cu)
-// ---------------------------------------------------------------------------------------
-bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
-  device_error_reset();
-  g_stats = PassStats();
-  for (int d = 0; d <= mesh->dim(); ++d) g_stats.nents_before[d] = g_stats.nents_after[d] = mesh->nents(d);
-  LO const nedges = mesh->nedges();
-  Reals lengths = mesh->ask_lengths();
-  Bytes edge_is_cand(nedges);
-  {
-    Real const* len = lengths.data();
-    I8* m = edge_is_cand.data();
-    Real const maxlen = opts.max_length_desired;
-    parallel_for(nedges, OSHB_LAMBDA(LO e) { m[e] = (len[e] > maxlen) ? 1 : 0; }, "each_gt");
-  }
-  LO ncands = 0;
-  LOs cands2edges = collect_marked(edge_is_cand, &ncands);
-  g_stats.ncands = ncands;
-  if (ncands == 0) return false;
-  Reals cand_quals = refine_qualities(mesh, cands2edges);
-  // each_geq_to + get_max + the two map_onto of refine_ghosted in one sweep over candidates
-  Bytes edges_are_initial = filled<I8>(nedges, 0);
-  Reals edge_quals = filled<Real>(nedges, 0.0);
-  int* flag = reinterpret_cast<int*>(static_cast<char*>(ctx().dscratch) + 1152);
-  {
-    int z = 0;
-    h2d(flag, &z, sizeof(int));
-    Real const* cq = cand_quals.data();
-    LO const* c2e = cands2edges.data();
-    I8* init = edges_are_initial.data();
-    Real* eq = edge_quals.data();
-    Real const minq = opts.min_quality_allowed;
-    parallel_for(ncands, OSHB_LAMBDA(LO c) {
-      LO e = c2e[c];
-      Real q = cq[c];
-      bool good = (q >= minq);
-      init[e] = good ? 1 : 0;
-      eq[e] = q;
-      if (good) atomic_or_i32(flag, 1);
-    }, "cands_are_good");
-  }
-  if (read_scalar(flag) == 0) return false;
-  device_error_check("refine_qualities");
-  int rounds = 0;
-  Bytes state = find_indset(mesh, EDGE, edge_quals, edges_are_initial, &rounds);
-  g_stats.indset_rounds = rounds;
-  // state is NOT_IN(0)/IN(1) once no UNKNOWN is left: it is the key mark array
-  LO nkeys = 0;
-  LOs keys2edges = collect_marked(state, &nkeys);
-  g_stats.nkeys = nkeys;
-  KeyOrder ko;
-  ko.edge_order = rep_vertex_order_from_keys(mesh->ask_verts_of(EDGE), mesh->nverts(), nedges, keys2edges,
-      &ko.keys_order, &ko.vert2keys_off, &ko.vert_keys);
-  refine_element_based(mesh, keys2edges, ko, &g_stats);
-  device_error_check("refine_element_based");
-  return true;
 }
 
 }  // namespace oshb

@@ -1,0 +1,364 @@
+// refine_by_size and the SELECTION half of the pass, element-centric
+// (src/Omega_h_refine.cpp:17-41,92-100; SURVEY.md section 8a rows a3,a4,a14-a17).
+//
+// The reference walks upward adjacencies from edges: refine_qualities loops over E->elem rows,
+// find_indset over a materialised edge star (15 entries per edge), refine_products over E->F and
+// E->R rows -- so every pass first inverts F->E and R->E for the WHOLE mesh (invert_adj: atomics,
+// scan, per-row sort; 4.8 ms of a 27 ms loop here, 9 % of the reference's CPU time).
+// Here nothing upward is derived for the whole mesh:
+//  * cavity qualities: one thread per (element, local edge); each evaluates the two children the
+//    split of that edge would create in that element and folds them into the edge's quality
+//    with an atomic min on an order-preserving integer image of the double (min is exact and
+//    order-independent, so the result is bit-identical to the reference's sequential min);
+//  * independent set: one thread per element compares its own edges pairwise (the neighbours of
+//    an edge ARE the other edges of its elements) and ORs "has a chosen neighbour" / "is beaten"
+//    bits into a per-edge flag word; a per-edge pass applies the Jacobi update. Idempotent ORs:
+//    deterministic;
+//  * upward rows are built only for the KEY edges (an independent set: at most one key per
+//    element, so one entry per cavity element): count, scan, claim, per-row sorting network.
+#include "mesh.hpp"
+#include "smallmath.hpp"
+#include "sortnet.hpp"
+
+namespace oshb {
+
+static PassStats g_stats;
+PassStats const& last_pass_stats() { return g_stats; }
+
+enum { NOT_IN = 0, IN = 1, UNKNOWN = 2 };
+
+// order-preserving map double -> uint64 (total order of finite doubles, -0 < +0)
+OSHB_HD unsigned long long ord_of_f64(double x) {
+  unsigned long long u;
+#ifdef OSHB_EMU
+  memcpy(&u, &x, 8);
+#else
+  u = static_cast<unsigned long long>(__double_as_longlong(x));
+#endif
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+OSHB_HD double f64_of_ord(unsigned long long u) {
+  unsigned long long b = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+#ifdef OSHB_EMU
+  double x;
+  memcpy(&x, &b, 8);
+  return x;
+#else
+  return __longlong_as_double(static_cast<long long>(b));
+#endif
+}
+#ifdef OSHB_EMU
+inline void atomic_min_u64(unsigned long long* p, unsigned long long v) {
+  if (v < *p) *p = v;
+}
+#else
+__device__ __forceinline__ void atomic_min_u64(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
+#endif
+
+// ---------------------------------------------------------------------------------------
+// midpoint metrics of the candidate edges, stored per EDGE (get_mident_metrics,
+// src/Omega_h_metric.cpp:56-99); reused by transfer_metric for the key edges, as the TODO at
+// src/Omega_h_refine_qualities.cpp:18-20 suggests
+// ---------------------------------------------------------------------------------------
+template <int mdim>
+static Reals edge_midpoint_metrics(LO const* ev2v, Real const* v2m, I8 const* cand, LO nedges) {
+  Reals out(int64_t(nedges) * Symm<mdim>::ncomps);
+  Real* o = out.data();
+  int* err = device_error_cell();
+  parallel_for(nedges, OSHB_LAMBDA(LO e) {
+    if (!cand[e]) return;
+    Mat<mdim> ms[2];
+    ms[0] = Symm<mdim>::get(v2m, ev2v[int64_t(e) * 2 + 0]);
+    ms[1] = Symm<mdim>::get(v2m, ev2v[int64_t(e) * 2 + 1]);
+    bool ok = true;
+    Mat<mdim> m = average_metric<mdim, 2>(ms, &ok);
+    if (!ok) atomic_or_i32(err, 2);
+    Symm<mdim>::set(o, e, m);
+  }, "edge_midpoint_metrics");
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------
+// cavity qualities, element-centric (refine_qualities, src/Omega_h_refine_qualities.cpp:34-86)
+// ---------------------------------------------------------------------------------------
+template <int dim, int mdim>
+static void cavity_qualities_tmpl(LO nelems, LO const* ce2e, I8 const* ce_codes, LO const* cv2v, LO const* ev2v,
+    I8 const* cand, Real const* coords, Real const* vert_metrics, Real const* edge_mid, unsigned long long* qord) {
+  constexpr int nce = (dim == 3) ? 6 : 3;
+  algo_bytes(int64_t(nelems) * (nce * 5 + (dim + 1) * 4));
+  parallel_for(int64_t(nelems) * nce, OSHB_LAMBDA(LO i) {
+    LO e = ce2e[i];
+    if (!cand[e]) return;
+    LO c = i / nce;
+    int cce = i - c * nce;
+    int rot = code_rotation(ce_codes[i]);
+    Vec<dim> ep0 = get_vec<dim>(coords, ev2v[int64_t(e) * 2 + 0]);
+    Vec<dim> ep1 = get_vec<dim>(coords, ev2v[int64_t(e) * 2 + 1]);
+    Vec<dim> midp = (ep0 + ep1) / 2.;
+    Mat<mdim> midm = Symm<mdim>::get(edge_mid, e);
+    LO ccv2v[dim + 1];
+    for (int k = 0; k <= dim; ++k) ccv2v[k] = cv2v[int64_t(c) * (dim + 1) + k];
+    Real minqual = 1.0;
+    for (int eev = 0; eev < 2; ++eev) {
+      int cev = eev ^ rot;
+      int ccv = simplex_down_template(dim, EDGE, cce, cev);
+      int ccs = simplex_opposite_template(dim, VERT, ccv);
+      LO csv2v[dim];
+      Vec<dim> ncp[dim + 1];
+      for (int csv = 0; csv < dim; ++csv) {
+        LO v2 = ccv2v[simplex_down_template(dim, dim - 1, ccs, csv)];
+        csv2v[csv] = v2;
+        ncp[csv] = get_vec<dim>(coords, v2);
+      }
+      ncp[dim] = midp;
+      if (dim == 3) {  // flip_new_elem (src/Omega_h_refine_topology.hpp:35-58)
+        LO tv = csv2v[1];
+        csv2v[1] = csv2v[2];
+        csv2v[2] = tv;
+        Vec<dim> tpp = ncp[1];
+        ncp[1] = ncp[2];
+        ncp[2] = tpp;
+      }
+      Mat<mdim> ms[dim + 1];
+      for (int csv = 0; csv < dim; ++csv) ms[csv] = Symm<mdim>::get(vert_metrics, csv2v[csv]);
+      ms[dim] = midm;
+      Mat<mdim> m = maxdet_metric<mdim, dim + 1>(ms);
+      Real cqual = metric_element_quality<dim, mdim>(ncp, m);
+      minqual = (cqual < minqual) ? cqual : minqual;
+    }
+    atomic_min_u64(&qord[e], ord_of_f64(minqual));
+  }, "cavity_qualities");
+}
+
+// ---------------------------------------------------------------------------------------
+// upward rows of the KEY edges only (the key edges' rows of invert_adj(elem->edge),
+// src/Omega_h_adj.cpp:231-263): entries sorted by element index, upward codes
+// ---------------------------------------------------------------------------------------
+static Adj key_rows(LO nelems, int nce, LO const* ce2e, I8 const* ce_codes, LO const* edge2key, LO nkeys, LOs* elem2key_out) {
+  LOs elem2key(nelems);
+  Bytes elem_k(nelems);
+  LOs counts = filled<LO>(nkeys, 0);
+  LO* e2k = elem2key.data();
+  I8* ek = elem_k.data();
+  LO* cnt = counts.data();
+  parallel_for(nelems, OSHB_LAMBDA(LO c) {
+    LO key = -1;
+    int kk = 0;
+    for (int k = 0; k < nce; ++k) {
+      LO kx = edge2key[ce2e[int64_t(c) * nce + k]];
+      if (kx >= 0) {
+        key = kx;
+        kk = k;
+      }
+    }
+    e2k[c] = key;
+    ek[c] = I8(kk);
+    if (key >= 0) atomic_add(&cnt[key], 1);
+  }, "key_rows(count)");
+  LOs offsets = offset_scan(counts);
+  LO const* off = offsets.data();
+  LO const total = last_of(offsets);
+  LOs ents(total);
+  Bytes codes(total);
+  LO* en = ents.data();
+  I8* co = codes.data();
+  parallel_for(nelems, OSHB_LAMBDA(LO c) {
+    LO key = e2k[c];
+    if (key < 0) return;
+    LO j = atomic_add(&cnt[key], -1);
+    en[off[key] + j - 1] = c;
+  }, "key_rows(fill)");
+  parallel_for(nkeys, OSHB_LAMBDA(LO key) {
+    LO b = off[key];
+    LO len = off[key + 1] - b;
+    sort_small_row(en + b, len);
+    for (LO s = b; s < b + len; ++s) {
+      LO c = en[s];
+      int k = ek[c];
+      I8 dc = ce_codes[int64_t(c) * nce + k];
+      co[s] = make_code(code_is_flipped(dc), code_rotation(dc), k);
+    }
+  }, "key_rows(sort+codes)");
+  Adj a;
+  a.a2ab = offsets;
+  a.ab2b = ents;
+  a.codes = codes;
+  if (elem2key_out) *elem2key_out = elem2key;
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------
+// refine_by_size (src/Omega_h_refine.cpp:92-100) -> refine_ghosted (:17-41, one rank)
+// -> refine_element_based (rebuild.cu)
+// ---------------------------------------------------------------------------------------
+bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
+  device_error_reset();
+  g_stats = PassStats();
+  int const dim = mesh->dim();
+  for (int d = 0; d <= dim; ++d) g_stats.nents_before[d] = g_stats.nents_after[d] = mesh->nents(d);
+  LO const nedges = mesh->nedges();
+  LO const nelems = mesh->nelems();
+  int const nce = simplex_degree(dim, EDGE);
+  Reals lengths = mesh->ask_lengths();
+  int* flags3 = reinterpret_cast<int*>(static_cast<char*>(ctx().dscratch) + 1152);  // 3 ints
+  {
+    int z[3] = {0, 0, 0};
+    h2d(flags3, z, sizeof(z));
+  }
+  // ---- candidates: each_gt(lengths, max_length_desired) + get_max (:95-97)
+  Bytes edge_is_cand(nedges);
+  I8* cand = edge_is_cand.data();
+  {
+    Real const* len = lengths.data();
+    Real const maxlen = opts.max_length_desired;
+    parallel_for(nedges, OSHB_LAMBDA(LO e) {
+      bool c = len[e] > maxlen;
+      cand[e] = c ? 1 : 0;
+      if (c) atomic_or_i32(flags3, 1);
+    }, "each_gt");
+  }
+  if (read_scalar(flags3) == 0) return false;
+  // ---- cavity qualities of the candidates (refine_qualities, :22)
+  Adj c2e = mesh->ask_down(dim, EDGE);
+  LOs cv2v = mesh->ask_verts_of(dim);
+  LOs ev2v = mesh->ask_verts_of(EDGE);
+  Reals coords = mesh->coords();
+  Reals vert_metrics = mesh->get_reals(VERT, "metric");
+  int const ncomps = mesh->metric_ncomps();
+  Selection sel;
+  DArr<GO> qord_a(nedges);
+  unsigned long long* qord = reinterpret_cast<unsigned long long*>(qord_a.data());
+  {
+    unsigned long long const one = ord_of_f64(1.0);
+    parallel_for(nedges, OSHB_LAMBDA(LO e) { qord[e] = one; }, "qualities(init)");
+  }
+#define OSHB_CQ(D, M)                                                                                       \
+  {                                                                                                         \
+    sel.edge_mid_metrics = edge_midpoint_metrics<M>(ev2v.data(), vert_metrics.data(), cand, nedges);        \
+    cavity_qualities_tmpl<D, M>(nelems, c2e.ab2b.data(), c2e.codes.data(), cv2v.data(), ev2v.data(), cand,  \
+        coords.data(), vert_metrics.data(), sel.edge_mid_metrics.data(), qord);                             \
+  }
+  if (dim == 3 && ncomps == 6) OSHB_CQ(3, 3)
+  else if (dim == 2 && ncomps == 3) OSHB_CQ(2, 2)
+  else if (dim == 3 && ncomps == 1) OSHB_CQ(3, 1)
+  else if (dim == 2 && ncomps == 1) OSHB_CQ(2, 1)
+  else fail(__FILE__, __LINE__, "refine_by_size: unsupported (dim, metric ncomps)");
+#undef OSHB_CQ
+  // ---- each_geq_to + get_max + the two map_onto of refine_ghosted (:23-28) in one sweep
+  Bytes state_a(nedges);
+  Reals edge_quals(nedges);
+  I8* state = state_a.data();
+  Real* eq = edge_quals.data();
+  {
+    Real const minq = opts.min_quality_allowed;
+    parallel_for(nedges, OSHB_LAMBDA(LO e) {
+      if (cand[e]) {
+        Real q = f64_of_ord(qord[e]);
+        eq[e] = q;
+        bool good = (q >= minq);
+        state[e] = good ? UNKNOWN : NOT_IN;
+        if (good) atomic_or_i32(flags3 + 1, 1);
+      } else {
+        eq[e] = 0.0;
+        state[e] = NOT_IN;
+      }
+    }, "cands_are_good");
+  }
+  qord_a.reset();
+  if (read_scalar(flags3 + 1) == 0) return false;
+  device_error_check("cavity_qualities");
+  // ---- independent set (find_indset, :29): element-centric Jacobi rounds
+  {
+    GOs globals = mesh->globals(EDGE);
+    GO const* g = globals.data();
+    LO const* ce2e = c2e.ab2b.data();
+    LOs flags = filled<LO>(nedges, 0);
+    LO* fl = flags.data();
+    int* more = flags3 + 2;
+    int rounds = 0;
+    int pending = 1;
+    while (pending) {
+      int z = 0;
+      h2d(more, &z, sizeof(int));
+      parallel_for(nelems, OSHB_LAMBDA(LO c) {
+        LO es[6];
+        I8 st[6];
+        bool any = false;
+        for (int k = 0; k < nce; ++k) {
+          es[k] = ce2e[int64_t(c) * nce + k];
+          st[k] = state[es[k]];
+          any = any || (st[k] == UNKNOWN);
+        }
+        if (!any) return;
+        for (int i = 0; i < nce; ++i) {
+          if (st[i] != UNKNOWN) continue;
+          LO v = es[i];
+          Real vq = eq[v];
+          GO vg = g[v];
+          int f = 0;
+          for (int j = 0; j < nce; ++j) {
+            if (j == i) continue;
+            if (st[j] == IN) {
+              f |= 1;
+            } else if (st[j] == UNKNOWN) {
+              // compare(u, v): u strictly below v in (quality, global id)
+              LO u = es[j];
+              Real uq = eq[u];
+              bool u_lt_v = (uq != vq) ? (uq < vq) : (g[u] < vg);
+              if (!u_lt_v) f |= 2;
+            }
+          }
+          if (f) atomic_or_i32(reinterpret_cast<int*>(fl) + v, f);
+        }
+      }, "indset(elements)");
+      parallel_for(nedges, OSHB_LAMBDA(LO e) {
+        if (state[e] != UNKNOWN) return;
+        int f = fl[e];
+        fl[e] = 0;
+        if (f & 1) {
+          state[e] = NOT_IN;
+        } else if (f & 2) {
+          atomic_or_i32(more, 1);
+        } else {
+          state[e] = IN;
+        }
+      }, "indset(edges)");
+      pending = read_scalar(more);
+      ++rounds;
+      OSHB_CHECK(rounds < 10000);
+    }
+    g_stats.indset_rounds = rounds;
+  }
+  // ---- keys: state is now NOT_IN(0)/IN(1) = the key marks (:30-33)
+  LOs key_scan = offset_scan(state_a);
+  LO const nkeys = last_of(key_scan);
+  g_stats.nkeys = nkeys;
+  sel.keys2edges = LOs(nkeys);
+  LOs edge2key_a(nedges);
+  {
+    LO* k2e = sel.keys2edges.data();
+    LO* e2k = edge2key_a.data();
+    LO const* ks = key_scan.data();
+    parallel_for(nedges, OSHB_LAMBDA(LO e) {
+      if (state[e]) {
+        k2e[ks[e]] = e;
+        e2k[e] = ks[e];
+      } else {
+        e2k[e] = -1;
+      }
+    }, "keys2edges");
+  }
+  sel.order.edge_order = rep_vertex_order_from_keys(ev2v, mesh->nverts(), nedges, sel.keys2edges, &sel.order.keys_order,
+      &sel.order.vert2keys_off, &sel.order.vert_keys);
+  // ---- cavities of the keys
+  Adj f2e = mesh->ask_down(FACE, EDGE);
+  sel.key_faces = key_rows(mesh->nents(FACE), 3, f2e.ab2b.data(), f2e.codes.data(), edge2key_a.data(), nkeys, &sel.face2key);
+  if (dim == 3) {
+    sel.key_tets = key_rows(nelems, 6, c2e.ab2b.data(), c2e.codes.data(), edge2key_a.data(), nkeys, &sel.tet2key);
+  }
+  refine_element_based(mesh, sel, &g_stats);
+  device_error_check("refine_element_based");
+  return true;
+}
+
+}  // namespace oshb
