@@ -347,7 +347,14 @@ def main_b200(args):
         lib.timer_start()
         run_loop(m, opts)
         total = lib.timer_stop()
-        agg = summarize_profile(lib.profile_end())
+        recs = lib.profile_end()
+        agg = summarize_profile(recs)
+        if os.environ.get("OSHB_PROFILE_LAUNCHES"):
+            want = os.environ["OSHB_PROFILE_LAUNCHES"].split(",")
+            for name, ms in recs:
+                nm = name.split("\t")[0]
+                if nm in want:
+                    print("  launch %-28s %9.3f ms  algo bytes %s" % (nm, ms, name.split("\t")[1]), file=sys.stderr)
         ksum = sum(v[1] for v in agg.values())
         print("loop %.3f ms (profiled), kernels %.3f ms, %d launches" % (total, ksum, sum(v[0] for v in agg.values())),
               file=sys.stderr)

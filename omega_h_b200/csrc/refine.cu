@@ -38,7 +38,7 @@ Bytes find_indset(Mesh* mesh, int ent_dim, Reals quality, Bytes candidates, int*
   parallel_for(n, OSHB_LAMBDA(LO i) {
     if (cand[i]) {
       sa[i] = UNKNOWN;
-      atomic_or_i32(flag, 1);
+      raise_flag(flag, 1);
     } else {
       sa[i] = NOT_IN;
     }
@@ -85,7 +85,7 @@ Bytes find_indset(Mesh* mesh, int ent_dim, Reals quality, Bytes candidates, int*
         ns[v] = IN;
       } else {
         ns[v] = UNKNOWN;
-        atomic_or_i32(flag, 1);
+        raise_flag(flag, 1);
       }
     }, "indset(round)");
     Bytes t = cur;

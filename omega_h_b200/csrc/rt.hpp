@@ -163,6 +163,13 @@ void parallel_for(int64_t n, F f, char const* = nullptr) {
   for (int64_t i = 0; i < n; ++i) f(LO(i));
   ctx().launches++;
 }
+template <class F>
+void parallel_for_any(int64_t n, F f, int* cell, int bit, char const* = nullptr) {
+  int any = 0;
+  for (int64_t i = 0; i < n; ++i) any |= f(LO(i)) ? 1 : 0;
+  if (any) *cell |= bit;
+  ctx().launches++;
+}
 OSHB_HD LO atomic_add(LO* p, LO v) {
   LO old = *p;
   *p += v;
@@ -172,6 +179,7 @@ OSHB_HD void atomic_max_i32(int* p, int v) {
   if (v > *p) *p = v;
 }
 OSHB_HD void atomic_or_i32(int* p, int v) { *p |= v; }
+OSHB_HD void raise_flag(int* cell, int v) { *cell |= v; }
 #else
 template <class F>
 __global__ void __launch_bounds__(256) k_for(int64_t n, F f) {
@@ -195,9 +203,48 @@ void parallel_for(int64_t n, F f, char const* name = nullptr) {
   if (c.prof_on) prof_end(name);
   c.launches++;
 }
+// parallel_for whose body returns a bool; the OR over all entities is raised into *cell as `bit`.
+// The reduction is done in registers along the grid-stride loop, then per block
+// (__syncthreads_or), so the global cell sees at most one atomic per CTA (the fused form of
+// the reference's each_* + get_max pairs, src/Omega_h_array_ops.cpp:47-68).
+template <class F>
+__global__ void __launch_bounds__(256) k_for_any(int64_t n, F f, int* cell, int bit) {
+  int64_t stride = int64_t(gridDim.x) * 256;
+  int any = 0;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) any |= f(LO(i)) ? 1 : 0;
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0 && any) atomicOr(cell, bit);
+}
+template <class F>
+void parallel_for_any(int64_t n, F f, int* cell, int bit, char const* name = nullptr) {
+  if (n <= 0) return;
+  Ctx& c = ctx();
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = int64_t(c.sms) * 16;
+  if (blocks > cap) blocks = cap;
+  if (c.prof_on) prof_begin(name);
+  k_for_any<<<unsigned(blocks), 256, 0, c.stream>>>(n, f, cell, bit);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(__FILE__, __LINE__, std::string("kernel launch: ") + cudaGetErrorString(e));
+  if (c.prof_on) prof_end(name);
+  c.launches++;
+}
 __device__ __forceinline__ LO atomic_add(LO* p, LO v) { return atomicAdd(p, v); }
 __device__ __forceinline__ void atomic_max_i32(int* p, int v) { atomicMax(p, v); }
-__device__ __forceinline__ void atomic_or_i32(int* p, int v) { atomicOr(p, v); }
+// idempotent OR on scattered addresses: skip the atomic when the bits are already set
+__device__ __forceinline__ void atomic_or_i32(int* p, int v) {
+  if ((*reinterpret_cast<volatile int*>(p) & v) != v) atomicOr(p, v);
+}
+// raise bits of ONE global cell ("anything left?", "any candidate?") from many threads: one
+// lane per warp looks at the cell, and only touches it while the bits are still clear --
+// millions of threads polling or hitting a single L2 address would serialise on its slice
+__device__ __forceinline__ void raise_flag(int* cell, int v) {
+  unsigned m = __activemask();
+  int lane = threadIdx.x & 31;
+  if (lane == __ffs(m) - 1) {
+    if ((*reinterpret_cast<volatile int*>(cell) & v) != v) atomicOr(cell, v);
+  }
+}
 #endif
 
 // ---- cooperative primitives (prims.cu) -------------------------------------------

@@ -30,22 +30,14 @@ enum { NOT_IN = 0, IN = 1, UNKNOWN = 2 };
 // order-preserving map double -> uint64 (total order of finite doubles, -0 < +0)
 OSHB_HD unsigned long long ord_of_f64(double x) {
   unsigned long long u;
-#ifdef OSHB_EMU
   memcpy(&u, &x, 8);
-#else
-  u = static_cast<unsigned long long>(__double_as_longlong(x));
-#endif
   return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
 }
 OSHB_HD double f64_of_ord(unsigned long long u) {
   unsigned long long b = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
-#ifdef OSHB_EMU
   double x;
   memcpy(&x, &b, 8);
   return x;
-#else
-  return __longlong_as_double(static_cast<long long>(b));
-#endif
 }
 #ifdef OSHB_EMU
 inline void atomic_min_u64(unsigned long long* p, unsigned long long v) {
@@ -85,10 +77,20 @@ template <int dim, int mdim>
 static void cavity_qualities_tmpl(LO nelems, LO const* ce2e, I8 const* ce_codes, LO const* cv2v, LO const* ev2v,
     I8 const* cand, Real const* coords, Real const* vert_metrics, Real const* edge_mid, unsigned long long* qord) {
   constexpr int nce = (dim == 3) ? 6 : 3;
-  algo_bytes(int64_t(nelems) * (nce * 5 + (dim + 1) * 4));
-  parallel_for(int64_t(nelems) * nce, OSHB_LAMBDA(LO i) {
+  int64_t const npairs = int64_t(nelems) * nce;
+  // compact the (element, local edge) pairs whose edge is a candidate: late passes have few
+  // candidates, and the quality evaluation is ~1500 FP64 instructions -- warps must be dense
+  Bytes marks(npairs);
+  I8* mk = marks.data();
+  parallel_for(npairs, OSHB_LAMBDA(LO i) { mk[i] = cand[ce2e[i]]; }, "cavity_pairs(mark)");
+  LOs active = collect_marked(marks);
+  marks.reset();
+  LO const nactive = LO(active.size());
+  LO const* act = active.data();
+  algo_bytes(int64_t(nactive) * (4 + 4 + 1 + (dim + 1) * 4 + 8));
+  parallel_for(nactive, OSHB_LAMBDA(LO a) {
+    LO i = act[a];
     LO e = ce2e[i];
-    if (!cand[e]) return;
     LO c = i / nce;
     int cce = i - c * nce;
     int rot = code_rotation(ce_codes[i]);
@@ -126,7 +128,8 @@ static void cavity_qualities_tmpl(LO nelems, LO const* ce2e, I8 const* ce_codes,
       Real cqual = metric_element_quality<dim, mdim>(ncp, m);
       minqual = (cqual < minqual) ? cqual : minqual;
     }
-    atomic_min_u64(&qord[e], ord_of_f64(minqual));
+    unsigned long long mine = ord_of_f64(minqual);
+    if (mine < qord[e]) atomic_min_u64(&qord[e], mine);  // a stale read only costs an extra atomic
   }, "cavity_qualities");
 }
 
@@ -211,11 +214,11 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
   {
     Real const* len = lengths.data();
     Real const maxlen = opts.max_length_desired;
-    parallel_for(nedges, OSHB_LAMBDA(LO e) {
+    parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool {
       bool c = len[e] > maxlen;
       cand[e] = c ? 1 : 0;
-      if (c) atomic_or_i32(flags3, 1);
-    }, "each_gt");
+      return c;
+    }, flags3, 1, "each_gt");
   }
   if (read_scalar(flags3) == 0) return false;
   // ---- cavity qualities of the candidates (refine_qualities, :22)
@@ -251,18 +254,18 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
   Real* eq = edge_quals.data();
   {
     Real const minq = opts.min_quality_allowed;
-    parallel_for(nedges, OSHB_LAMBDA(LO e) {
+    parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool {
       if (cand[e]) {
         Real q = f64_of_ord(qord[e]);
         eq[e] = q;
         bool good = (q >= minq);
         state[e] = good ? UNKNOWN : NOT_IN;
-        if (good) atomic_or_i32(flags3 + 1, 1);
-      } else {
-        eq[e] = 0.0;
-        state[e] = NOT_IN;
+        return good;
       }
-    }, "cands_are_good");
+      eq[e] = 0.0;
+      state[e] = NOT_IN;
+      return false;
+    }, flags3 + 1, 1, "cands_are_good");
   }
   qord_a.reset();
   if (read_scalar(flags3 + 1) == 0) return false;
@@ -311,19 +314,19 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
           if (f) atomic_or_i32(reinterpret_cast<int*>(fl) + v, f);
         }
       }, "indset(elements)");
-      parallel_for(nedges, OSHB_LAMBDA(LO e) {
-        if (state[e] != UNKNOWN) return;
+      parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool {
+        if (state[e] != UNKNOWN) return false;
         int f = fl[e];
-        fl[e] = 0;
         if (f & 1) {
           state[e] = NOT_IN;
-        } else if (f & 2) {
-          atomic_or_i32(more, 1);
-        } else {
-          state[e] = IN;
+          return false;
         }
-      }, "indset(edges)");
+        if (f & 2) return true;  // still undecided: another round is needed
+        state[e] = IN;
+        return false;
+      }, more, 1, "indset(edges)");
       pending = read_scalar(more);
+      if (pending) dev_memset(fl, 0, size_t(nedges) * sizeof(LO));
       ++rounds;
       OSHB_CHECK(rounds < 10000);
     }
