@@ -102,6 +102,7 @@ void Mesh::add_tag(int d, Tag const& t, bool internal) {
     *old = t;
   else
     tags_[d].push_back(t);
+  if (t.name == "global") globals_state_[d] = 0;
   // user-visible changes of coordinates / metric invalidate the cached measures
   // (react_to_set_tag, src/Omega_h_mesh.cpp:167-177)
   if (!internal && d == VERT && (t.name == "coordinates" || t.name == "metric")) {
@@ -177,6 +178,19 @@ Reals Mesh::ask_qualities() {
     add_tag(dim_, "quality", 1, q, true);
   }
   return get_reals(dim_, "quality");
+}
+
+bool Mesh::globals_are_identity(int d) {
+  if (globals_state_[d] == 0) {
+    GOs g = globals(d);
+    GO const* gp = g.data();
+    int* cell = reinterpret_cast<int*>(static_cast<char*>(ctx().dscratch) + 1216);
+    int z = 0;
+    h2d(cell, &z, sizeof(int));
+    parallel_for_any(nents(d), OSHB_LAMBDA(LO i)->bool { return gp[i] != GO(i); }, cell, 1, "globals_identity");
+    globals_state_[d] = (read_scalar(cell) == 0) ? 1 : 2;
+  }
+  return globals_state_[d] == 1;
 }
 
 Mesh Mesh::copy_meta() const {

@@ -73,6 +73,12 @@ class Mesh {
   bool has_adj_[4][4];
   Adj star_[4];
   bool has_star_[4];
+  // 0 = not checked, 1 = global[i] == i for every entity, 2 = general numbering.
+  // With identity globals the linear-partition rendezvous of modify_globals
+  // (src/Omega_h_modify.cpp:406-444) reproduces the local scan, so new globals are again the
+  // identity and the refine pass skips that scan; verified on the device, never assumed.
+  int globals_state_[4] = {0, 0, 0, 0};
+  bool globals_are_identity(int d);
 
   Mesh();
   int dim() const { return dim_; }
@@ -159,6 +165,7 @@ struct Selection {
   KeyOrder order;
   Adj key_faces;   // key -> triangles around it: the key edge's E->F row (sorted, with upward codes)
   Adj key_tets;    // key -> tets around it: the key edge's E->R row (3-D only)
+  LOs edge2key;    // per edge: its key index, or -1
   LOs face2key;    // per triangle: the key whose cavity contains it, or -1
   LOs tet2key;     // per tet (3-D only)
   Reals edge_mid_metrics;  // log-Euclidean midpoint metric per EDGE, valid on candidate edges

@@ -86,23 +86,39 @@ __global__ void __launch_bounds__(SCAN_T) k_scan(Tin const* __restrict__ in, Tac
   __syncthreads();
   unsigned const tile = s_tile;
   int64_t const base = int64_t(tile) * SCAN_TILE;
-  // coalesced (striped) load into padded shared memory
-#pragma unroll
-  for (int j = 0; j < SCAN_I; ++j) {
-    int const k = j * SCAN_T + t;
-    int64_t const g = base + k;
-    Tacc v = 0;
-    if (g < n) v = Tacc(in[g]);
-    s_vals[pad17(k)] = v;
-  }
-  __syncthreads();
   // blocked: thread t owns items [16t, 16t+16)
   Tacc loc[SCAN_I];
   Tacc sum = 0;
+  bool const full = (base + SCAN_TILE <= n) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  if (full) {
+    // full tile: each thread reads its 16 items as 16-byte vectors (one LDG.128 per 16/sizeof(Tin) items)
+    constexpr int NV = int(sizeof(Tin));  // number of int4 per thread
+    int4 v[NV];
+    int4 const* p = reinterpret_cast<int4 const*>(in + base + t * SCAN_I);
 #pragma unroll
-  for (int j = 0; j < SCAN_I; ++j) {
-    loc[j] = s_vals[pad17(t * SCAN_I + j)];
-    sum += loc[j];
+    for (int j = 0; j < NV; ++j) v[j] = p[j];
+    Tin const* items = reinterpret_cast<Tin const*>(v);
+#pragma unroll
+    for (int j = 0; j < SCAN_I; ++j) {
+      loc[j] = Tacc(items[j]);
+      sum += loc[j];
+    }
+  } else {
+    // ragged tile: coalesced (striped) load into padded shared memory, then blocked read
+#pragma unroll
+    for (int j = 0; j < SCAN_I; ++j) {
+      int const k = j * SCAN_T + t;
+      int64_t const g = base + k;
+      Tacc v = 0;
+      if (g < n) v = Tacc(in[g]);
+      s_vals[pad17(k)] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SCAN_I; ++j) {
+      loc[j] = s_vals[pad17(t * SCAN_I + j)];
+      sum += loc[j];
+    }
   }
   // inclusive warp scan of thread sums
   Tacc incl = sum;

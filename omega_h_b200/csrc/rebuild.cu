@@ -116,7 +116,7 @@ OSHB_HD void product_tri(Topo const& tp, LO key, LO t, LO* verts, LO* lows, I8* 
     int dev = eev ^ rot;
     int ddv = simplex_down_template(2, EDGE, dde, dev);  // face-local index of the removed key endpoint
     int dds = simplex_opposite_template(2, VERT, ddv);   // face-local edge that survives
-    int l0 = dds, l1 = (dds + 1) % 3;
+    int l0 = dds, l1 = mod_small(dds + 1, 3);
     verts[0] = ov2nv[tp.fv2v[int64_t(f) * 3 + l0]];
     verts[1] = ov2nv[tp.fv2v[int64_t(f) * 3 + l1]];
     verts[2] = M;
@@ -202,7 +202,7 @@ OSHB_HD void product_tet(Topo const& tp, LO key, int j, int eev, LO* verts, LO* 
   int const ya[3] = {0, 2, 1};
   for (int k = 0; k < 3; ++k) {
     int la = l[ya[k]];
-    int lb = l[ya[(k + 1) % 3]];
+    int lb = l[ya[mod_small(k + 1, 3)]];
     LO ua = x[ya[k]];  // old id of the use's first vertex
     if (la != Kl && lb != Kl) {
       // the tip edge + M: the cut triangle of this tet, stored (p, q, M)
@@ -342,40 +342,44 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
   // (get_mods2reps, src/Omega_h_modify.cpp:141-176: the key itself for edges, the first upward
   //  adjacent entity for triangles / tets; for vertices the key's first vertex, which survives)
   LOs old2new[4], pbase[4], offsets[4], status[4];
+  bool identity[4] = {false, false, false, false};
   GOs gbase[4], new_globals[4], lin_globals[4];
   LO nnew[4] = {0, 0, 0, 0};
   for (int ent_dim = 0; ent_dim <= dim; ++ent_dim) {
     LO const nold = mesh->nents(ent_dim);
     Topo const t1 = tp;
+    // status + representative counts in one sweep (get_mods2reps / get_rep_counts,
+    // src/Omega_h_modify.cpp:141-243)
     LO* st = nullptr;
+    LO const* ent2key = nullptr;
+    LO const* row_off = nullptr;
+    LO const* row_ents = nullptr;
     if (ent_dim >= EDGE) {
-      status[ent_dim] = filled<LO>(nold, -1);
+      status[ent_dim] = LOs(nold);
       st = status[ent_dim].data();
       if (ent_dim == EDGE) {
-        parallel_for(nkeys, OSHB_LAMBDA(LO key) { st[k2e[key]] = key; }, "status(edge)");
+        ent2key = sel.edge2key.data();
       } else {
         // every entity of a key's cavity dies; the first of the key's (sorted) row represents it
         Adj const& e2d = (ent_dim == FACE) ? e2f : e2r;
-        LO const* d_off = e2d.a2ab.data();
-        LO const* d_ents = e2d.ab2b.data();
-        LO const* ent2key = (ent_dim == FACE) ? sel.face2key.data() : sel.tet2key.data();
-        parallel_for(nold, OSHB_LAMBDA(LO e) {
-          LO key = ent2key[e];
-          if (key >= 0) st[e] = (d_ents[d_off[key]] == e) ? key : -2;
-        }, "status(cavity)");
+        row_off = e2d.a2ab.data();
+        row_ents = e2d.ab2b.data();
+        ent2key = (ent_dim == FACE) ? sel.face2key.data() : sel.tet2key.data();
       }
     }
-    // representative counts (get_rep_counts, src/Omega_h_modify.cpp:178-243)
     LOs rep_counts(nold);
     LO* rc = rep_counts.data();
     parallel_for(nold, OSHB_LAMBDA(LO e) {
       if (ent_dim == VERT) {
         rc[e] = 1 + (voff[e + 1] - voff[e]);
-      } else {
-        LO s = st[e];
-        rc[e] = (s == -1) ? 1 : ((s == -2) ? 0 : key_nprods(t1, ent_dim, s));
+        return;
       }
-    }, "rep_counts");
+      LO key = ent2key[e];
+      LO s = -1;
+      if (key >= 0) s = (ent_dim == EDGE || row_ents[row_off[key]] == e) ? key : -2;
+      st[e] = s;
+      rc[e] = (s == -1) ? 1 : ((s == -2) ? 0 : key_nprods(t1, ent_dim, s));
+    }, "status+rep_counts");
     offsets[ent_dim] = offset_scan(rep_counts);
     rep_counts.reset();
     LO const* off = offsets[ent_dim].data();
@@ -384,10 +388,16 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
     LO* o2n = old2new[ent_dim].data();
     // globals of the old entities on the linear partition (modify_globals,
     // src/Omega_h_modify.cpp:406-444); one rank: exchange = identity, rescan = exclusive scan
+    // With identity globals (verified on the device by Mesh::globals_are_identity) the scan over
+    // the linear partition IS the local scan: new global = new local index, nothing to compute.
+    bool const ident = mesh->globals_are_identity(ent_dim);
+    identity[ent_dim] = ident;
     GOs old_globals = mesh->globals(ent_dim);
     GO const* og = old_globals.data();
-    lin_globals[ent_dim] = GOs(int64_t(nold) + 1);
-    {
+    if (ident) {
+      parallel_for(nold, OSHB_LAMBDA(LO e) { o2n[e] = (st && st[e] != -1) ? -1 : off[e]; }, "old2new");
+    } else {
+      lin_globals[ent_dim] = GOs(int64_t(nold) + 1);
       LOs lin_counts(nold);
       LO* lc = lin_counts.data();
       parallel_for(nold, OSHB_LAMBDA(LO e) {
@@ -396,7 +406,7 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
       }, "old2new+to_lin");
       scan_offsets(lin_counts.data(), nold, lin_globals[ent_dim].data());
     }
-    GO const* lg = lin_globals[ent_dim].data();
+    GO const* lg = ident ? nullptr : lin_globals[ent_dim].data();
     pbase[ent_dim] = LOs(nkeys);
     gbase[ent_dim] = GOs(nkeys);
     LO* pb = pbase[ent_dim].data();
@@ -411,11 +421,11 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
       if (ent_dim == VERT) {
         LO rep = ev2v[int64_t(e) * 2];
         pb[key] = off[rep] + kord[key] + 1;
-        gb[key] = lg[og[rep]] + eord[e] + 1;
+        gb[key] = (ident ? GO(off[rep]) : lg[og[rep]]) + eord[e] + 1;
       } else {
         LO rep = (ent_dim == EDGE) ? e : d_ents[d_off[key]];
         pb[key] = off[rep];
-        gb[key] = lg[og[rep]];
+        gb[key] = ident ? GO(off[rep]) : lg[og[rep]];
       }
     }, "prod_bases");
     new_globals[ent_dim] = GOs(nnew[ent_dim]);
@@ -510,7 +520,8 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
     GO* ng = tp.ng[d];
     GOs ogs = mesh->globals(d);
     GO const* og = ogs.data();
-    GO const* lg = lin_globals[d].data();
+    bool const ident = identity[d];
+    GO const* lg = ident ? nullptr : lin_globals[d].data();
     I8* pm = prod_marks[d].exists() ? prod_marks[d].data() : nullptr;
     TagTable const stab = same_tab[d];
     TagTable const itab = inh_tab[d];
@@ -541,7 +552,7 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
       if (s == -1 && local == 0) {
         // a surviving entity keeps its place: remapped row, codes, vertices, global, tags
         // (modify_conn / transfer_common2, src/Omega_h_modify.cpp:20-70, Omega_h_transfer.cpp:160-170)
-        ng[ne] = lg[og[e]];
+        ng[ne] = ident ? GO(ne) : lg[og[e]];
         for (int k = 0; k < deg; ++k) {
           nd[int64_t(ne) * deg + k] = ol2nl[od[int64_t(e) * deg + k]];
           if (nc) nc[int64_t(ne) * deg + k] = oc[int64_t(e) * deg + k];
@@ -644,6 +655,7 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
   }
   for (int d = 0; d <= dim; ++d) {
     new_mesh.add_tag(d, "global", 1, new_globals[d], true);
+    if (identity[d]) new_mesh.globals_state_[d] = 1;  // products are numbered base + t = their new index
     for (auto const& nt : new_tags[d]) new_mesh.add_tag(d, nt, true);
   }
 

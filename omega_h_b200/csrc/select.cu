@@ -337,7 +337,8 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
   LO const nkeys = last_of(key_scan);
   g_stats.nkeys = nkeys;
   sel.keys2edges = LOs(nkeys);
-  LOs edge2key_a(nedges);
+  sel.edge2key = LOs(nedges);
+  LOs edge2key_a = sel.edge2key;
   {
     LO* k2e = sel.keys2edges.data();
     LO* e2k = edge2key_a.data();

@@ -183,7 +183,7 @@ def random_case(seed, dim, n, aniso):
     return rng
 
 
-def jittered_input(fx, seed, aniso):
+def jittered_input(fx, seed, aniso, permute_globals=False):
     """copy of a fixture's input mesh with seeded jitter on interior coordinates and a random metric"""
     rng = np.random.default_rng(seed)
     out = {k: v.copy() for k, v in fx.items() if k.startswith("in:") or k.startswith("opts:") or k in ("metric_kind", "box_n")}
@@ -210,6 +210,11 @@ def jittered_input(fx, seed, aniso):
             ms.append([m[0, 0], m[1, 1], m[0, 1]] if dim == 2 else [m[0, 0], m[1, 1], m[2, 2], m[0, 1], m[1, 2], m[0, 2]])
         out["in:tag0:metric"] = np.array(ms).reshape(-1)
         out["in:tag0:metric:ncomps"] = np.array([3 if dim == 2 else 6], dtype=np.int64)
+    if permute_globals:
+        # general (non-identity) global numbering exercises the linear-partition scan of modify_globals
+        for d in range(dim + 1):
+            n = int(fx["in:nents%d" % d][0])
+            out["in:tag%d:global" % d] = rng.permutation(n).astype(np.int64)
     for k in list(out):
         if k.startswith("in:tag1:length") or k.startswith("in:tag%d:quality" % dim):
             del out[k]

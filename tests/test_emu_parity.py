@@ -83,3 +83,12 @@ def test_against_oracle_on_jittered_inputs(emu_lib, fixture, seed, aniso):
     fx = parity.load(os.path.join(parity.HERE, "golden", fixture + ".oshd.gz"))
     rep = parity.check_against_oracle(parity.jittered_input(fx, seed, aniso), emu_lib)
     rep.assert_ok()
+
+
+@pytest.mark.parametrize("fixture,seed", [("d3n3m0_pass0", 31), ("d2n6m2_pass0", 32)])
+def test_permuted_globals_against_oracle(emu_lib, fixture, seed):
+    """non-identity global ids: new globals follow the scan over the OLD GLOBAL order
+    (modify_globals, src/Omega_h_modify.cpp:406-444), not the local order"""
+    fx = parity.load(os.path.join(parity.HERE, "golden", fixture + ".oshd.gz"))
+    rep = parity.check_against_oracle(parity.jittered_input(fx, seed, False, permute_globals=True), emu_lib)
+    rep.assert_ok()

@@ -194,3 +194,12 @@ def test_sort_by_keys(gpu_lib, width, dtype, n):
     got = d_p.to_host()
     want = np.lexsort([keys[:, k] for k in range(width - 1, -1, -1)]).astype(np.int32)  # lexsort is stable
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("fixture,seed", [("d3n3m0_pass0", 31), ("d2n6m2_pass0", 32)])
+def test_permuted_globals_against_oracle(gpu_lib, fixture, seed):
+    """non-identity global ids: new globals follow the scan over the OLD GLOBAL order
+    (modify_globals, src/Omega_h_modify.cpp:406-444), not the local order"""
+    fx = parity.load(os.path.join(parity.HERE, "golden", fixture + ".oshd.gz"))
+    rep = parity.check_against_oracle(parity.jittered_input(fx, seed, False, permute_globals=True), gpu_lib)
+    rep.assert_ok()
