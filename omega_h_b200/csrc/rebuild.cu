@@ -288,6 +288,133 @@ OSHB_HD LO key_nprods(Topo const& tp, int ent_dim, LO key) {
   return 2 * nr;
 }
 
+struct GatherArgs {
+  LO nold, nnew;
+  LO const* od;     // old downward rows
+  I8 const* oc;     // old codes
+  LO const* ovo;    // old entity -> vertices (dims 2, 3)
+  LO const* off;    // scanned representative counts (nold + 1)
+  LO const* st;     // status per old entity (dims >= 1)
+  LO const* ol2nl;  // old low -> new low
+  GO const* og;     // old globals
+  GO const* lg;     // scanned counts on the linear partition (general globals only)
+  bool ident;       // globals are the identity
+  I8* pm;           // product marks (only where a product-only transfer follows)
+  LO const* cs;     // coarse samples of the slot search
+  LO const* voff;   // first vertex -> keys
+  LO const* vkeys;
+  TagTable stab, itab;
+};
+
+// One thread per NEW entity of dimension D (compile-time: rows are unrolled and vectorised).
+template <int D>
+static void run_gather(GatherArgs const& ga, Topo const& t2) {
+  constexpr int deg = (D == 0) ? 0 : ((D == 1) ? 2 : ((D == 2) ? 3 : 4));
+  constexpr int nv = D + 1;
+  GatherArgs const a = ga;
+  LO* nd = t2.nd[D];
+  I8* nc = t2.nc[D];
+  LO* nvo = t2.nvo[D];
+  GO* ng = t2.ng[D];
+  LO const* ov2nv = t2.o2n[0];
+  parallel_for(a.nnew, OSHB_LAMBDA(LO ne) {
+    // the old entity that represents this slot: last e with off[e] <= ne
+    LO lo = a.cs[ne >> 8];
+    LO hi = a.cs[(ne >> 8) + 1];
+    LO e = lo + upper_bound(a.off + lo + 1, hi - lo, ne);
+    LO local = ne - a.off[e];
+    LO s = (D >= 1) ? a.st[e] : -1;
+    if (s == -1 && local == 0) {
+      // a surviving entity keeps its place: remapped row, codes, vertices, global, tags
+      // (modify_conn / transfer_common2, src/Omega_h_modify.cpp:20-70, Omega_h_transfer.cpp:160-170)
+      ng[ne] = a.ident ? GO(ne) : a.lg[a.og[e]];
+      if (D >= 1) {
+        LO row[deg > 0 ? deg : 1];
+#pragma unroll
+        for (int k = 0; k < deg; ++k) row[k] = a.od[int64_t(e) * deg + k];
+#pragma unroll
+        for (int k = 0; k < deg; ++k) nd[int64_t(ne) * deg + k] = a.ol2nl[row[k]];
+      }
+      if (D >= 2) {
+#pragma unroll
+        for (int k = 0; k < deg; ++k) nc[int64_t(ne) * deg + k] = a.oc[int64_t(e) * deg + k];
+        LO vr[nv];
+#pragma unroll
+        for (int k = 0; k < nv; ++k) vr[k] = a.ovo[int64_t(e) * nv + k];
+#pragma unroll
+        for (int k = 0; k < nv; ++k) nvo[int64_t(ne) * nv + k] = ov2nv[vr[k]];
+      }
+      for (int k = 0; k < a.stab.n; ++k) copy_ent(a.stab.t[k].dst, ne, a.stab.t[k].src, e, a.stab.t[k].bytes);
+      if (a.pm) a.pm[ne] = 0;
+      return;
+    }
+    if (a.pm) a.pm[ne] = 1;
+    if (D == VERT) {
+      // midpoint vertex of the (local-1)-th key whose first vertex is e
+      LO key = a.vkeys[a.voff[e] + local - 1];
+      LO ke = t2.k2e[key];
+      ng[ne] = t2.gbase[0][key];
+      for (int k = 0; k < a.itab.n; ++k) copy_ent(a.itab.t[k].dst, ne, a.itab.t[k].src_up, ke, a.itab.t[k].bytes);
+      return;
+    }
+    LO key = s;
+    LO t = local;
+    ng[ne] = a.ident ? GO(ne) : (t2.gbase[D][key] + t);
+    LO fb = t2.ef_off[key];
+    LO nf = t2.ef_off[key + 1] - fb;
+    if (D == EDGE) {
+      LO ke = t2.k2e[key];
+      LO M = t2.pbase[0][key];
+      if (t < 2) {
+        // halves of the key: (A', M), (M, B')  (refine_edges_to_pairs, refine_topology.cpp:13-34)
+        LO end = ov2nv[t2.ev2v[int64_t(ke) * 2 + t]];
+        nd[int64_t(ne) * 2 + 0] = (t == 0) ? end : M;
+        nd[int64_t(ne) * 2 + 1] = (t == 0) ? M : end;
+        for (int k = 0; k < a.itab.n; ++k) copy_ent(a.itab.t[k].dst, ne, a.itab.t[k].src, ke, a.itab.t[k].bytes);
+      } else {
+        // cut edge of face t-2: (tip', M)  (refine_domains_to_cuts(dim 2), :121-166)
+        LO f = t2.ef_ents[fb + t - 2];
+        int dde = code_which_down(t2.ef_codes[fb + t - 2]);
+        int tipl = simplex_opposite_template(2, EDGE, dde);
+        nd[int64_t(ne) * 2 + 0] = ov2nv[t2.fv2v[int64_t(f) * 3 + tipl]];
+        nd[int64_t(ne) * 2 + 1] = M;
+        for (int k = 0; k < a.itab.n; ++k) copy_ent(a.itab.t[k].dst, ne, a.itab.t[k].src_up, f, a.itab.t[k].bytes);
+      }
+    } else if (D == FACE) {
+      LO verts[3];
+      LO lows[3];
+      I8 codes[3];
+      product_tri(t2, key, t, verts, lows, codes);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        nd[int64_t(ne) * 3 + k] = lows[k];
+        nc[int64_t(ne) * 3 + k] = codes[k];
+        nvo[int64_t(ne) * 3 + k] = verts[k];
+      }
+      if (t < 2 * nf) {
+        LO f = t2.ef_ents[fb + (t >> 1)];
+        for (int k = 0; k < a.itab.n; ++k) copy_ent(a.itab.t[k].dst, ne, a.itab.t[k].src, f, a.itab.t[k].bytes);
+      } else {
+        LO r = t2.er_ents[t2.er_off[key] + (t - 2 * nf)];
+        for (int k = 0; k < a.itab.n; ++k) copy_ent(a.itab.t[k].dst, ne, a.itab.t[k].src_up, r, a.itab.t[k].bytes);
+      }
+    } else if (D == REGION) {
+      LO verts[4];
+      LO lows[4];
+      I8 codes[4];
+      product_tet(t2, key, int(t >> 1), int(t & 1), verts, lows, codes);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        nd[int64_t(ne) * 4 + k] = lows[k];
+        nc[int64_t(ne) * 4 + k] = codes[k];
+        nvo[int64_t(ne) * 4 + k] = verts[k];
+      }
+      LO r = t2.er_ents[t2.er_off[key] + (t >> 1)];
+      for (int k = 0; k < a.itab.n; ++k) copy_ent(a.itab.t[k].dst, ne, a.itab.t[k].src, r, a.itab.t[k].bytes);
+    }
+  }, "rebuild(gather)");
+}
+
 // ---------------------------------------------------------------------------------------
 // refine_element_based
 // ---------------------------------------------------------------------------------------
@@ -502,131 +629,53 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
 
   // ---- one gather kernel per dimension: thread per NEW entity -----------------------------------
   for (int d = 0; d <= dim; ++d) {
-    LO const nold = mesh->nents(d);
-    int const deg = (d >= 1) ? simplex_degree(d, d - 1) : 0;
-    int const nv = d + 1;
+    GatherArgs ga;
+    ga.nold = mesh->nents(d);
+    ga.nnew = nnew[d];
     Adj old_down;
     if (d >= 1) old_down = mesh->ask_down(d, d - 1);
-    LO const* od = (d >= 1) ? old_down.ab2b.data() : nullptr;
-    I8 const* oc = (d >= 2) ? old_down.codes.data() : nullptr;
-    LO const* ovo = (d == FACE) ? tp.fv2v : ((d == REGION) ? tp.rv2v : nullptr);
-    LO const* off = offsets[d].data();
-    LO const* st = (d >= 1) ? status[d].data() : nullptr;
-    LO const* ol2nl = (d >= 1) ? tp.o2n[d - 1] : nullptr;
-    LO const* ov2nv = tp.o2n[0];
-    LO* nd = tp.nd[d];
-    I8* nc = tp.nc[d];
-    LO* nvo = tp.nvo[d];
-    GO* ng = tp.ng[d];
+    ga.od = (d >= 1) ? old_down.ab2b.data() : nullptr;
+    ga.oc = (d >= 2) ? old_down.codes.data() : nullptr;
+    ga.ovo = (d == FACE) ? tp.fv2v : ((d == REGION) ? tp.rv2v : nullptr);
+    ga.off = offsets[d].data();
+    ga.st = (d >= 1) ? status[d].data() : nullptr;
+    ga.ol2nl = (d >= 1) ? tp.o2n[d - 1] : nullptr;
     GOs ogs = mesh->globals(d);
-    GO const* og = ogs.data();
-    bool const ident = identity[d];
-    GO const* lg = ident ? nullptr : lin_globals[d].data();
-    I8* pm = prod_marks[d].exists() ? prod_marks[d].data() : nullptr;
-    TagTable const stab = same_tab[d];
-    TagTable const itab = inh_tab[d];
-    Topo const t2 = tp;
-    int64_t tag_bytes = 0;
-    for (int k = 0; k < stab.n; ++k) tag_bytes += stab.t[k].bytes;
-    // coarse[i] = old entity representing new slot 256*i: the per-thread search below then
-    // only bisects the (cache-resident) stretch of offsets between two coarse samples
+    ga.og = ogs.data();
+    ga.ident = identity[d];
+    ga.lg = ga.ident ? nullptr : lin_globals[d].data();
+    ga.pm = prod_marks[d].exists() ? prod_marks[d].data() : nullptr;
+    ga.voff = voff;
+    ga.vkeys = vkeys;
+    ga.stab = same_tab[d];
+    ga.itab = inh_tab[d];
+    // coarse[i] = old entity representing new slot 256*i: the per-thread search then only
+    // bisects the (cache-resident) stretch of offsets between two coarse samples
     LO const ncoarse = nnew[d] / 256 + 2;
     LOs coarse(ncoarse);
     LO* cs = coarse.data();
     LO const nnew_d = nnew[d];
+    LO const nold_d = ga.nold;
+    LO const* off = ga.off;
     parallel_for(ncoarse, OSHB_LAMBDA(LO i) {
       int64_t slot = int64_t(i) * 256;
       if (slot > nnew_d - 1) slot = nnew_d - 1;
-      cs[i] = upper_bound(off, nold + 1, LO(slot)) - 1;
+      cs[i] = upper_bound(off, nold_d + 1, LO(slot)) - 1;
     }, "rebuild(coarse)");
+    ga.cs = cs;
+    int const deg = (d >= 1) ? simplex_degree(d, d - 1) : 0;
+    int const nv = d + 1;
+    int64_t tag_bytes = 0;
+    for (int k = 0; k < ga.stab.n; ++k) tag_bytes += ga.stab.t[k].bytes;
     // algorithmic bytes: every new array written once + the old arrays read once
     algo_bytes(int64_t(nnew[d]) * (8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes) +
-               int64_t(nold) * (4 + 4 + 8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes));
-    parallel_for(nnew[d], OSHB_LAMBDA(LO ne) {
-      // the old entity that represents this slot: last e with off[e] <= ne
-      LO lo = cs[ne >> 8];
-      LO hi = cs[(ne >> 8) + 1];
-      LO e = lo + upper_bound(off + lo + 1, hi - lo, ne);
-      LO local = ne - off[e];
-      LO s = st ? st[e] : -1;
-      if (s == -1 && local == 0) {
-        // a surviving entity keeps its place: remapped row, codes, vertices, global, tags
-        // (modify_conn / transfer_common2, src/Omega_h_modify.cpp:20-70, Omega_h_transfer.cpp:160-170)
-        ng[ne] = ident ? GO(ne) : lg[og[e]];
-        for (int k = 0; k < deg; ++k) {
-          nd[int64_t(ne) * deg + k] = ol2nl[od[int64_t(e) * deg + k]];
-          if (nc) nc[int64_t(ne) * deg + k] = oc[int64_t(e) * deg + k];
-        }
-        if (nvo)
-          for (int k = 0; k < nv; ++k) nvo[int64_t(ne) * nv + k] = ov2nv[ovo[int64_t(e) * nv + k]];
-        for (int k = 0; k < stab.n; ++k) copy_ent(stab.t[k].dst, ne, stab.t[k].src, e, stab.t[k].bytes);
-        if (pm) pm[ne] = 0;
-        return;
-      }
-      if (pm) pm[ne] = 1;
-      if (d == VERT) {
-        // midpoint vertex of the (local-1)-th key whose first vertex is e
-        LO key = vkeys[voff[e] + local - 1];
-        LO ke = t2.k2e[key];
-        ng[ne] = t2.gbase[0][key];
-        for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src_up, ke, itab.t[k].bytes);
-        return;
-      }
-      LO key = s;
-      LO t = local;
-      LO ke = t2.k2e[key];
-      ng[ne] = t2.gbase[d][key] + t;
-      LO fb = t2.ef_off[key];
-      LO nf = t2.ef_off[key + 1] - fb;
-      if (d == EDGE) {
-        LO M = t2.pbase[0][key];
-        if (t < 2) {
-          // halves of the key: (A', M), (M, B')  (refine_edges_to_pairs, refine_topology.cpp:13-34)
-          LO end = ov2nv[t2.ev2v[int64_t(ke) * 2 + t]];
-          nd[int64_t(ne) * 2 + 0] = (t == 0) ? end : M;
-          nd[int64_t(ne) * 2 + 1] = (t == 0) ? M : end;
-          for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src, ke, itab.t[k].bytes);
-        } else {
-          // cut edge of face t-2: (tip', M)  (refine_domains_to_cuts(dim 2), :121-166)
-          LO f = t2.ef_ents[fb + t - 2];
-          int dde = code_which_down(t2.ef_codes[fb + t - 2]);
-          int tipl = simplex_opposite_template(2, EDGE, dde);
-          nd[int64_t(ne) * 2 + 0] = ov2nv[t2.fv2v[int64_t(f) * 3 + tipl]];
-          nd[int64_t(ne) * 2 + 1] = M;
-          for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src_up, f, itab.t[k].bytes);
-        }
-      } else if (d == FACE) {
-        LO verts[3];
-        LO lows[3];
-        I8 codes[3];
-        product_tri(t2, key, t, verts, lows, codes);
-        for (int k = 0; k < 3; ++k) {
-          nd[int64_t(ne) * 3 + k] = lows[k];
-          nc[int64_t(ne) * 3 + k] = codes[k];
-          nvo[int64_t(ne) * 3 + k] = verts[k];
-        }
-        if (t < 2 * nf) {
-          LO f = t2.ef_ents[fb + (t >> 1)];
-          for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src, f, itab.t[k].bytes);
-        } else {
-          LO r = t2.er_ents[t2.er_off[key] + (t - 2 * nf)];
-          for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src_up, r, itab.t[k].bytes);
-        }
-      } else {
-        LO verts[4];
-        LO lows[4];
-        I8 codes[4];
-        product_tet(t2, key, int(t >> 1), int(t & 1), verts, lows, codes);
-        for (int k = 0; k < 4; ++k) {
-          nd[int64_t(ne) * 4 + k] = lows[k];
-          nc[int64_t(ne) * 4 + k] = codes[k];
-          nvo[int64_t(ne) * 4 + k] = verts[k];
-        }
-        LO r = t2.er_ents[t2.er_off[key] + (t >> 1)];
-        for (int k = 0; k < itab.n; ++k) copy_ent(itab.t[k].dst, ne, itab.t[k].src, r, itab.t[k].bytes);
-      }
-    }, "rebuild(gather)");
+               int64_t(ga.nold) * (4 + 4 + 8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes));
+    if (d == VERT) run_gather<0>(ga, tp);
+    else if (d == EDGE) run_gather<1>(ga, tp);
+    else if (d == FACE) run_gather<2>(ga, tp);
+    else run_gather<3>(ga, tp);
     LO const* o2n = tp.o2n[d];
+    LO const nold = ga.nold;
     for (auto const& ov : overflow[d]) {
       Tag const& ot = ov.first;
       Tag& nt = new_tags[d][ov.second];
