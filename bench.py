@@ -36,17 +36,27 @@ UNIT = "tets/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=64, help="box cells per axis (config[1] = 64)")
+    ap.add_argument("--workload", default="iso", choices=["iso", "aniso"],
+                    help="iso = BASELINE config[1] (the metric's configuration); aniso = config[2] tanh shock layer")
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table to stderr and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def workload_config(n):
+def workload_config(n, workload="iso"):
+    if workload == "aniso":
+        return {
+            "workload": "3D tet unit cube build_box %d^3 (x6 tets), anisotropic tanh shock-layer metric (3x3, "
+                        "hx=1/n, hy=0.7/n, hz=(1/n)(1-0.75 sech^2(20(z-1/2)))), while(refine_by_size) loop with "
+                        "field transfer" % n,
+            "box_n": n, "metric": "anisotropic ncomps=6",
+            "l2": "inputs larger than L2; no explicit flush",
+        }
     return {
         "workload": "3D tet unit cube build_box %d^3 (x6 tets), uniform isotropic metric h=1/(2n), "
                     "while(refine_by_size) loop (4 doubling passes, x16 elements)" % n,
@@ -72,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -186,12 +196,24 @@ def main_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def build_input(n, lib):
+def build_input(n, lib, workload="iso"):
     import numpy as np
     from omega_h_b200 import VERT, build_box
     m = build_box(1.0, 1.0, 1.0, n, n, n, lib=lib)
-    h = 1.0 / n / 2.0
-    m.add_tag(VERT, "metric", 1, np.full(m.nverts(), 1.0 / (h * h)))
+    if workload == "aniso":
+        # BASELINE config[2]: tanh shock layer at z = 1/2, hx = 1/n, hy = 0.7/n (distinct
+        # eigenvalues), hz = (1/n) (1 - 0.75 sech^2(20 (z - 1/2))); metric = diag(1/h^2)
+        x = m.coords().reshape(-1, 3)
+        t = np.tanh(20.0 * (x[:, 2] - 0.5))
+        hz = (1.0 / n) * (1.0 - 0.75 * (1.0 - t * t))
+        met = np.zeros((m.nverts(), 6))
+        met[:, 0] = 1.0 / (1.0 / n) ** 2
+        met[:, 1] = 1.0 / (0.7 / n) ** 2
+        met[:, 2] = 1.0 / hz ** 2
+        m.add_tag(VERT, "metric", 6, met.reshape(-1))
+    else:
+        h = 1.0 / n / 2.0
+        m.add_tag(VERT, "metric", 1, np.full(m.nverts(), 1.0 / (h * h)))
     m.ask_lengths()
     m.ask_qualities()
     lib.sync()
@@ -314,7 +336,7 @@ def main_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    base = build_input(args.n, lib)
+    base = build_input(args.n, lib, args.workload)
     opts = AdaptOpts(base)
     nelems0 = base.nelems()
 
@@ -466,7 +488,7 @@ def main_b200(args):
             cpu = {k: s[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        cfg = workload_config(args.n)
+        cfg = workload_config(args.n, args.workload)
         cfg["parallelism"] = "1 GPU" if world == 1 else "%d independent replicas (one box per GPU, no ghost exchange yet)" % world
         cfg["passes_per_step"] = npasses
         cfg["tets_per_step"] = "%d -> %d" % (nelems0, nelems1)
