@@ -163,66 +163,6 @@ static inline double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Caching device allocator. Every array of the pass is allocated and released on ONE stream,
-// so a released block can be handed out again immediately: any kernel that still reads it was
-// enqueued earlier on the same stream. Blocks are binned by size rounded up to 1/8 of the
-// leading power of two (<= 12.5 % slack); the sizes of a refine loop repeat exactly from
-// step to step, so after the first step every request is a free-list hit (~100 ns instead of
-// the ~45 us measured for cudaMallocAsync). On out-of-memory the cache is returned to the
-// driver and the request retried.
-static std::map<size_t, std::vector<void*>> g_free_blocks;
-static size_t g_cached_bytes = 0;
-
-static size_t round_size(size_t bytes) {
-  if (bytes < 512) return 512;
-  size_t p = size_t(1) << (63 - __builtin_clzll(static_cast<unsigned long long>(bytes)));
-  size_t step = p >> 3;
-  if (step < 512) step = 512;
-  return (bytes + step - 1) / step * step;
-}
-
-static void release_cache() {
-  cudaStreamSynchronize(g_ctx.stream);
-  for (auto& kv : g_free_blocks)
-    for (void* p : kv.second) cudaFree(p);
-  g_free_blocks.clear();
-  g_cached_bytes = 0;
-}
-
-void* dev_alloc(size_t bytes) {
-  Ctx& c = g_ctx;
-  if (!c.ready) init_ctx(-1);
-  double t0 = now_s();
-  size_t rs = round_size(bytes);
-  void* p = nullptr;
-  auto it = g_free_blocks.find(rs);
-  if (it != g_free_blocks.end() && !it->second.empty()) {
-    p = it->second.back();
-    it->second.pop_back();
-    g_cached_bytes -= rs;
-  } else {
-    cudaError_t e = cudaMalloc(&p, rs);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      release_cache();
-      OSHB_CUDA(cudaMalloc(&p, rs));
-    }
-  }
-  c.host_s_alloc += now_s() - t0;
-  c.n_alloc++;
-  c.alloc_bytes += bytes;
-  if (c.alloc_bytes > c.peak_bytes) c.peak_bytes = c.alloc_bytes;
-  return p;
-}
-
-void dev_free(void* p, size_t bytes) {
-  Ctx& c = g_ctx;
-  c.alloc_bytes -= bytes;
-  size_t rs = round_size(bytes);
-  g_free_blocks[rs].push_back(p);
-  g_cached_bytes += rs;
-}
-
 void h2d(void* dst, void const* src, size_t bytes) {
   Ctx& c = g_ctx;
   if (!c.ready) init_ctx(-1);
