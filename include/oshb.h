@@ -164,6 +164,44 @@ typedef struct oshb_pass_stats {
 } oshb_pass_stats;
 int oshb_last_pass_stats(oshb_pass_stats* out);
 
+/* ---- one refine pass, stage by stage -------------------------------------------------------------
+ * The same pass as oshb_refine_by_size, cut at the points where the reference synchronises
+ * across MPI ranks, so that a caller owning a partitioned mesh can do that synchronisation:
+ *   begin          candidates + cavity qualities + initial set states
+ *                  (src/Omega_h_refine.cpp:17-28; the sync_array of :25 goes after it)
+ *   restate        recompute the set states after qualities of non-owned edges were replaced
+ *   indset_round   one round of find_indset (src/Omega_h_indset_inline.hpp:20-47; the
+ *                  sync_array of :38 goes after it)
+ *   select_keys    keys + their cavities (src/Omega_h_refine.cpp:30-33)
+ *   number         local numbering of every dimension (src/Omega_h_modify.cpp:141-243, :357-404)
+ *   finish         the new mesh (src/Omega_h_modify.cpp:660-745, src/Omega_h_transfer.cpp)
+ * Between number and finish a caller that passed external_globals = 1 reads OSHB_PASS_OFFSETS
+ * (exclusive scan of the per-old-entity counts of new entities) and must set
+ * OSHB_PASS_GLOBAL_BASES for every dimension: the new global number of the first new entity
+ * each old entity stands for -- what modify_globals obtains from the scan over the linear
+ * partition (src/Omega_h_modify.cpp:406-444). */
+typedef struct oshb_pass oshb_pass;
+enum {
+  OSHB_PASS_CANDIDATES = 0,   /* int8   per edge */
+  OSHB_PASS_STATES = 1,       /* int8   per edge: 0 NOT_IN, 1 IN, 2 UNKNOWN */
+  OSHB_PASS_QUALITIES = 2,    /* double per edge */
+  OSHB_PASS_OFFSETS = 3,      /* int32  per old entity of dim, + 1 */
+  OSHB_PASS_OLD2NEW = 4,      /* int32  per old entity of dim (-1: the entity dies) */
+  OSHB_PASS_KEYS2EDGES = 5,   /* int32  per key */
+  OSHB_PASS_GLOBAL_BASES = 6  /* int64  per old entity of dim (set only) */
+};
+int oshb_pass_create(oshb_mesh* m, const oshb_adapt_opts* opts, oshb_pass** out);
+int oshb_pass_destroy(oshb_pass* p);
+int oshb_pass_begin(oshb_pass* p, int keep_going, int* status); /* 0 no candidate, 1 none good, 2 work */
+int oshb_pass_restate(oshb_pass* p, int* any_good);
+int oshb_pass_indset_round(oshb_pass* p, int* pending);
+int oshb_pass_select_keys(oshb_pass* p, int32_t* nkeys);
+int oshb_pass_number(oshb_pass* p, int external_globals);
+int oshb_pass_finish(oshb_pass* p);
+int oshb_pass_size(oshb_pass* p, int which, int dim, int64_t* n);
+int oshb_pass_get(oshb_pass* p, int which, int dim, void* out, int host);
+int oshb_pass_set(oshb_pass* p, int which, int dim, const void* in, int host);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * CUDA-event timer and per-kernel event timing on the library's own stream
  * (the reference's counterpart is the --osh-time call tree, src/Omega_h_profile.hpp:185-232). */

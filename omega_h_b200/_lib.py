@@ -57,6 +57,9 @@ SYMBOLS = [
     "oshb_mesh_ask_lengths", "oshb_mesh_ask_qualities", "oshb_build_box",
     "oshb_adapt_opts_init", "oshb_refine_qualities", "oshb_mident_metrics", "oshb_find_indset",
     "oshb_rep_vertex2md_order", "oshb_refine_by_size", "oshb_last_pass_stats",
+    "oshb_pass_create", "oshb_pass_destroy", "oshb_pass_begin", "oshb_pass_restate", "oshb_pass_indset_round",
+    "oshb_pass_select_keys", "oshb_pass_number", "oshb_pass_finish", "oshb_pass_size", "oshb_pass_get",
+    "oshb_pass_set",
     "oshb_timer_start", "oshb_timer_stop", "oshb_profile_begin", "oshb_profile_end", "oshb_host_alloc",
     "oshb_host_free", "oshb_host_time_stats",
 ]

@@ -446,9 +446,8 @@ int oshb_rep_vertex2md_order(oshb_mesh* m, const int8_t* keys, int32_t* order_ou
   OSHB_CATCH
 }
 
-int oshb_refine_by_size(oshb_mesh* m, const oshb_adapt_opts* o, int* did) {
-  OSHB_TRY
-  AdaptOpts a(m->m.dim());
+static AdaptOpts opts_from_c(int dim, const oshb_adapt_opts* o) {
+  AdaptOpts a(dim);
   if (o) {
     a.min_length_desired = o->min_length_desired;
     a.max_length_desired = o->max_length_desired;
@@ -457,8 +456,136 @@ int oshb_refine_by_size(oshb_mesh* m, const oshb_adapt_opts* o, int* did) {
     a.min_quality_desired = o->min_quality_desired;
     a.verbosity = o->verbosity;
   }
-  bool r = refine_by_size(&m->m, a);
+  return a;
+}
+
+int oshb_refine_by_size(oshb_mesh* m, const oshb_adapt_opts* o, int* did) {
+  OSHB_TRY
+  bool r = refine_by_size(&m->m, opts_from_c(m->m.dim(), o));
   *did = r ? 1 : 0;
+  OSHB_CATCH
+}
+
+// ---- staged pass ------------------------------------------------------------------------------
+int oshb_pass_create(oshb_mesh* m, const oshb_adapt_opts* o, oshb_pass** out) {
+  OSHB_TRY
+  *out = reinterpret_cast<oshb_pass*>(pass_create(&m->m, opts_from_c(m->m.dim(), o)));
+  OSHB_CATCH
+}
+int oshb_pass_destroy(oshb_pass* p) {
+  OSHB_TRY
+  pass_destroy(reinterpret_cast<Pass*>(p));
+  OSHB_CATCH
+}
+int oshb_pass_begin(oshb_pass* p, int keep_going, int* status) {
+  OSHB_TRY
+  *status = pass_begin(reinterpret_cast<Pass*>(p), keep_going != 0);
+  OSHB_CATCH
+}
+int oshb_pass_restate(oshb_pass* p, int* any_good) {
+  OSHB_TRY
+  *any_good = pass_restate(reinterpret_cast<Pass*>(p));
+  OSHB_CATCH
+}
+int oshb_pass_indset_round(oshb_pass* p, int* pending) {
+  OSHB_TRY
+  *pending = pass_indset_round(reinterpret_cast<Pass*>(p));
+  OSHB_CATCH
+}
+int oshb_pass_select_keys(oshb_pass* p, int32_t* nkeys) {
+  OSHB_TRY
+  pass_select_keys(reinterpret_cast<Pass*>(p));
+  *nkeys = pass_nkeys(reinterpret_cast<Pass*>(p));
+  OSHB_CATCH
+}
+int oshb_pass_number(oshb_pass* p, int external_globals) {
+  OSHB_TRY
+  pass_number(reinterpret_cast<Pass*>(p), external_globals != 0);
+  OSHB_CATCH
+}
+int oshb_pass_finish(oshb_pass* p) {
+  OSHB_TRY
+  pass_finish(reinterpret_cast<Pass*>(p));
+  OSHB_CATCH
+}
+// (pointer, element count, element bytes) of one of the pass arrays
+static void pass_array(Pass* p, int which, int dim, void** ptr, int64_t* n, int* ebytes) {
+  switch (which) {
+    case OSHB_PASS_CANDIDATES: {
+      Bytes a = pass_candidates(p);
+      *ptr = a.data(), *n = a.size(), *ebytes = 1;
+      return;
+    }
+    case OSHB_PASS_STATES: {
+      Bytes a = pass_states(p);
+      *ptr = a.data(), *n = a.size(), *ebytes = 1;
+      return;
+    }
+    case OSHB_PASS_QUALITIES: {
+      Reals a = pass_qualities(p);
+      *ptr = a.data(), *n = a.size(), *ebytes = 8;
+      return;
+    }
+    case OSHB_PASS_OFFSETS: {
+      LOs a = pass_offsets(p, dim);
+      *ptr = a.data(), *n = a.size(), *ebytes = 4;
+      return;
+    }
+    case OSHB_PASS_OLD2NEW: {
+      LOs a = pass_old2new(p, dim);
+      *ptr = a.data(), *n = a.size(), *ebytes = 4;
+      return;
+    }
+    case OSHB_PASS_KEYS2EDGES: {
+      LOs a = pass_keys2edges(p);
+      *ptr = a.data(), *n = a.size(), *ebytes = 4;
+      return;
+    }
+    default:
+      fail(__FILE__, __LINE__, "oshb_pass: unknown array selector");
+  }
+}
+int oshb_pass_size(oshb_pass* p, int which, int dim, int64_t* n) {
+  OSHB_TRY
+  void* ptr;
+  int eb;
+  pass_array(reinterpret_cast<Pass*>(p), which, dim, &ptr, n, &eb);
+  OSHB_CATCH
+}
+int oshb_pass_get(oshb_pass* p, int which, int dim, void* out, int host) {
+  OSHB_TRY
+  void* ptr;
+  int64_t n;
+  int eb;
+  pass_array(reinterpret_cast<Pass*>(p), which, dim, &ptr, &n, &eb);
+  if (n) {
+    if (host)
+      d2h(out, ptr, size_t(n) * size_t(eb));
+    else
+      d2d(out, ptr, size_t(n) * size_t(eb));
+  }
+  OSHB_CATCH
+}
+int oshb_pass_set(oshb_pass* p, int which, int dim, const void* in, int host) {
+  OSHB_TRY
+  Pass* ps = reinterpret_cast<Pass*>(p);
+  if (which == OSHB_PASS_GLOBAL_BASES) {
+    int64_t n = pass_offsets(ps, dim).size() - 1;
+    pass_set_global_bases(ps, dim, import_array<GO>(static_cast<GO const*>(in), n, host));
+  } else {
+    OSHB_CHECK(which == OSHB_PASS_STATES || which == OSHB_PASS_QUALITIES);
+    void* ptr;
+    int64_t n;
+    int eb;
+    pass_array(ps, which, dim, &ptr, &n, &eb);
+    if (n) {
+      if (host)
+        h2d(ptr, in, size_t(n) * size_t(eb));
+      else
+        d2d(ptr, in, size_t(n) * size_t(eb));
+    }
+  }
+  if (host) sync_stream();
   OSHB_CATCH
 }
 int oshb_last_pass_stats(oshb_pass_stats* out) {

@@ -172,6 +172,34 @@ struct Selection {
 };
 struct PassStats;
 void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats);  // rebuild.cu
+// the rebuild half in two steps (rebuild.cu): local numbering, then the new mesh. Between
+// them a distributed caller reads the per-old-entity counts (the differences of offsets) and
+// hands back the global-number bases of the old entities.
+struct Rebuild;
+Rebuild* rebuild_number(Mesh* mesh, Selection const& sel, PassStats* stats, bool external_globals);
+LOs rebuild_offsets(Rebuild* r, int d);
+LOs rebuild_old2new(Rebuild* r, int d);
+void rebuild_set_global_bases(Rebuild* r, int d, GOs bases);
+void rebuild_finish(Rebuild* r);
+void rebuild_discard(Rebuild* r);
+// one refine pass stage by stage (select.cu)
+struct Pass;
+Pass* pass_create(Mesh* mesh, AdaptOpts const& opts);
+void pass_destroy(Pass* p);
+int pass_begin(Pass* p, bool keep_going);
+int pass_restate(Pass* p);
+int pass_indset_round(Pass* p);
+void pass_select_keys(Pass* p);
+void pass_number(Pass* p, bool external_globals);
+void pass_finish(Pass* p);
+LO pass_nkeys(Pass* p);
+Bytes pass_candidates(Pass* p);
+Bytes pass_states(Pass* p);
+Reals pass_qualities(Pass* p);
+LOs pass_keys2edges(Pass* p);
+LOs pass_offsets(Pass* p, int d);
+LOs pass_old2new(Pass* p, int d);
+void pass_set_global_bases(Pass* p, int d, GOs bases);
 LOs rep_vertex_order_from_keys(LOs ev2v, LO nverts, LO nedges, LOs keys2edges, LOs* keys_order_out,
     LOs* vert2keys_off_out, LOs* vert_keys_out);  // refine.cu
 

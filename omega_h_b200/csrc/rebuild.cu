@@ -227,7 +227,10 @@ OSHB_HD void product_tet(Topo const& tp, LO key, int j, int eev, LO* verts, LO* 
 
 // should_inherit (src/Omega_h_transfer.cpp:20-34): class_id / class_dim present with the
 // same type and width on every dimension
-static bool should_inherit(Mesh* mesh, Tag const& tag) {
+static bool should_inherit(Mesh* mesh, Tag const& tag, int d) {
+  // partition bookkeeping of a distributed caller ("own:rank", "own:depth"): products of an
+  // element carry their parent's value
+  if (d == mesh->dim() && tag.name.compare(0, 4, "own:") == 0) return true;
   if (!(tag.name == "class_id" || tag.name == "class_dim" || tag.name == "momentum_velocity_fixed")) return false;
   for (int i = 0; i <= mesh->dim(); ++i) {
     Tag const* t = mesh->find_tag(i, tag.name);
@@ -327,7 +330,7 @@ static void run_gather(GatherArgs const& ga, Topo const& t2) {
     if (s == -1 && local == 0) {
       // a surviving entity keeps its place: remapped row, codes, vertices, global, tags
       // (modify_conn / transfer_common2, src/Omega_h_modify.cpp:20-70, Omega_h_transfer.cpp:160-170)
-      ng[ne] = a.ident ? GO(ne) : a.lg[a.og[e]];
+      ng[ne] = a.ident ? GO(ne) : (a.og ? a.lg[a.og[e]] : a.lg[e]);
       if (D >= 1) {
         LO row[deg > 0 ? deg : 1];
 #pragma unroll
@@ -418,29 +421,46 @@ static void run_gather(GatherArgs const& ga, Topo const& t2) {
 // ---------------------------------------------------------------------------------------
 // refine_element_based
 // ---------------------------------------------------------------------------------------
-void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
-  LOs keys2edges = sel.keys2edges;
+// The rebuild half runs in two steps so that a caller owning a partitioned mesh can number the
+// globals across ranks in between: number() fixes every local index (status, representative
+// counts, old2new, product bases), finish() writes the new mesh.
+struct Rebuild {
+  Mesh* mesh;
+  Selection sel;
+  PassStats* stats;
+  bool ext;  // new globals come from per-old-entity bases handed in by the caller
+  LOs keys2edges;
+  Mesh new_mesh;
+  LOs ev2v_old, fv2v, rv2v;
+  Adj e2f, e2r, f2e, r2f, r2e;
+  Topo tp;
+  LOs old2new[4], pbase[4], offsets[4], status[4];
+  bool identity[4];
+  GOs gbase[4], new_globals[4], lin_globals[4], ext_bases[4];
+  LO nnew[4];
+  void number();
+  void finish();
+};
+
+void Rebuild::number() {
+  keys2edges = sel.keys2edges;
   KeyOrder const& ko = sel.order;
   int const dim = mesh->dim();
   LO const nkeys = LO(keys2edges.size());
   LO const* k2e = keys2edges.data();
-  Mesh new_mesh = mesh->copy_meta();
-  LOs ev2v_old = mesh->ask_verts_of(EDGE);
+  new_mesh = mesh->copy_meta();
+  ev2v_old = mesh->ask_verts_of(EDGE);
   LO const* ev2v = ev2v_old.data();
   // key-indexed cavity rows (the key edges' E->F / E->R rows), built by the selection half
-  Adj e2f = sel.key_faces;
-  Adj e2r;
-  Adj f2e = mesh->ask_down(FACE, EDGE);
-  LOs fv2v = mesh->ask_verts_of(FACE);
-  Adj r2f, r2e;
-  LOs rv2v;
+  e2f = sel.key_faces;
+  f2e = mesh->ask_down(FACE, EDGE);
+  fv2v = mesh->ask_verts_of(FACE);
   if (dim == 3) {
     e2r = sel.key_tets;
     r2f = mesh->ask_down(REGION, FACE);
     r2e = mesh->ask_down(REGION, EDGE);
     rv2v = mesh->ask_verts_of(REGION);
   }
-  Topo tp;
   memset(&tp, 0, sizeof(tp));
   tp.dim = dim;
   tp.k2e = k2e;
@@ -462,16 +482,16 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
     tp.re_codes = r2e.codes.data();
   }
   LO const* voff = ko.vert2keys_off.data();
-  LO const* vkeys = ko.vert_keys.data();
+  bool const ext_g = ext;
 
   // ---- numbering of every dimension ---------------------------------------------------------
   // status[e]: -1 the entity survives, -2 it dies, k >= 0 it dies and represents key k
   // (get_mods2reps, src/Omega_h_modify.cpp:141-176: the key itself for edges, the first upward
   //  adjacent entity for triangles / tets; for vertices the key's first vertex, which survives)
-  LOs old2new[4], pbase[4], offsets[4], status[4];
-  bool identity[4] = {false, false, false, false};
-  GOs gbase[4], new_globals[4], lin_globals[4];
-  LO nnew[4] = {0, 0, 0, 0};
+  for (int d = 0; d < 4; ++d) {
+    identity[d] = false;
+    nnew[d] = 0;
+  }
   for (int ent_dim = 0; ent_dim <= dim; ++ent_dim) {
     LO const nold = mesh->nents(ent_dim);
     Topo const t1 = tp;
@@ -517,11 +537,11 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
     // src/Omega_h_modify.cpp:406-444); one rank: exchange = identity, rescan = exclusive scan
     // With identity globals (verified on the device by Mesh::globals_are_identity) the scan over
     // the linear partition IS the local scan: new global = new local index, nothing to compute.
-    bool const ident = mesh->globals_are_identity(ent_dim);
+    bool const ident = !ext_g && mesh->globals_are_identity(ent_dim);
     identity[ent_dim] = ident;
     GOs old_globals = mesh->globals(ent_dim);
     GO const* og = old_globals.data();
-    if (ident) {
+    if (ident || ext_g) {
       parallel_for(nold, OSHB_LAMBDA(LO e) { o2n[e] = (st && st[e] != -1) ? -1 : off[e]; }, "old2new");
     } else {
       lin_globals[ent_dim] = GOs(int64_t(nold) + 1);
@@ -533,7 +553,7 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
       }, "old2new+to_lin");
       scan_offsets(lin_counts.data(), nold, lin_globals[ent_dim].data());
     }
-    GO const* lg = ident ? nullptr : lin_globals[ent_dim].data();
+    GO const* lg = (ident || ext_g) ? nullptr : lin_globals[ent_dim].data();
     pbase[ent_dim] = LOs(nkeys);
     gbase[ent_dim] = GOs(nkeys);
     LO* pb = pbase[ent_dim].data();
@@ -548,11 +568,11 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
       if (ent_dim == VERT) {
         LO rep = ev2v[int64_t(e) * 2];
         pb[key] = off[rep] + kord[key] + 1;
-        gb[key] = (ident ? GO(off[rep]) : lg[og[rep]]) + eord[e] + 1;
+        if (!ext_g) gb[key] = (ident ? GO(off[rep]) : lg[og[rep]]) + eord[e] + 1;
       } else {
         LO rep = (ent_dim == EDGE) ? e : d_ents[d_off[key]];
         pb[key] = off[rep];
-        gb[key] = ident ? GO(off[rep]) : lg[og[rep]];
+        if (!ext_g) gb[key] = ident ? GO(off[rep]) : lg[og[rep]];
       }
     }, "prod_bases");
     new_globals[ent_dim] = GOs(nnew[ent_dim]);
@@ -563,6 +583,34 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
     stats->nents_after[ent_dim] = nnew[ent_dim];
   }
   new_mesh.set_verts(nnew[0]);
+}
+
+void Rebuild::finish() {
+  KeyOrder const& ko = sel.order;
+  int const dim = mesh->dim();
+  LO const nkeys = LO(keys2edges.size());
+  LO const* k2e = keys2edges.data();
+  LO const* ev2v = ev2v_old.data();
+  LO const* voff = ko.vert2keys_off.data();
+  LO const* vkeys = ko.vert_keys.data();
+  if (ext) {
+    // product globals from the caller's per-old-entity bases: base of the representative
+    // (+ the key's rank at its first vertex + 1 for midpoint vertices)
+    for (int d = 0; d <= dim; ++d) {
+      OSHB_CHECK(ext_bases[d].exists() && ext_bases[d].size() == int64_t(mesh->nents(d)));
+      GO const* xb = ext_bases[d].data();
+      GO* gb = gbase[d].data();
+      LO const* eord = ko.edge_order.data();
+      Adj const& e2d = (d == FACE) ? e2f : e2r;
+      LO const* d_off = (d >= FACE) ? e2d.a2ab.data() : nullptr;
+      LO const* d_ents = (d >= FACE) ? e2d.ab2b.data() : nullptr;
+      parallel_for(nkeys, OSHB_LAMBDA(LO key) {
+        LO e = k2e[key];
+        if (d == VERT) gb[key] = xb[ev2v[int64_t(e) * 2]] + eord[e] + 1;
+        else gb[key] = xb[(d == EDGE) ? e : d_ents[d_off[key]]];
+      }, "prod_bases(external)");
+    }
+  }
 
   // ---- new arrays + tag tables ----------------------------------------------------------------
   LOs new_down[4], new_vo[4];
@@ -592,7 +640,7 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
     }
     for (auto const& tag : mesh->tags_[d]) {
       int kind = -1;
-      bool inherit = should_inherit(mesh, tag);
+      bool inherit = should_inherit(mesh, tag, d);
       if (inherit) kind = 0;
       else if (d == VERT && tag.type == TAG_F64 && (tag.name == "coordinates" || tag.name == "warp")) kind = 1;
       else if (d == VERT && tag.type == TAG_F64 && (tag.name == "metric" || tag.name == "target_metric") &&
@@ -641,9 +689,9 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
     ga.st = (d >= 1) ? status[d].data() : nullptr;
     ga.ol2nl = (d >= 1) ? tp.o2n[d - 1] : nullptr;
     GOs ogs = mesh->globals(d);
-    ga.og = ogs.data();
+    ga.og = ext ? nullptr : ogs.data();
     ga.ident = identity[d];
-    ga.lg = ga.ident ? nullptr : lin_globals[d].data();
+    ga.lg = ga.ident ? nullptr : (ext ? ext_bases[d].data() : lin_globals[d].data());
     ga.pm = prod_marks[d].exists() ? prod_marks[d].data() : nullptr;
     ga.voff = voff;
     ga.vkeys = vkeys;
@@ -760,6 +808,38 @@ void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
     scatter_by<Real>(prod.data(), new_tags[dim][s.new_index].f64.data(), list.data(), LO(list.size()), 1);
   }
   *mesh = new_mesh;
+}
+
+Rebuild* rebuild_number(Mesh* mesh, Selection const& sel, PassStats* stats, bool external_globals) {
+  Rebuild* r = new Rebuild();
+  r->mesh = mesh;
+  r->sel = sel;
+  r->stats = stats;
+  r->ext = external_globals;
+  try {
+    r->number();
+  } catch (...) {
+    delete r;
+    throw;
+  }
+  return r;
+}
+LOs rebuild_offsets(Rebuild* r, int d) { return r->offsets[d]; }
+LOs rebuild_old2new(Rebuild* r, int d) { return r->old2new[d]; }
+void rebuild_set_global_bases(Rebuild* r, int d, GOs bases) { r->ext_bases[d] = bases; }
+void rebuild_finish(Rebuild* r) {
+  try {
+    r->finish();
+  } catch (...) {
+    delete r;
+    throw;
+  }
+  delete r;
+}
+void rebuild_discard(Rebuild* r) { delete r; }
+
+void refine_element_based(Mesh* mesh, Selection const& sel, PassStats* stats) {
+  rebuild_finish(rebuild_number(mesh, sel, stats, false));
 }
 
 }  // namespace oshb

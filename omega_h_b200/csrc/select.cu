@@ -194,22 +194,56 @@ static Adj key_rows(LO nelems, int nce, LO const* ce2e, I8 const* ce_codes, LO c
 // refine_by_size (src/Omega_h_refine.cpp:92-100) -> refine_ghosted (:17-41, one rank)
 // -> refine_element_based (rebuild.cu)
 // ---------------------------------------------------------------------------------------
-bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
+// One refine pass as a sequence of stages. refine_by_size() runs them back to back; a caller
+// that owns a partitioned mesh (omega_h_b200/dist.py) runs them one by one and synchronises
+// the per-edge qualities / set states / global numbering across ranks in between -- the places
+// where the reference calls sync_array and modify_globals (src/Omega_h_refine.cpp:25-29,
+// src/Omega_h_indset_inline.hpp:38, src/Omega_h_modify.cpp:406-444).
+struct Pass {
+  Mesh* mesh = nullptr;
+  AdaptOpts opts = AdaptOpts(3);
+  int dim = 0, nce = 0;
+  LO nedges = 0, nelems = 0;
+  Bytes edge_is_cand, state_a;
+  Reals edge_quals;
+  LOs flags;
+  Adj c2e;
+  LOs cv2v, ev2v;
+  Selection sel;
+  Rebuild* rb = nullptr;
+  int rounds = 0;
+  bool flags_clean = false;
+  int* flags3 = nullptr;
+  ~Pass() {
+    if (rb) rebuild_discard(rb);
+  }
+  int begin(bool keep_going);
+  int restate();
+  int indset_round();
+  void select_keys();
+  void number(bool ext);
+  void finish();
+};
+
+// candidates + cavity qualities + initial set states. Returns 0: no candidate edge,
+// 1: candidates but none whose cavity is good enough, 2: there is work.
+// keep_going: compute every array even when this rank has nothing to do (its neighbours may).
+int Pass::begin(bool keep_going) {
   device_error_reset();
   g_stats = PassStats();
-  int const dim = mesh->dim();
+  dim = mesh->dim();
   for (int d = 0; d <= dim; ++d) g_stats.nents_before[d] = g_stats.nents_after[d] = mesh->nents(d);
-  LO const nedges = mesh->nedges();
-  LO const nelems = mesh->nelems();
-  int const nce = simplex_degree(dim, EDGE);
+  nedges = mesh->nedges();
+  nelems = mesh->nelems();
+  nce = simplex_degree(dim, EDGE);
   Reals lengths = mesh->ask_lengths();
-  int* flags3 = reinterpret_cast<int*>(static_cast<char*>(ctx().dscratch) + 1152);  // 3 ints
+  flags3 = reinterpret_cast<int*>(static_cast<char*>(ctx().dscratch) + 1152);  // 3 ints
   {
     int z[3] = {0, 0, 0};
     h2d(flags3, z, sizeof(z));
   }
   // ---- candidates: each_gt(lengths, max_length_desired) + get_max (:95-97)
-  Bytes edge_is_cand(nedges);
+  edge_is_cand = Bytes(nedges);
   I8* cand = edge_is_cand.data();
   {
     Real const* len = lengths.data();
@@ -220,15 +254,15 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
       return c;
     }, flags3, 1, "each_gt");
   }
-  if (read_scalar(flags3) == 0) return false;
+  bool const any_cand = read_scalar(flags3) != 0;
+  if (!any_cand && !keep_going) return 0;
   // ---- cavity qualities of the candidates (refine_qualities, :22)
-  Adj c2e = mesh->ask_down(dim, EDGE);
-  LOs cv2v = mesh->ask_verts_of(dim);
-  LOs ev2v = mesh->ask_verts_of(EDGE);
+  c2e = mesh->ask_down(dim, EDGE);
+  cv2v = mesh->ask_verts_of(dim);
+  ev2v = mesh->ask_verts_of(EDGE);
   Reals coords = mesh->coords();
   Reals vert_metrics = mesh->get_reals(VERT, "metric");
   int const ncomps = mesh->metric_ncomps();
-  Selection sel;
   DArr<GO> qord_a(nedges);
   unsigned long long* qord = reinterpret_cast<unsigned long long*>(qord_a.data());
   {
@@ -248,8 +282,8 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
   else fail(__FILE__, __LINE__, "refine_by_size: unsupported (dim, metric ncomps)");
 #undef OSHB_CQ
   // ---- each_geq_to + get_max + the two map_onto of refine_ghosted (:23-28) in one sweep
-  Bytes state_a(nedges);
-  Reals edge_quals(nedges);
+  state_a = Bytes(nedges);
+  edge_quals = Reals(nedges);
   I8* state = state_a.data();
   Real* eq = edge_quals.data();
   {
@@ -268,71 +302,99 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
     }, flags3 + 1, 1, "cands_are_good");
   }
   qord_a.reset();
-  if (read_scalar(flags3 + 1) == 0) return false;
+  bool const any_good = read_scalar(flags3 + 1) != 0;
   device_error_check("cavity_qualities");
-  // ---- independent set (find_indset, :29): element-centric Jacobi rounds
-  {
-    GOs globals = mesh->globals(EDGE);
-    GO const* g = globals.data();
-    LO const* ce2e = c2e.ab2b.data();
-    LOs flags = filled<LO>(nedges, 0);
-    LO* fl = flags.data();
-    int* more = flags3 + 2;
-    int rounds = 0;
-    int pending = 1;
-    while (pending) {
-      int z = 0;
-      h2d(more, &z, sizeof(int));
-      parallel_for(nelems, OSHB_LAMBDA(LO c) {
-        LO es[6];
-        I8 st[6];
-        bool any = false;
-        for (int k = 0; k < nce; ++k) {
-          es[k] = ce2e[int64_t(c) * nce + k];
-          st[k] = state[es[k]];
-          any = any || (st[k] == UNKNOWN);
-        }
-        if (!any) return;
-        for (int i = 0; i < nce; ++i) {
-          if (st[i] != UNKNOWN) continue;
-          LO v = es[i];
-          Real vq = eq[v];
-          GO vg = g[v];
-          int f = 0;
-          for (int j = 0; j < nce; ++j) {
-            if (j == i) continue;
-            if (st[j] == IN) {
-              f |= 1;
-            } else if (st[j] == UNKNOWN) {
-              // compare(u, v): u strictly below v in (quality, global id)
-              LO u = es[j];
-              Real uq = eq[u];
-              bool u_lt_v = (uq != vq) ? (uq < vq) : (g[u] < vg);
-              if (!u_lt_v) f |= 2;
-            }
-          }
-          if (f) atomic_or_i32(reinterpret_cast<int*>(fl) + v, f);
-        }
-      }, "indset(elements)");
-      parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool {
-        if (state[e] != UNKNOWN) return false;
-        int f = fl[e];
-        if (f & 1) {
-          state[e] = NOT_IN;
-          return false;
-        }
-        if (f & 2) return true;  // still undecided: another round is needed
-        state[e] = IN;
-        return false;
-      }, more, 1, "indset(edges)");
-      pending = read_scalar(more);
-      if (pending) dev_memset(fl, 0, size_t(nedges) * sizeof(LO));
-      ++rounds;
-      OSHB_CHECK(rounds < 10000);
+  flags = filled<LO>(nedges, 0);
+  flags_clean = true;
+  if (!any_cand) return 0;
+  return any_good ? 2 : 1;
+}
+
+// recompute the set states after the caller replaced qualities of edges it does not own
+int Pass::restate() {
+  I8 const* cand = edge_is_cand.data();
+  I8* state = state_a.data();
+  Real const* eq = edge_quals.data();
+  Real const minq = opts.min_quality_allowed;
+  int z = 0;
+  h2d(flags3 + 1, &z, sizeof(int));
+  parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool {
+    bool good = cand[e] && (eq[e] >= minq);
+    state[e] = good ? UNKNOWN : NOT_IN;
+    return good;
+  }, flags3 + 1, 1, "cands_are_good(restate)");
+  return read_scalar(flags3 + 1) != 0;
+}
+
+// ---- independent set (find_indset, :29): one element-centric Jacobi round; returns whether
+// any edge of this mesh is still undecided
+int Pass::indset_round() {
+  GOs globals = mesh->globals(EDGE);
+  GO const* g = globals.data();
+  LO const* ce2e = c2e.ab2b.data();
+  LO* fl = flags.data();
+  I8* state = state_a.data();
+  Real const* eq = edge_quals.data();
+  int const nce_ = nce;
+  int* more = flags3 + 2;
+  int z = 0;
+  h2d(more, &z, sizeof(int));
+  // a distributed caller asks for another round whenever ANY rank is undecided
+  if (!flags_clean) dev_memset(fl, 0, size_t(nedges) * sizeof(LO));
+  parallel_for(nelems, OSHB_LAMBDA(LO c) {
+    LO es[6];
+    I8 st[6];
+    bool any = false;
+    for (int k = 0; k < nce_; ++k) {
+      es[k] = ce2e[int64_t(c) * nce_ + k];
+      st[k] = state[es[k]];
+      any = any || (st[k] == UNKNOWN);
     }
-    g_stats.indset_rounds = rounds;
-  }
-  // ---- keys: state is now NOT_IN(0)/IN(1) = the key marks (:30-33)
+    if (!any) return;
+    for (int i = 0; i < nce_; ++i) {
+      if (st[i] != UNKNOWN) continue;
+      LO v = es[i];
+      Real vq = eq[v];
+      GO vg = g[v];
+      int f = 0;
+      for (int j = 0; j < nce_; ++j) {
+        if (j == i) continue;
+        if (st[j] == IN) {
+          f |= 1;
+        } else if (st[j] == UNKNOWN) {
+          // compare(u, v): u strictly below v in (quality, global id)
+          LO u = es[j];
+          Real uq = eq[u];
+          bool u_lt_v = (uq != vq) ? (uq < vq) : (g[u] < vg);
+          if (!u_lt_v) f |= 2;
+        }
+      }
+      if (f) atomic_or_i32(reinterpret_cast<int*>(fl) + v, f);
+    }
+  }, "indset(elements)");
+  parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool {
+    if (state[e] != UNKNOWN) return false;
+    int f = fl[e];
+    if (f & 1) {
+      state[e] = NOT_IN;
+      return false;
+    }
+    if (f & 2) return true;  // still undecided: another round is needed
+    state[e] = IN;
+    return false;
+  }, more, 1, "indset(edges)");
+  int pending = read_scalar(more);
+  if (pending) dev_memset(fl, 0, size_t(nedges) * sizeof(LO));
+  flags_clean = (pending != 0);
+  ++rounds;
+  OSHB_CHECK(rounds < 10000);
+  g_stats.indset_rounds = rounds;
+  return pending;
+}
+
+// ---- keys: state is now NOT_IN(0)/IN(1) = the key marks (:30-33); then their cavities
+void Pass::select_keys() {
+  I8 const* state = state_a.data();
   LOs key_scan = offset_scan(state_a);
   LO const nkeys = last_of(key_scan);
   g_stats.nkeys = nkeys;
@@ -354,15 +416,56 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
   }
   sel.order.edge_order = rep_vertex_order_from_keys(ev2v, mesh->nverts(), nedges, sel.keys2edges, &sel.order.keys_order,
       &sel.order.vert2keys_off, &sel.order.vert_keys);
-  // ---- cavities of the keys
   Adj f2e = mesh->ask_down(FACE, EDGE);
   sel.key_faces = key_rows(mesh->nents(FACE), 3, f2e.ab2b.data(), f2e.codes.data(), edge2key_a.data(), nkeys, &sel.face2key);
   if (dim == 3) {
     sel.key_tets = key_rows(nelems, 6, c2e.ab2b.data(), c2e.codes.data(), edge2key_a.data(), nkeys, &sel.tet2key);
   }
-  refine_element_based(mesh, sel, &g_stats);
+}
+
+void Pass::number(bool ext) { rb = rebuild_number(mesh, sel, &g_stats, ext); }
+
+void Pass::finish() {
+  Rebuild* r = rb;
+  rb = nullptr;
+  rebuild_finish(r);
   device_error_check("refine_element_based");
+}
+
+bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
+  Pass p;
+  p.mesh = mesh;
+  p.opts = opts;
+  if (p.begin(false) != 2) return false;
+  while (p.indset_round()) {
+  }
+  p.select_keys();
+  p.number(false);
+  p.finish();
   return true;
 }
+
+// ---- staged interface (capi.cu) -------------------------------------------------------------
+Pass* pass_create(Mesh* mesh, AdaptOpts const& opts) {
+  Pass* p = new Pass();
+  p->mesh = mesh;
+  p->opts = opts;
+  return p;
+}
+void pass_destroy(Pass* p) { delete p; }
+int pass_begin(Pass* p, bool keep_going) { return p->begin(keep_going); }
+int pass_restate(Pass* p) { return p->restate(); }
+int pass_indset_round(Pass* p) { return p->indset_round(); }
+void pass_select_keys(Pass* p) { p->select_keys(); }
+void pass_number(Pass* p, bool ext) { p->number(ext); }
+void pass_finish(Pass* p) { p->finish(); }
+LO pass_nkeys(Pass* p) { return LO(p->sel.keys2edges.size()); }
+Bytes pass_candidates(Pass* p) { return p->edge_is_cand; }
+Bytes pass_states(Pass* p) { return p->state_a; }
+Reals pass_qualities(Pass* p) { return p->edge_quals; }
+LOs pass_keys2edges(Pass* p) { return p->sel.keys2edges; }
+LOs pass_offsets(Pass* p, int d) { return rebuild_offsets(p->rb, d); }
+LOs pass_old2new(Pass* p, int d) { return rebuild_old2new(p->rb, d); }
+void pass_set_global_bases(Pass* p, int d, GOs bases) { rebuild_set_global_bases(p->rb, d, bases); }
 
 }  // namespace oshb

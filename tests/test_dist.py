@@ -1,0 +1,40 @@
+"""Partitioned refine_by_size (omega_h_b200/dist.py) against the serial loop: world_size 2 and 3
+over gloo on CPU (the library is the host emulation build), world_size 2 over NCCL on GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+WORKER = os.path.join(HERE, "dist_worker.py")
+
+
+def run_worker(nranks, lib_path, device, n, halo, aniso, dim, port, timeout=900):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, lib_path, device, str(n), str(halo),
+           str(aniso), str(dim)]
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = "1"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("nranks,n,halo,aniso,dim", [
+    (2, 8, 4, 0, 3),    # 4 doubling passes, the halo exactly used up
+    (3, 6, 5, 0, 3),    # uneven parts, 5 passes
+    (2, 5, 8, 1, 3),    # anisotropic metric (ncomps 6), metric transfer
+    (2, 16, 4, 0, 2),   # triangles
+])
+def test_partitioned_loop_matches_serial_gloo(emu_lib, nranks, n, halo, aniso, dim):
+    run_worker(nranks, emu_lib.path, "cpu", n, halo, aniso, dim, 29530 + nranks + n)
+
+
+@pytest.mark.gpu
+def test_partitioned_loop_matches_serial_nccl(gpu_lib):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_worker(2, gpu_lib.path, "cuda", 24, 4, 0, 3, 29541)
+    run_worker(2, gpu_lib.path, "cuda", 12, 8, 1, 3, 29542)
