@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table to stderr and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--halo", type=int, default=4, help="N > 1: element layers each part keeps of its neighbours")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent boxes instead of one partitioned box")
     return ap.parse_args()
 
 
@@ -506,10 +508,163 @@ def main_b200(args):
     return 0
 
 
+def box_shape(world):
+    """ranks as a block of unit cubes: 2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2 ..."""
+    shape = [1, 1, 1]
+    i = 0
+    w = world
+    while w > 1:
+        if w % 2:
+            shape[i % 3] *= w
+            break
+        shape[i % 3] *= 2
+        w //= 2
+        i += 1
+    return shape
+
+
+def main_b200_partitioned(args):
+    """N > 1: ONE box of N x n^3 cells, partitioned over the ranks (omega_h_b200/dist.py): every
+    rank refines the elements it owns + a halo, the shell's edge data and the global-number scan go
+    over NCCL. Weak scaling: the per-rank share is the N = 1 workload."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from omega_h_b200 import AdaptOpts, Lib, VERT, build_box
+    from omega_h_b200 import dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=device)
+    lib = Lib(device=local_rank).init()
+    if lib.is_emulation:
+        raise SystemExit("bench.py refuses to run on the emulation build")
+    n = args.n
+    shape = box_shape(world)
+    base = build_box(float(shape[0]), float(shape[1]), float(shape[2]), shape[0] * n, shape[1] * n, shape[2] * n, lib=lib)
+    h = 1.0 / n / 2.0
+    base.add_tag(VERT, "metric", 1, np.full(base.nverts(), 1.0 / (h * h)))
+    base.ask_lengths()
+    base.ask_qualities()
+    halo = args.halo
+    part0 = D.distribute(base, halo, device)
+    nglobal0 = base.nelems()
+    del base
+    opts = AdaptOpts(part0.mesh)
+
+    def barrier():
+        lib.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def loop(part):
+        passes = 0
+        while part.refine_by_size(opts):
+            passes += 1
+        return passes
+
+    for _ in range(max(args.warmup, 3)):
+        part = part0.clone()
+        npasses = loop(part)
+    owned1 = part.owned_nelems()
+    t = torch.tensor([float(owned1)], device=device, dtype=torch.float64)
+    dist.all_reduce(t)
+    nglobal1 = int(t.item())
+    local1 = part.mesh.nelems()
+    last = dict(part.last)
+    del part
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        part = part0.clone()
+        loop(part)
+    lib.sync()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = lib.launch_count() - launches0
+    clocks = sampler.stop()
+    del part
+    tm = torch.tensor([dev_ms], device=device, dtype=torch.float64)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(tm[0])
+    total_new = float(nglobal1 - nglobal0) * args.steps
+    value = total_new / (dev_ms_max / 1e3)
+
+    # end to end: every rank uploads its part from pinned host arrays and reads its refined part back
+    e2e = None
+    if not args.no_e2e:
+        img = host_copy_of(part0.mesh, lib)
+        down = Download(lib)
+
+        def e2e_step():
+            m = upload(img, lib)
+            part = D.DistMesh(m, device, halo)
+            part.nglobal = list(part0.nglobal)
+            loop(part)
+            return down(part.mesh)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            d2h_bytes = e2e_step()
+        barrier()
+        e_s = time.perf_counter() - t0
+        te = torch.tensor([e_s], device=device, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_s = float(te[0])
+        tb = torch.tensor([float(img["nbytes"]), float(d2h_bytes)], device=device, dtype=torch.float64)
+        dist.all_reduce(tb)
+        e2e = {"value": total_new / e_s, "unit": UNIT, "h2d_bytes_per_step": int(tb[0]), "d2h_bytes_per_step": int(tb[1]),
+               "ms_per_step": e_s * 1e3 / args.steps,
+               "timing": "wall clock around upload + partitioned loop + download of every rank's part, max over ranks"}
+
+    if rank == 0:
+        cfg = workload_config(n, "iso")
+        cfg["workload"] = ("3D tet box build_box %dx%dx%d cells (x6 tets) = %d ranks x %d^3, uniform isotropic metric "
+                           "h=1/(2n), while(refine_by_size) loop on the partitioned mesh" %
+                           (shape[0] * n, shape[1] * n, shape[2] * n, world, n))
+        cfg["parallelism"] = ("%d parts (contiguous ranges of the Hilbert element order), halo %d layers, per-pass "
+                              "shell exchange + global-number scan over NCCL" % (world, halo))
+        cfg["passes_per_step"] = npasses
+        cfg["tets_per_step"] = "%d -> %d" % (nglobal0, nglobal1)
+        cfg["local_tets_rank0"] = local1
+        cfg["last_pass"] = last
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None,
+            "peak_device_bytes": lib.peak_bytes(),
+        }
+        print(json.dumps(line))
+    if D.TIMING is not None:
+        nloops = args.steps * (1 if args.no_e2e else 2) + max(args.warmup, 3) + (0 if args.no_e2e else 1)
+        for r in range(world):
+            if r == rank:
+                for k, v in sorted(D.TIMING.items(), key=lambda kv: -kv[1]):
+                    print("  rank %d %-28s %9.3f ms/step" % (rank, k, v * 1e3 / nloops), file=sys.stderr)
+            dist.barrier()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         return main_reference(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.replicas:
+        return main_b200_partitioned(args)
     return main_b200(args)
 
 

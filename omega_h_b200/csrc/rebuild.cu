@@ -228,10 +228,12 @@ OSHB_HD void product_tet(Topo const& tp, LO key, int j, int eev, LO* verts, LO* 
 // should_inherit (src/Omega_h_transfer.cpp:20-34): class_id / class_dim present with the
 // same type and width on every dimension
 static bool should_inherit(Mesh* mesh, Tag const& tag, int d) {
-  // partition bookkeeping of a distributed caller ("own:rank", "own:depth"): products of an
-  // element carry their parent's value
-  if (d == mesh->dim() && tag.name.compare(0, 4, "own:") == 0) return true;
-  if (!(tag.name == "class_id" || tag.name == "class_dim" || tag.name == "momentum_velocity_fixed")) return false;
+  // "own:*": partition bookkeeping of a distributed caller (omega_h_b200/dist.py), inherited like
+  // the classification
+  (void)d;
+  if (!(tag.name == "class_id" || tag.name == "class_dim" || tag.name == "momentum_velocity_fixed" ||
+          tag.name.compare(0, 4, "own:") == 0))
+    return false;
   for (int i = 0; i <= mesh->dim(); ++i) {
     Tag const* t = mesh->find_tag(i, tag.name);
     if (!t || t->type != tag.type || t->ncomps != tag.ncomps) return false;

@@ -41,6 +41,32 @@ _PASS_DTYPE = {PASS_CANDIDATES: torch.int8, PASS_STATES: torch.int8, PASS_QUALIT
                PASS_OFFSETS: torch.int32, PASS_OLD2NEW: torch.int32, PASS_KEYS2EDGES: torch.int32}
 DEEP = 127
 
+# optional wall-clock breakdown of the partitioned pass (OSHB_DIST_TIMING=1): every section is
+# bracketed by full synchronisation, so the numbers are for diagnosis, never for the bench
+import os as _os
+import time as _time
+TIMING = {} if _os.environ.get("OSHB_DIST_TIMING") else None
+
+
+class _Section:
+    def __init__(self, dmesh, name):
+        self.dmesh, self.name = dmesh, name
+
+    def _sync(self):
+        self.dmesh.lib.sync()
+        if self.dmesh.device.type == "cuda":
+            torch.cuda.synchronize(self.dmesh.device)
+
+    def __enter__(self):
+        if TIMING is not None:
+            self._sync()
+            self.t0 = _time.perf_counter()
+
+    def __exit__(self, *a):
+        if TIMING is not None:
+            self._sync()
+            TIMING[self.name] = TIMING.get(self.name, 0.0) + (_time.perf_counter() - self.t0)
+
 
 class DevMesh:
     """Tensor-level access to a library mesh: arrays go in and out by device pointer."""
@@ -160,15 +186,31 @@ class _Pass:
 
 
 # ---- collectives ------------------------------------------------------------------------------
+def _tick(name, t0, dev):
+    if TIMING is None:
+        return 0.0
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    t1 = _time.perf_counter()
+    if t0:
+        TIMING[name] = TIMING.get(name, 0.0) + (t1 - t0)
+    return t1
+
+
 def _alltoallv(send, send_counts, group=None):
     """send is grouped by destination rank; returns (received values grouped by source rank, counts)."""
     dev = send.device
+    t = _tick("", 0.0, dev)
     sc = torch.as_tensor(list(send_counts), dtype=torch.int64, device=dev)
     rc = torch.empty_like(sc)
+    t = _tick("a2a: h2d counts", t, dev)
     dist.all_to_all_single(rc, sc, group=group)
+    t = _tick("a2a: counts exchange", t, dev)
     rc_l = [int(x) for x in rc.tolist()]
     recv = torch.empty(sum(rc_l), dtype=send.dtype, device=dev)
+    t = _tick("a2a: tolist+empty", t, dev)
     dist.all_to_all_single(recv, send.contiguous(), rc_l, [int(x) for x in send_counts], group=group)
+    t = _tick("a2a: data", t, dev)
     return recv, rc_l
 
 
@@ -178,8 +220,8 @@ def _any_rank(flag, device, group=None):
     return bool(t.item())
 
 
-class ShellPlan:
-    """Owner -> requester transfers of per-edge values for the edges a rank cannot compute itself."""
+class FetchPlan:
+    """Owner -> requester transfers of per-entity values (one value per requested entity)."""
 
     def __init__(self, send_idx, send_counts, recv_idx, recv_counts, group=None):
         self.send_idx, self.send_counts = send_idx, send_counts
@@ -207,32 +249,44 @@ class DistMesh:
         self.nglobal = [0, 0, 0, 0]
         self.last = {}
 
-    # ---- depth of every entity = min over its local elements ------------------------------------
-    def _elem_depth(self):
-        return self.dm.tag(self.mesh.dim(), "own:depth").to(torch.int64)
-
-    def _first_elem(self, ent_dim, elem_depth):
-        """per entity of ent_dim: its depth (min over its local elements), the lowest-numbered
-        element of that depth, and the lowest-numbered of all its local elements"""
-        dim = self.mesh.dim()
-        nel = self.mesh.nents(dim)
-        ids = torch.arange(nel, device=self.device, dtype=torch.int64)
-        if ent_dim == dim:
-            return elem_depth, ids, ids
-        c2d, _ = self.dm.down(dim, ent_dim)
-        c2d = c2d.to(torch.int64)
-        deg = simplex_degree(dim, ent_dim)
-        key = ((elem_depth << 40) + ids).repeat_interleave(deg)
-        n = self.mesh.nents(ent_dim)
-        best = torch.full((n,), (DEEP << 40), dtype=torch.int64, device=self.device)
-        best.scatter_reduce_(0, c2d, key, reduce="amin", include_self=True)
-        lowest = torch.full((n,), nel, dtype=torch.int64, device=self.device)
-        lowest.scatter_reduce_(0, c2d, ids.repeat_interleave(deg), reduce="amin", include_self=True)
-        return best >> 40, best & ((1 << 40) - 1), lowest
+    def clone(self):
+        """a fresh handle on the same (immutable) arrays, as Mesh.copy()"""
+        c = DistMesh(self.mesh.copy(), self.device, self.halo, self.group)
+        c.passes = self.passes
+        c.nglobal = list(self.nglobal)
+        return c
 
     def owned_mask(self, ent_dim):
         """entities in the closure of this rank's own elements"""
-        return self._first_elem(ent_dim, self._elem_depth())[0] == 0
+        return self.dm.tag(ent_dim, "own:depth") == 0
+
+    def owned_nelems(self):
+        return int(self.owned_mask(self.mesh.dim()).sum().item())
+
+    # ---- plans ------------------------------------------------------------------------------------
+    def _counted(self, ent_dim, rank_tag=None, gid=None):
+        """(local indices, global numbers) of the entities this rank counts and answers for: those
+        whose lowest adjacent owner rank ("own:rank") is this rank. In increasing global number."""
+        if rank_tag is None:
+            rank_tag = self.dm.tag(ent_dim, "own:rank")
+        if gid is None:
+            gid = self.dm.tag(ent_dim, "global")
+        idx = torch.nonzero(rank_tag == self.rank).flatten()
+        return idx, gid[idx]
+
+    def _fetch_plan(self, want_idx, want_owner, want_gid, have_idx, have_gid):
+        """want_*: local entities whose value lives on another rank (want_owner);
+        have_*: this rank's counted entities sorted by global number (the lookup table)."""
+        P = self.size
+        order = torch.argsort(want_owner, stable=True)
+        want_idx, want_owner, want_gid = want_idx[order], want_owner[order], want_gid[order]
+        counts = torch.bincount(want_owner, minlength=P).tolist()
+        asked, asked_counts = _alltoallv(want_gid, counts, self.group)
+        pos = torch.searchsorted(have_gid, asked).clamp(max=max(have_gid.numel() - 1, 0))
+        if asked.numel():
+            ok = bool((have_gid[pos] == asked).all().item()) if have_gid.numel() else False
+            assert ok, "a neighbour asked for an entity this rank does not answer for"
+        return FetchPlan(have_idx[pos], asked_counts, want_idx, counts, self.group)
 
     # ---- the pass -------------------------------------------------------------------------------
     def refine_by_size(self, opts=None):
@@ -242,129 +296,136 @@ class DistMesh:
         trust = self.halo - self.passes - 1   # deepest layer whose entities see their whole star
         ps = _Pass(dm, opts)
         try:
-            ps.begin(True)
-            elem_depth = self._elem_depth()
-            edge_depth, edge_first, _ = self._first_elem(EDGE, elem_depth)
-            mine = edge_depth == 0
-            cand = ps.get(PASS_CANDIDATES)
-            if not _any_rank(bool((cand[mine] != 0).any().item()), dev, self.group):
+            with _Section(dm, "begin(lib)"):
+                ps.begin(True)
+            with _Section(dm, "edge tags"):
+                edge_depth = dm.tag(EDGE, "own:depth")
+                mine = edge_depth == 0
+                cand = ps.get(PASS_CANDIDATES)
+                any_cand = bool(((cand != 0) & mine).any().item())
+            if not _any_rank(any_cand, dev, self.group):
                 return False
             if trust < 0:
                 raise _lib.OshbError("halo of %d layers is used up after %d passes; re-ghosting is not implemented"
                                      % (self.halo, self.passes))
-            erank = dm.tag(dim, "own:rank").to(torch.int64)
-            egid = dm.tag(EDGE, "global")
-            plan = self._shell_plan(edge_depth, edge_first, erank, egid, trust + 1)
-            quals = plan.pull(ps.get(PASS_QUALITIES).view(torch.int64)).view(torch.float64)
-            ps.set(PASS_QUALITIES, quals)
-            ps.restate()
-            state = ps.get(PASS_STATES)
-            if not _any_rank(bool((state[mine] == UNKNOWN).any().item()), dev, self.group):
+            with _Section(dm, "shell plan"):
+                edge_rank = dm.tag(EDGE, "own:rank")
+                egid = dm.tag(EDGE, "global")
+                have_idx, have_gid = self._counted(EDGE, edge_rank, egid)
+                if have_gid.numel() > 1:
+                    assert bool((have_gid[1:] > have_gid[:-1]).all().item()), "local edge order lost the global order"
+                shell = torch.nonzero(edge_depth == trust + 1).flatten()
+                plan = self._fetch_plan(shell, edge_rank[shell].to(torch.int64), egid[shell], have_idx, have_gid)
+            with _Section(dm, "qualities exchange"):
+                quals = plan.pull(ps.get(PASS_QUALITIES).view(torch.int64)).view(torch.float64)
+                ps.set(PASS_QUALITIES, quals)
+                ps.restate()
+                state = ps.get(PASS_STATES)
+                any_good = bool(((state == UNKNOWN) & mine).any().item())
+            if not _any_rank(any_good, dev, self.group):
                 return False
             rounds = 0
             while True:
-                ps.indset_round()
-                state = plan.pull(ps.get(PASS_STATES))
-                ps.set(PASS_STATES, state)
-                rounds += 1
-                if not _any_rank(bool((state[mine] == UNKNOWN).any().item()), dev, self.group):
+                with _Section(dm, "indset round(lib)"):
+                    ps.indset_round()
+                with _Section(dm, "indset exchange"):
+                    state = plan.pull(ps.get(PASS_STATES))
+                    ps.set(PASS_STATES, state)
+                    rounds += 1
+                    more = _any_rank(bool(((state == UNKNOWN) & mine).any().item()), dev, self.group)
+                if not more:
                     break
-            # edges deeper than the shell never hear from their owner: keep them out of the set
-            state = torch.where(edge_depth <= trust + 1, state, torch.zeros_like(state))
-            state = torch.where(state == UNKNOWN, torch.zeros_like(state), state)
-            ps.set(PASS_STATES, state)
-            nkeys = ps.select_keys()
+            with _Section(dm, "select_keys(lib)"):
+                # edges deeper than the shell never hear from their owner: keep them out of the set
+                state = torch.where((edge_depth <= trust + 1) & (state == IN), 1, 0).to(torch.int8)
+                ps.set(PASS_STATES, state)
+                nkeys = ps.select_keys()
             self.last = {"rounds": rounds, "nkeys_local": nkeys, "shell_edges": int(plan.recv_idx.numel())}
-            if nkeys == 0:
-                # nothing splits here, but the numbers of everything shift with the other ranks' products
-                for d in range(dim + 1):
-                    n = mesh.nents(d)
-                    counts = torch.ones(n, dtype=torch.int64, device=dev)
-                    bases = self._global_bases(d, counts, elem_depth, erank)
-                    dm.set_tag(d, "global", 1, bases)
-            else:
-                ps.number(True)
-                for d in range(dim + 1):
-                    off = ps.get(PASS_OFFSETS, d).to(torch.int64)
-                    bases = self._global_bases(d, off[1:] - off[:-1], elem_depth, erank)
-                    ps.set(PASS_GLOBAL_BASES, bases, d)
-                ps.finish()
+            if nkeys:
+                with _Section(dm, "number(lib)"):
+                    ps.number(True)
+            nnext = [0, 0, 0, 0]
+            for d in range(dim + 1):
+                with _Section(dm, "global bases dim %d" % d):
+                    if nkeys:
+                        off = ps.get(PASS_OFFSETS, d).to(torch.int64)
+                        counts = off[1:] - off[:-1]
+                    else:
+                        # nothing splits here, but every number shifts with the other ranks' products
+                        counts = torch.ones(mesh.nents(d), dtype=torch.int64, device=dev)
+                    bases, nnext[d] = self._global_bases(d, counts, trust)
+                    if nkeys:
+                        ps.set(PASS_GLOBAL_BASES, bases, d)
+                    else:
+                        dm.set_tag(d, "global", 1, bases)
+            if nkeys:
+                with _Section(dm, "finish(lib)"):
+                    ps.finish()
+            self.nglobal = nnext
             self.passes += 1
             return True
         finally:
             ps.close()
 
-    def _shell_plan(self, edge_depth, edge_first, erank, egid, shell_depth):
-        """Who sends which edge values to whom: each rank asks the owner of a neighbouring element
-        for its shell edges; the owner finds them among the edges of its own elements by global number."""
-        P = self.size
-        dev = self.device
-        shell = torch.nonzero(edge_depth == shell_depth).flatten()
-        owner = erank[edge_first[shell]]
-        order = torch.argsort(owner, stable=True)
-        shell, owner = shell[order], owner[order]
-        counts = torch.bincount(owner, minlength=P).tolist()
-        assert counts[self.rank] == 0 or shell_depth == 0
-        asked, asked_counts = _alltoallv(egid[shell], counts, self.group)
-        mine_idx = torch.nonzero(edge_depth == 0).flatten()
-        mine_gid = egid[mine_idx]
-        if mine_gid.numel() > 1:
-            assert bool((mine_gid[1:] > mine_gid[:-1]).all().item()), "local edge order lost the global order"
-        pos = torch.searchsorted(mine_gid, asked)
-        pos = pos.clamp(max=max(mine_gid.numel() - 1, 0))
-        if asked.numel():
-            assert bool((mine_gid[pos] == asked).all().item()), "a neighbour asked for an edge this rank does not own"
-        return ShellPlan(mine_idx[pos], asked_counts, shell, counts, self.group)
-
-    def _global_bases(self, ent_dim, counts, elem_depth, erank):
+    def _global_bases(self, ent_dim, counts, trust):
         """modify_globals (src/Omega_h_modify.cpp:406-444): exclusive scan, in global-number order, of
-        how many new entities each old entity stands for. Every entity is counted once, by the owner
-        of its lowest-numbered element, on the linear partition of the old global numbers; every rank
-        then reads back the bases of the entities it holds."""
-        P, dev = self.size, self.device
+        how many new entities each old entity stands for.
+
+        Old global numbers are dense, so a rank sees where its own stretch of the global order is
+        interrupted: its counted entities fall into runs of consecutive numbers, inside a run the scan
+        is the local one, and only (first number, sum) of every run goes to the linear partition of
+        the numbers, which scans the runs of all ranks and answers with each run's base. The traffic
+        follows the partition boundary, not the mesh size. Entities counted by another rank get their
+        base from that rank."""
+        P, dev, me = self.size, self.device, self.rank
+        dm = self.dm
         N = self.nglobal[ent_dim]
-        chunk = (N + P - 1) // P
-        gid = self.dm.tag(ent_dim, "global")
-        depth, _, lowest = self._first_elem(ent_dim, elem_depth)
-        mine = (depth == 0) & (erank[lowest.clamp(max=erank.numel() - 1)] == self.rank)
-        idx = torch.nonzero(mine).flatten()
-        g = gid[idx]
-        if g.numel() > 1:
-            assert bool((g[1:] > g[:-1]).all().item()), "local order lost the global order"
-        dest_bounds = torch.searchsorted(g, torch.arange(P + 1, device=dev, dtype=torch.int64) * chunk)
-        sc = (dest_bounds[1:] - dest_bounds[:-1]).tolist()
-        rg, rcounts = _alltoallv(g, sc, self.group)
-        rc, _ = _alltoallv(counts[idx].contiguous(), sc, self.group)
-        lo = self.rank * chunk
-        nloc = max(min(chunk, N - lo), 0)
-        dense = torch.zeros(nloc, dtype=torch.int64, device=dev)
-        seen = torch.zeros(nloc, dtype=torch.int64, device=dev)
-        dense[rg - lo] = rc
-        seen.index_add_(0, rg - lo, torch.ones_like(rg))
-        assert bool((seen == 1).all().item()), "an old entity was counted %s" % ("twice" if bool((seen > 1).any().item()) else "by no rank")
-        incl = torch.cumsum(dense, 0)
-        total = incl[-1:].clone() if nloc else torch.zeros(1, dtype=torch.int64, device=dev)
+        chunk = max((N + P - 1) // P, 1)
+        gid = dm.tag(ent_dim, "global")
+        rk = dm.tag(ent_dim, "own:rank")
+        dp = dm.tag(ent_dim, "own:depth")
+        counted = rk == me
+        w = torch.where(counted, counts, 0)
+        incl = torch.cumsum(w, 0)
+        pre = incl - w
+        didx = torch.nonzero(counted).flatten()
+        dg = gid[didx]
+        dpre = pre[didx]
+        nd = dg.numel()
+        start = torch.ones(nd, dtype=torch.bool, device=dev)
+        if nd > 1:
+            start[1:] = dg[1:] != dg[:-1] + 1
+        rfirst = torch.nonzero(start).flatten()
+        run_gid = dg[rfirst]
+        run_pre = dpre[rfirst]
+        total = incl[-1:] if incl.numel() else torch.zeros(1, dtype=torch.int64, device=dev)
+        run_sum = torch.cat([run_pre[1:], total]) - run_pre if nd else run_pre
+        # runs -> linear partition of the old numbers -> base of every run
+        bounds = torch.searchsorted(run_gid, torch.arange(P + 1, device=dev, dtype=torch.int64) * chunk)
+        sc = (bounds[1:] - bounds[:-1]).tolist()
+        both, rcounts = _alltoallv(torch.stack([run_gid, run_sum], 1).flatten(), [2 * c for c in sc], self.group)
+        both = both.view(-1, 2)
+        rg, rs = both[:, 0], both[:, 1]
+        order = torch.argsort(rg)
+        rs_sorted = rs[order]
+        cs = torch.cumsum(rs_sorted, 0)
+        tot = cs[-1:] if cs.numel() else torch.zeros(1, dtype=torch.int64, device=dev)
         totals = torch.empty(P, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(totals, total, group=self.group)
-        base = int(totals[: self.rank].sum().item())
-        excl = incl - dense + base
-        self.nglobal_next = getattr(self, "nglobal_next", [0, 0, 0, 0])
-        self.nglobal_next[ent_dim] = int(totals.sum().item())
-        # queries: every local entity whose number can be trusted; others are clamped into range
-        q = gid.clamp(0, max(N - 1, 0))
-        order = torch.argsort(q, stable=True)
-        qs = q[order]
-        qb = torch.searchsorted(qs, torch.arange(P + 1, device=dev, dtype=torch.int64) * chunk)
-        qc = (qb[1:] - qb[:-1]).tolist()
-        asked, asked_counts = _alltoallv(qs, qc, self.group)
-        answers = excl[asked - lo]
-        got = torch.empty(qs.numel(), dtype=torch.int64, device=dev)
-        dist.all_to_all_single(got, answers, qc, asked_counts, group=self.group)
-        bases = torch.empty_like(got)
-        bases[order] = got
-        if ent_dim == self.mesh.dim():
-            self.nglobal = list(self.nglobal_next)
-        return bases
+        dist.all_gather_into_tensor(totals, tot.contiguous(), group=self.group)
+        totals_h = totals.tolist()
+        excl = torch.empty_like(rs)
+        excl[order] = cs - rs_sorted + sum(totals_h[:me])
+        run_base = torch.empty(run_gid.numel(), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(run_base, excl, sc, [c // 2 for c in rcounts], group=self.group)
+        rid = torch.cumsum(start.to(torch.int64), 0) - 1
+        bases = pre.clone()                      # uncounted, untrusted entities: any number will do
+        bases[didx] = run_base[rid] + (dpre - run_pre[rid])
+        # entities another rank counts: everything this pass trusts, and one layer more -- the
+        # representative (first triangle / tet) of a trusted key's cavity may lie in the shell
+        want = torch.nonzero((~counted) & (dp <= trust + 1)).flatten()
+        plan = self._fetch_plan(want, rk[want].to(torch.int64), gid[want], didx, dg)
+        plan.pull(bases)
+        return bases, int(sum(totals_h))
 
 
 def distribute(base, halo, device, group=None):
@@ -403,12 +464,25 @@ def distribute(base, halo, device, group=None):
         pm.set_ents(d, new_down, codes)
     for d in range(dim + 1):
         for name, ttype, nc in base.tags(d):
-            if name in ("length", "quality") or name.startswith("own:"):
+            if name.startswith("own:"):
                 continue
             t = src.tag(d, name).view(n[d], nc)[keep[d]].flatten()
             pm.set_tag(d, name, nc, t, internal=(name != "global"))
-    pm.set_tag(dim, "own:rank", 1, owner[keep[dim]].to(torch.int32))
-    pm.set_tag(dim, "own:depth", 1, depth[keep[dim]].to(torch.int8))
+    # "own:rank" / "own:depth" on every dimension: the lowest owner rank / depth over the adjacent
+    # elements, from the FULL mesh; refinement inherits both (products of an entity are adjacent to
+    # children of exactly the elements the entity was adjacent to)
+    for d in range(dim + 1):
+        if d == dim:
+            rk, dp = owner, depth
+        else:
+            c2d = src.down(dim, d)[0].to(torch.int64)
+            deg = simplex_degree(dim, d)
+            rk = torch.full((n[d],), P, dtype=torch.int64, device=dev)
+            rk.scatter_reduce_(0, c2d, owner.repeat_interleave(deg), reduce="amin", include_self=True)
+            dp = torch.full((n[d],), DEEP, dtype=torch.int64, device=dev)
+            dp.scatter_reduce_(0, c2d, depth.repeat_interleave(deg), reduce="amin", include_self=True)
+        pm.set_tag(d, "own:rank", 1, rk[keep[d]].to(torch.int32))
+        pm.set_tag(d, "own:depth", 1, dp[keep[d]].to(torch.int8))
     out = DistMesh(part, device, halo, group)
     out.nglobal = n + [0] * (4 - len(n))
     return out

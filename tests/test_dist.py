@@ -36,5 +36,6 @@ def test_partitioned_loop_matches_serial_nccl(gpu_lib):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    run_worker(2, gpu_lib.path, "cuda", 24, 4, 0, 3, 29541)
-    run_worker(2, gpu_lib.path, "cuda", 12, 8, 1, 3, 29542)
+    run_worker(2, gpu_lib.path, "cuda", 16, 4, 0, 3, 29541)
+    run_worker(2, gpu_lib.path, "cuda", 24, 5, 0, 3, 29542)
+    run_worker(2, gpu_lib.path, "cuda", 10, 10, 1, 3, 29543)
