@@ -40,6 +40,7 @@ _TYPE_OF_T = {v: k for k, v in _TT.items()}
 _PASS_DTYPE = {PASS_CANDIDATES: torch.int8, PASS_STATES: torch.int8, PASS_QUALITIES: torch.float64,
                PASS_OFFSETS: torch.int32, PASS_OLD2NEW: torch.int32, PASS_KEYS2EDGES: torch.int32}
 DEEP = 127
+CHECK = bool(int(__import__("os").environ.get("OSHB_DIST_CHECK", "0")))  # consistency asserts (tests turn them on)
 
 # optional wall-clock breakdown of the partitioned pass (OSHB_DIST_TIMING=1): every section is
 # bracketed by full synchronisation, so the numbers are for diagnosis, never for the bench
@@ -95,6 +96,13 @@ class DevMesh:
                 self._post()
                 return out
         raise _lib.OshbError("no tag %s on dimension %d" % (name, ent_dim))
+
+    def tag_into(self, ent_dim, name, out):
+        """copy a tag into a slice of a caller's buffer; the caller brackets a batch of these with
+        _pre() / _post()"""
+        assert out.is_contiguous()
+        self.lib.check(self.lib.c.oshb_mesh_get_tag(self.mesh.h, C.c_int(ent_dim), name.encode(),
+                                                    C.c_void_p(out.data_ptr()), C.c_int(0)))
 
     def set_tag(self, ent_dim, name, ncomps, t, internal=True):
         t = t.contiguous()
@@ -283,7 +291,7 @@ class DistMesh:
         counts = torch.bincount(want_owner, minlength=P).tolist()
         asked, asked_counts = _alltoallv(want_gid, counts, self.group)
         pos = torch.searchsorted(have_gid, asked).clamp(max=max(have_gid.numel() - 1, 0))
-        if asked.numel():
+        if CHECK and asked.numel():
             ok = bool((have_gid[pos] == asked).all().item()) if have_gid.numel() else False
             assert ok, "a neighbour asked for an entity this rank does not answer for"
         return FetchPlan(have_idx[pos], asked_counts, want_idx, counts, self.group)
@@ -312,7 +320,7 @@ class DistMesh:
                 edge_rank = dm.tag(EDGE, "own:rank")
                 egid = dm.tag(EDGE, "global")
                 have_idx, have_gid = self._counted(EDGE, edge_rank, egid)
-                if have_gid.numel() > 1:
+                if CHECK and have_gid.numel() > 1:
                     assert bool((have_gid[1:] > have_gid[:-1]).all().item()), "local edge order lost the global order"
                 shell = torch.nonzero(edge_depth == trust + 1).flatten()
                 plan = self._fetch_plan(shell, edge_rank[shell].to(torch.int64), egid[shell], have_idx, have_gid)
@@ -344,20 +352,21 @@ class DistMesh:
             if nkeys:
                 with _Section(dm, "number(lib)"):
                     ps.number(True)
-            nnext = [0, 0, 0, 0]
-            for d in range(dim + 1):
-                with _Section(dm, "global bases dim %d" % d):
+            with _Section(dm, "global bases"):
+                counts = []
+                for d in range(dim + 1):
                     if nkeys:
-                        off = ps.get(PASS_OFFSETS, d).to(torch.int64)
-                        counts = off[1:] - off[:-1]
+                        off = ps.get(PASS_OFFSETS, d)
+                        counts.append((off[1:] - off[:-1]).to(torch.int64))
                     else:
                         # nothing splits here, but every number shifts with the other ranks' products
-                        counts = torch.ones(mesh.nents(d), dtype=torch.int64, device=dev)
-                    bases, nnext[d] = self._global_bases(d, counts, trust)
+                        counts.append(torch.ones(mesh.nents(d), dtype=torch.int64, device=dev))
+                bases, nnext = self._global_bases(counts, trust)
+                for d in range(dim + 1):
                     if nkeys:
-                        ps.set(PASS_GLOBAL_BASES, bases, d)
+                        ps.set(PASS_GLOBAL_BASES, bases[d], d)
                     else:
-                        dm.set_tag(d, "global", 1, bases)
+                        dm.set_tag(d, "global", 1, bases[d])
             if nkeys:
                 with _Section(dm, "finish(lib)"):
                     ps.finish()
@@ -367,55 +376,78 @@ class DistMesh:
         finally:
             ps.close()
 
-    def _global_bases(self, ent_dim, counts, trust):
+    def _global_bases(self, counts_per_dim, trust):
         """modify_globals (src/Omega_h_modify.cpp:406-444): exclusive scan, in global-number order, of
-        how many new entities each old entity stands for.
+        how many new entities each old entity stands for -- all dimensions at once, on the key
+        (dimension, old global number) flattened to one dense axis.
 
-        Old global numbers are dense, so a rank sees where its own stretch of the global order is
-        interrupted: its counted entities fall into runs of consecutive numbers, inside a run the scan
-        is the local one, and only (first number, sum) of every run goes to the linear partition of
-        the numbers, which scans the runs of all ranks and answers with each run's base. The traffic
+        Old numbers are dense, so a rank sees where its own stretch of the global order is
+        interrupted: the entities it counts fall into runs of consecutive keys, inside a run the scan
+        is the local one, and only (first key, sum) of every run goes to the linear partition of
+        the key axis, which scans the runs of all ranks and answers with each run's base. The traffic
         follows the partition boundary, not the mesh size. Entities counted by another rank get their
         base from that rank."""
         P, dev, me = self.size, self.device, self.rank
-        dm = self.dm
-        N = self.nglobal[ent_dim]
+        dm, mesh = self.dm, self.mesh
+        dim = mesh.dim()
+        ns = [mesh.nents(d) for d in range(dim + 1)]
+        lo = [sum(ns[:d]) for d in range(dim + 2)]
+        koff = [sum(self.nglobal[:d]) for d in range(dim + 2)]
+        ntot, N = lo[-1], koff[-1]
         chunk = max((N + P - 1) // P, 1)
-        gid = dm.tag(ent_dim, "global")
-        rk = dm.tag(ent_dim, "own:rank")
-        dp = dm.tag(ent_dim, "own:depth")
+        key = torch.empty(ntot, dtype=torch.int64, device=dev)
+        rk = torch.empty(ntot, dtype=torch.int32, device=dev)
+        dp = torch.empty(ntot, dtype=torch.int8, device=dev)
+        dm._pre()
+        for d in range(dim + 1):
+            dm.tag_into(d, "global", key[lo[d]:lo[d + 1]])
+            dm.tag_into(d, "own:rank", rk[lo[d]:lo[d + 1]])
+            dm.tag_into(d, "own:depth", dp[lo[d]:lo[d + 1]])
+        dm._post()
+        for d in range(1, dim + 1):
+            key[lo[d]:lo[d + 1]] += koff[d]
+        counts = torch.cat(counts_per_dim)
         counted = rk == me
         w = torch.where(counted, counts, 0)
         incl = torch.cumsum(w, 0)
         pre = incl - w
+        # new entity totals per dimension
+        edges = torch.tensor([x - 1 for x in lo[1:]], device=dev, dtype=torch.int64)
+        upto = incl[edges]
+        tot_d = upto - torch.cat([upto.new_zeros(1), upto[:-1]])
         didx = torch.nonzero(counted).flatten()
-        dg = gid[didx]
+        dg = key[didx]
         dpre = pre[didx]
         nd = dg.numel()
+        if CHECK and nd > 1:
+            assert bool((dg[1:] > dg[:-1]).all().item()), "local order lost the global order"
         start = torch.ones(nd, dtype=torch.bool, device=dev)
         if nd > 1:
             start[1:] = dg[1:] != dg[:-1] + 1
         rfirst = torch.nonzero(start).flatten()
-        run_gid = dg[rfirst]
+        run_key = dg[rfirst]
         run_pre = dpre[rfirst]
-        total = incl[-1:] if incl.numel() else torch.zeros(1, dtype=torch.int64, device=dev)
-        run_sum = torch.cat([run_pre[1:], total]) - run_pre if nd else run_pre
-        # runs -> linear partition of the old numbers -> base of every run
-        bounds = torch.searchsorted(run_gid, torch.arange(P + 1, device=dev, dtype=torch.int64) * chunk)
+        run_sum = torch.cat([run_pre[1:], incl[-1:]]) - run_pre
+        # runs -> linear partition of the key axis -> base of every run
+        bounds = torch.searchsorted(run_key, torch.arange(P + 1, device=dev, dtype=torch.int64) * chunk)
         sc = (bounds[1:] - bounds[:-1]).tolist()
-        both, rcounts = _alltoallv(torch.stack([run_gid, run_sum], 1).flatten(), [2 * c for c in sc], self.group)
+        both, rcounts = _alltoallv(torch.stack([run_key, run_sum], 1).flatten(), [2 * c for c in sc], self.group)
         both = both.view(-1, 2)
         rg, rs = both[:, 0], both[:, 1]
         order = torch.argsort(rg)
         rs_sorted = rs[order]
         cs = torch.cumsum(rs_sorted, 0)
         tot = cs[-1:] if cs.numel() else torch.zeros(1, dtype=torch.int64, device=dev)
-        totals = torch.empty(P, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(totals, tot.contiguous(), group=self.group)
-        totals_h = totals.tolist()
+        gathered = torch.empty(P * (dim + 2), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, torch.cat([tot, tot_d]).contiguous(), group=self.group)
+        gathered = gathered.view(P, dim + 2)
+        below = int(gathered[:me, 0].sum().item())
+        nnext = [int(x) for x in gathered[:, 1:].sum(0).tolist()] + [0] * (3 - dim)
+        if CHECK:
+            assert int(gathered[:, 0].sum().item()) == sum(nnext)
         excl = torch.empty_like(rs)
-        excl[order] = cs - rs_sorted + sum(totals_h[:me])
-        run_base = torch.empty(run_gid.numel(), dtype=torch.int64, device=dev)
+        excl[order] = cs - rs_sorted + below
+        run_base = torch.empty(run_key.numel(), dtype=torch.int64, device=dev)
         dist.all_to_all_single(run_base, excl, sc, [c // 2 for c in rcounts], group=self.group)
         rid = torch.cumsum(start.to(torch.int64), 0) - 1
         bases = pre.clone()                      # uncounted, untrusted entities: any number will do
@@ -423,9 +455,12 @@ class DistMesh:
         # entities another rank counts: everything this pass trusts, and one layer more -- the
         # representative (first triangle / tet) of a trusted key's cavity may lie in the shell
         want = torch.nonzero((~counted) & (dp <= trust + 1)).flatten()
-        plan = self._fetch_plan(want, rk[want].to(torch.int64), gid[want], didx, dg)
+        plan = self._fetch_plan(want, rk[want].to(torch.int64), key[want], didx, dg)
         plan.pull(bases)
-        return bases, int(sum(totals_h))
+        out = []
+        for d in range(dim + 1):
+            out.append(bases[lo[d]:lo[d + 1]] - sum(nnext[:d]))
+        return out, nnext
 
 
 def distribute(base, halo, device, group=None):

@@ -16,6 +16,7 @@ def run_worker(nranks, lib_path, device, n, halo, aniso, dim, port, timeout=900)
            str(aniso), str(dim)]
     env = dict(os.environ)
     env["OMP_NUM_THREADS"] = "1"
+    env["OSHB_DIST_CHECK"] = "1"
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     return r.stdout
