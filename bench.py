@@ -15,8 +15,9 @@ metric h = 1/(2n) (4 doubling passes, 1,572,864 -> 25,165,824 tets, 23,592,960 n
   cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref, OpenMP build) on the
           box's host cores, bounded sample of the same workload
 
-N > 1 (round 1): every rank refines its own box (independent replicas, no ghost exchange yet
--- see DESIGN.md "multi-GPU"); value = sum of new tets / max time.
+N > 1: ONE box of N x n^3 cells partitioned over the ranks (omega_h_b200/dist.py, DESIGN.md
+"Multi-GPU"): weak scaling, value = global new tets / max-over-ranks time. --replicas: N
+independent boxes instead.
 """
 import argparse
 import json
