@@ -201,6 +201,33 @@ int oshb_pass_finish(oshb_pass* p);
 int oshb_pass_size(oshb_pass* p, int which, int dim, int64_t* n);
 int oshb_pass_get(oshb_pass* p, int which, int dim, void* out, int host);
 int oshb_pass_set(oshb_pass* p, int which, int dim, const void* in, int host);
+/* values of a per-edge pass array (STATES / QUALITIES) at a list of edges, out and back in: what
+ * a rank sends to / receives from its neighbours after sync points (the reference's
+ * Dist::exch of the shared entities, src/Omega_h_dist.cpp:80-138) */
+int oshb_pass_gather(oshb_pass* p, int which, const int32_t* edges, int64_t n, void* out, int host);
+int oshb_pass_scatter(oshb_pass* p, int which, const int32_t* edges, int64_t n, const void* in, int host);
+
+/* Distributed numbering, the volume work of modify_globals (src/Omega_h_modify.cpp:406-444) on
+ * a partitioned mesh whose entities carry "own:rank" (int32: the rank that counts the entity)
+ * and "own:depth" (int8) tags on every dimension; call between number and finish (or after
+ * select_keys returned 0 keys: every entity then counts once and commit renumbers in place).
+ * Keys flatten (dimension, old global number) into one axis: key = number + key_offset[dim].
+ *   runs_begin   scans the counts of the entities my_rank counts; lists the runs of consecutive
+ *                keys among them, and the "wanted" entities (counted elsewhere, depth <= trust+1)
+ *   runs_get     (first key, sum of counts) per run, in increasing key order
+ *   runs_set_bases  the caller's answer: the global exclusive scan at each run's first key;
+ *                new_offset[d] = global number of new entities of dimensions < d
+ *   want_get / runs_lookup / want_set   key + owner rank of every wanted entity; the owner
+ *                translates keys to bases; the requester stores them (same order as want_get)
+ *   runs_commit  hands the bases to finish (OSHB_PASS_GLOBAL_BASES) */
+int oshb_pass_runs_begin(oshb_pass* p, int32_t my_rank, int32_t trust_depth, const int64_t* key_offset,
+    int64_t* nruns, int64_t* nwant, int64_t* new_counts /* [4] */);
+int oshb_pass_runs_get(oshb_pass* p, int64_t* run_key, int64_t* run_sum, int host);
+int oshb_pass_runs_set_bases(oshb_pass* p, const int64_t* run_base, const int64_t* new_offset /* [4] */, int host);
+int oshb_pass_want_get(oshb_pass* p, int64_t* want_key, int32_t* want_owner, int host);
+int oshb_pass_runs_lookup(oshb_pass* p, const int64_t* keys, int64_t n, int64_t* bases_out, int host);
+int oshb_pass_want_set(oshb_pass* p, const int64_t* bases, int host);
+int oshb_pass_runs_commit(oshb_pass* p);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * CUDA-event timer and per-kernel event timing on the library's own stream

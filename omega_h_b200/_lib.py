@@ -59,7 +59,9 @@ SYMBOLS = [
     "oshb_rep_vertex2md_order", "oshb_refine_by_size", "oshb_last_pass_stats",
     "oshb_pass_create", "oshb_pass_destroy", "oshb_pass_begin", "oshb_pass_restate", "oshb_pass_indset_round",
     "oshb_pass_select_keys", "oshb_pass_number", "oshb_pass_finish", "oshb_pass_size", "oshb_pass_get",
-    "oshb_pass_set",
+    "oshb_pass_set", "oshb_pass_gather", "oshb_pass_scatter", "oshb_pass_runs_begin", "oshb_pass_runs_get",
+    "oshb_pass_runs_set_bases", "oshb_pass_want_get", "oshb_pass_runs_lookup", "oshb_pass_want_set",
+    "oshb_pass_runs_commit",
     "oshb_timer_start", "oshb_timer_stop", "oshb_profile_begin", "oshb_profile_end", "oshb_host_alloc",
     "oshb_host_free", "oshb_host_time_stats",
 ]

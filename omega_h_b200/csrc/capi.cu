@@ -45,6 +45,15 @@ static void export_array(DArr<T> const& a, T* out, int host) {
     d2d(out, a.data(), size_t(a.size()) * sizeof(T));
 }
 
+template <class T>
+static void gather_scatter(T* arr, LO const* idx, int64_t n, T* buf, bool scatter) {
+  if (scatter) {
+    parallel_for(n, OSHB_LAMBDA(LO i) { arr[idx[i]] = buf[i]; }, "pass_scatter");
+  } else {
+    parallel_for(n, OSHB_LAMBDA(LO i) { buf[i] = arr[idx[i]]; }, "pass_gather");
+  }
+}
+
 extern "C" {
 
 int oshb_init(int device) {
@@ -566,6 +575,93 @@ int oshb_pass_get(oshb_pass* p, int which, int dim, void* out, int host) {
   }
   OSHB_CATCH
 }
+static void pass_gather_scatter(oshb_pass* p, int which, const int32_t* edges, int64_t n, void* buf, int host,
+    bool scatter) {
+  OSHB_CHECK(which == OSHB_PASS_STATES || which == OSHB_PASS_QUALITIES);
+  void* ptr;
+  int64_t na;
+  int eb;
+  pass_array(reinterpret_cast<Pass*>(p), which, 0, &ptr, &na, &eb);
+  if (n == 0) return;
+  LOs idx = import_array<LO>(edges, n, host);
+  if (eb == 1) {
+    Bytes b = scatter ? import_array<I8>(static_cast<I8 const*>(buf), n, host) : Bytes(n);
+    gather_scatter<I8>(static_cast<I8*>(ptr), idx.data(), n, b.data(), scatter);
+    if (!scatter) export_array(b, static_cast<I8*>(buf), host);
+  } else {
+    Reals b = scatter ? import_array<Real>(static_cast<Real const*>(buf), n, host) : Reals(n);
+    gather_scatter<Real>(static_cast<Real*>(ptr), idx.data(), n, b.data(), scatter);
+    if (!scatter) export_array(b, static_cast<Real*>(buf), host);
+  }
+  if (host) sync_stream();
+}
+int oshb_pass_gather(oshb_pass* p, int which, const int32_t* edges, int64_t n, void* out, int host) {
+  OSHB_TRY
+  pass_gather_scatter(p, which, edges, n, out, host, false);
+  OSHB_CATCH
+}
+int oshb_pass_scatter(oshb_pass* p, int which, const int32_t* edges, int64_t n, const void* in, int host) {
+  OSHB_TRY
+  pass_gather_scatter(p, which, edges, n, const_cast<void*>(in), host, true);
+  OSHB_CATCH
+}
+
+// ---- distributed numbering ----------------------------------------------------------------------
+int oshb_pass_runs_begin(oshb_pass* p, int32_t my_rank, int32_t trust_depth, const int64_t* key_offset,
+    int64_t* nruns, int64_t* nwant, int64_t* new_counts) {
+  OSHB_TRY
+  pass_runs_begin(reinterpret_cast<Pass*>(p), my_rank, trust_depth, reinterpret_cast<GO const*>(key_offset), nruns,
+      nwant, reinterpret_cast<GO*>(new_counts));
+  OSHB_CATCH
+}
+int oshb_pass_runs_get(oshb_pass* p, int64_t* run_key, int64_t* run_sum, int host) {
+  OSHB_TRY
+  GOs k, s;
+  pass_runs_get(reinterpret_cast<Pass*>(p), &k, &s);
+  export_array(k, reinterpret_cast<GO*>(run_key), host);
+  export_array(s, reinterpret_cast<GO*>(run_sum), host);
+  if (!host) sync_stream();
+  OSHB_CATCH
+}
+int oshb_pass_runs_set_bases(oshb_pass* p, const int64_t* run_base, const int64_t* new_offset, int host) {
+  OSHB_TRY
+  Pass* ps = reinterpret_cast<Pass*>(p);
+  pass_runs_set_bases(ps, import_array<GO>(reinterpret_cast<GO const*>(run_base), pass_nruns(ps), host),
+      reinterpret_cast<GO const*>(new_offset));
+  if (host) sync_stream();
+  OSHB_CATCH
+}
+int oshb_pass_want_get(oshb_pass* p, int64_t* want_key, int32_t* want_owner, int host) {
+  OSHB_TRY
+  GOs k;
+  LOs o;
+  pass_want_get(reinterpret_cast<Pass*>(p), &k, &o);
+  export_array(k, reinterpret_cast<GO*>(want_key), host);
+  export_array(o, want_owner, host);
+  if (!host) sync_stream();
+  OSHB_CATCH
+}
+int oshb_pass_runs_lookup(oshb_pass* p, const int64_t* keys, int64_t n, int64_t* bases_out, int host) {
+  OSHB_TRY
+  GOs out = pass_runs_lookup(reinterpret_cast<Pass*>(p), import_array<GO>(reinterpret_cast<GO const*>(keys), n, host));
+  export_array(out, reinterpret_cast<GO*>(bases_out), host);
+  if (!host) sync_stream();
+  OSHB_CATCH
+}
+int oshb_pass_want_set(oshb_pass* p, const int64_t* bases, int host) {
+  OSHB_TRY
+  Pass* ps = reinterpret_cast<Pass*>(p);
+  // the want list's length is fixed by runs_begin
+  pass_want_set(ps, import_array<GO>(reinterpret_cast<GO const*>(bases), pass_nwant(ps), host));
+  if (host) sync_stream();
+  OSHB_CATCH
+}
+int oshb_pass_runs_commit(oshb_pass* p) {
+  OSHB_TRY
+  pass_runs_commit(reinterpret_cast<Pass*>(p));
+  OSHB_CATCH
+}
+
 int oshb_pass_set(oshb_pass* p, int which, int dim, const void* in, int host) {
   OSHB_TRY
   Pass* ps = reinterpret_cast<Pass*>(p);

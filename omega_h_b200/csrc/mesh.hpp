@@ -200,6 +200,16 @@ LOs pass_keys2edges(Pass* p);
 LOs pass_offsets(Pass* p, int d);
 LOs pass_old2new(Pass* p, int d);
 void pass_set_global_bases(Pass* p, int d, GOs bases);
+// distributed numbering helpers (select.cu, "distributed numbering")
+void pass_runs_begin(Pass* p, int me, int trust, GO const* koff, int64_t* nruns, int64_t* nwant, GO* new_counts);
+void pass_runs_get(Pass* p, GOs* run_key, GOs* run_sum);
+void pass_want_get(Pass* p, GOs* want_key, LOs* want_owner);
+void pass_runs_set_bases(Pass* p, GOs run_base, GO const* new_off);
+GOs pass_runs_lookup(Pass* p, GOs keys);
+void pass_want_set(Pass* p, GOs values);
+void pass_runs_commit(Pass* p);
+LO pass_nruns(Pass* p);
+LO pass_nwant(Pass* p);
 LOs rep_vertex_order_from_keys(LOs ev2v, LO nverts, LO nedges, LOs keys2edges, LOs* keys_order_out,
     LOs* vert2keys_off_out, LOs* vert_keys_out);  // refine.cu
 

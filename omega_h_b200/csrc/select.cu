@@ -214,6 +214,27 @@ struct Pass {
   int rounds = 0;
   bool flags_clean = false;
   int* flags3 = nullptr;
+  // distributed numbering (runs_begin .. runs_commit): all dimensions on one concatenated axis
+  struct Numbering {
+    int me = 0, trust = 0, dim = 0;
+    GO koff[5] = {0, 0, 0, 0, 0};
+    GO new_off[4] = {0, 0, 0, 0};
+    LO lo[5] = {0, 0, 0, 0, 0};
+    GOs gid[4];
+    LOs rk[4];
+    Bytes dp[4];
+    Bytes start;
+    LOs rid;       // exclusive scan of start
+    GOs pre;       // exclusive scan of the counted counts (ntot + 1)
+    LOs run_pos, want_pos;
+    GOs run_key, run_delta;  // run_delta = base - pre at the run's first entity (after set_bases)
+    GOs bases[4];
+  } nb;
+  void runs_begin(int me, int trust, GO const* koff, int64_t* nruns, int64_t* nwant, GO* new_counts);
+  void runs_set_bases(GOs run_base, GO const* new_off);
+  GOs runs_lookup(GOs keys);
+  void want_set(GOs values);
+  void runs_commit();
   ~Pass() {
     if (rb) rebuild_discard(rb);
   }
@@ -432,6 +453,212 @@ void Pass::finish() {
   device_error_check("refine_element_based");
 }
 
+
+// ---- distributed numbering ------------------------------------------------------------------
+// modify_globals (src/Omega_h_modify.cpp:406-444) for a partitioned mesh, the volume work. The
+// caller (omega_h_b200/dist.py) owns the exchanges. Every entity is counted by one rank, the one
+// in its "own:rank" tag. Old global numbers are dense, so the entities a rank counts fall into
+// runs of consecutive numbers at consecutive local positions; inside a run the global scan is
+// the local scan. runs_begin scans the counted counts and lists the runs (first key, sum); the
+// caller has them scanned across ranks and returns each run's base (runs_set_bases); entities
+// counted elsewhere ("want": uncounted, depth <= trust + 1) are looked up on their owner
+// (runs_lookup there, want_set here). Keys flatten (dimension, number) into one axis.
+void Pass::runs_begin(int me, int trust, GO const* koff, int64_t* nruns, int64_t* nwant, GO* new_counts) {
+  Numbering& n = nb;
+  n.me = me;
+  n.trust = trust;
+  n.dim = mesh->dim();
+  n.lo[0] = 0;
+  for (int d = 0; d <= n.dim; ++d) {
+    n.koff[d] = koff[d];
+    n.lo[d + 1] = n.lo[d] + mesh->nents(d);
+    n.gid[d] = mesh->globals(d);
+    n.rk[d] = mesh->get_los(d, "own:rank");
+    n.dp[d] = mesh->get_bytes(d, "own:depth");
+  }
+  LO const ntot = n.lo[n.dim + 1];
+  LOs w(ntot);
+  n.start = Bytes(ntot);
+  Bytes wantm(ntot);
+  for (int d = 0; d <= n.dim; ++d) {
+    LO const nd = mesh->nents(d);
+    LO const lo = n.lo[d];
+    GO const* gid = n.gid[d].data();
+    LO const* rk = n.rk[d].data();
+    I8 const* dp = n.dp[d].data();
+    LO const* off = rb ? pass_offsets(this, d).data() : nullptr;
+    LO* wp = w.data();
+    I8* sp = n.start.data();
+    I8* wm = wantm.data();
+    parallel_for(nd, OSHB_LAMBDA(LO i) {
+      bool counted = (rk[i] == me);
+      LO cnt = off ? (off[i + 1] - off[i]) : 1;
+      wp[lo + i] = counted ? cnt : 0;
+      // continues a run iff the local predecessor is counted and holds the previous number
+      bool cont = counted && i > 0 && rk[i - 1] == me && gid[i - 1] + 1 == gid[i];
+      sp[lo + i] = (counted && !cont) ? 1 : 0;
+      wm[lo + i] = (!counted && dp[i] <= trust + 1) ? 1 : 0;
+    }, "numbering(mark)");
+  }
+  n.pre = GOs(int64_t(ntot) + 1);
+  scan_offsets(w.data(), ntot, n.pre.data());
+  n.rid = offset_scan(n.start);
+  LO nr = 0, nw = 0;
+  n.run_pos = collect_marked(n.start, &nr);
+  n.want_pos = collect_marked(wantm, &nw);
+  n.run_key = GOs(nr);
+  n.run_delta = GOs(nr);  // holds the run sums until set_bases
+  {
+    // dimension of a concatenated position: lo[] is tiny, kept in registers
+    LO const l1 = n.lo[1], l2 = n.lo[2], l3 = n.lo[3];
+    GO const k0 = n.koff[0], k1 = n.koff[1], k2 = n.koff[2], k3 = n.koff[3];
+    GO const* g0 = n.gid[0].data();
+    GO const* g1 = n.gid[1].data();
+    GO const* g2 = n.dim >= 2 ? n.gid[2].data() : nullptr;
+    GO const* g3 = n.dim >= 3 ? n.gid[3].data() : nullptr;
+    int const dim_ = n.dim;
+    LO const* rp = n.run_pos.data();
+    GO const* pre = n.pre.data();
+    GO* rkey = n.run_key.data();
+    GO* rsum = n.run_delta.data();
+    parallel_for(nr, OSHB_LAMBDA(LO r) {
+      LO pos = rp[r];
+      GO key;
+      if (pos < l1) key = g0[pos] + k0;
+      else if (pos < l2 || dim_ < 2) key = g1[pos - l1] + k1;
+      else if (pos < l3 || dim_ < 3) key = g2[pos - l2] + k2;
+      else key = g3[pos - l3] + k3;
+      rkey[r] = key;
+      LO next = (r + 1 < nr) ? rp[r + 1] : ntot;
+      rsum[r] = pre[next] - pre[pos];
+    }, "numbering(runs)");
+  }
+  // counted new entities per dimension
+  {
+    GOs cnts(4);
+    GO* cp = cnts.data();
+    GO const* pre = n.pre.data();
+    LO const l0 = n.lo[0], l1 = n.lo[1], l2 = n.lo[2], l3 = n.lo[3], l4 = n.lo[4];
+    int const dim_ = n.dim;
+    parallel_for(4, OSHB_LAMBDA(LO d) {
+      LO a = (d == 0) ? l0 : (d == 1 ? l1 : (d == 2 ? l2 : l3));
+      LO b = (d == 0) ? l1 : (d == 1 ? l2 : (d == 2 ? l3 : l4));
+      cp[d] = (d <= dim_) ? pre[b] - pre[a] : 0;
+    }, "numbering(totals)");
+    d2h(new_counts, cnts.data(), 4 * sizeof(GO));
+  }
+  *nruns = nr;
+  *nwant = nw;
+}
+
+void Pass::runs_set_bases(GOs run_base, GO const* new_off) {
+  Numbering& n = nb;
+  LO const nr = LO(n.run_pos.size());
+  OSHB_CHECK(run_base.size() == nr);
+  {
+    GO const* rbp = run_base.data();
+    GO const* pre = n.pre.data();
+    LO const* rp = n.run_pos.data();
+    GO* delta = n.run_delta.data();
+    parallel_for(nr, OSHB_LAMBDA(LO r) { delta[r] = rbp[r] - pre[rp[r]]; }, "numbering(run_delta)");
+  }
+  for (int d = 0; d <= n.dim; ++d) {
+    n.new_off[d] = new_off[d];
+    LO const nd = mesh->nents(d);
+    LO const lo = n.lo[d];
+    n.bases[d] = GOs(nd);
+    GO* bp = n.bases[d].data();
+    LO const* rk = n.rk[d].data();
+    GO const* pre = n.pre.data();
+    I8 const* sp = n.start.data();
+    LO const* rid = n.rid.data();
+    GO const* delta = n.run_delta.data();
+    int const me = n.me;
+    GO const noff = new_off[d];
+    parallel_for(nd, OSHB_LAMBDA(LO i) {
+      LO pos = lo + i;
+      GO b = pre[pos];  // uncounted + untrusted: any number will do
+      if (rk[i] == me) b += delta[rid[pos] + sp[pos] - 1] - noff;
+      bp[i] = b;
+    }, "numbering(bases)");
+  }
+}
+
+// owner side: bases of the asked keys (all of them counted here)
+GOs Pass::runs_lookup(GOs keys) {
+  Numbering& n = nb;
+  LO const nk = LO(keys.size());
+  GOs out(nk);
+  LO const nr = LO(n.run_pos.size());
+  GO const* kp = keys.data();
+  GO* op = out.data();
+  GO const* rkey = n.run_key.data();
+  LO const* rp = n.run_pos.data();
+  LO const l1 = n.lo[1], l2 = n.lo[2], l3 = n.lo[3], l4 = n.lo[n.dim + 1];
+  int const dim_ = n.dim;
+  GO const* b0 = n.bases[0].data();
+  GO const* b1 = n.bases[1].data();
+  GO const* b2 = n.dim >= 2 ? n.bases[2].data() : nullptr;
+  GO const* b3 = n.dim >= 3 ? n.bases[3].data() : nullptr;
+  int* err = device_error_cell();
+  parallel_for(nk, OSHB_LAMBDA(LO j) {
+    GO key = kp[j];
+    // last run whose first key is <= key
+    LO a = 0, b = nr;
+    while (a < b) {
+      LO m = a + (b - a) / 2;
+      if (rkey[m] <= key) a = m + 1;
+      else b = m;
+    }
+    LO r = a - 1;
+    int64_t pos = (r >= 0) ? int64_t(rp[r]) + (key - rkey[r]) : -1;
+    LO next = (r >= 0 && r + 1 < nr) ? rp[r + 1] : l4;
+    if (pos < 0 || pos >= next) {
+      raise_flag(err, 8);  // asked for an entity this rank does not count
+      op[j] = -1;
+      return;
+    }
+    LO p = LO(pos);
+    if (p < l1) op[j] = b0[p];
+    else if (p < l2 || dim_ < 2) op[j] = b1[p - l1];
+    else if (p < l3 || dim_ < 3) op[j] = b2[p - l2];
+    else op[j] = b3[p - l3];
+  }, "numbering(lookup)");
+  return out;
+}
+
+void Pass::want_set(GOs values) {
+  Numbering& n = nb;
+  LO const nw = LO(n.want_pos.size());
+  OSHB_CHECK(values.size() == nw);
+  LO const* wp = n.want_pos.data();
+  GO const* vp = values.data();
+  LO const l1 = n.lo[1], l2 = n.lo[2], l3 = n.lo[3];
+  int const dim_ = n.dim;
+  GO* b0 = n.bases[0].data();
+  GO* b1 = n.bases[1].data();
+  GO* b2 = n.dim >= 2 ? n.bases[2].data() : nullptr;
+  GO* b3 = n.dim >= 3 ? n.bases[3].data() : nullptr;
+  parallel_for(nw, OSHB_LAMBDA(LO j) {
+    LO p = wp[j];
+    if (p < l1) b0[p] = vp[j];
+    else if (p < l2 || dim_ < 2) b1[p - l1] = vp[j];
+    else if (p < l3 || dim_ < 3) b2[p - l2] = vp[j];
+    else b3[p - l3] = vp[j];
+  }, "numbering(want_set)");
+}
+
+// hand the bases to the rebuild (or, when nothing splits on this rank, renumber in place)
+void Pass::runs_commit() {
+  Numbering& n = nb;
+  device_error_check("numbering");
+  for (int d = 0; d <= n.dim; ++d) {
+    if (rb) rebuild_set_global_bases(rb, d, n.bases[d]);
+    else mesh->add_tag(d, "global", 1, n.bases[d], true);
+  }
+  n = Numbering();
+}
+
 bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
   Pass p;
   p.mesh = mesh;
@@ -467,5 +694,45 @@ LOs pass_keys2edges(Pass* p) { return p->sel.keys2edges; }
 LOs pass_offsets(Pass* p, int d) { return rebuild_offsets(p->rb, d); }
 LOs pass_old2new(Pass* p, int d) { return rebuild_old2new(p->rb, d); }
 void pass_set_global_bases(Pass* p, int d, GOs bases) { rebuild_set_global_bases(p->rb, d, bases); }
+void pass_runs_begin(Pass* p, int me, int trust, GO const* koff, int64_t* nruns, int64_t* nwant, GO* new_counts) {
+  p->runs_begin(me, trust, koff, nruns, nwant, new_counts);
+}
+void pass_runs_get(Pass* p, GOs* run_key, GOs* run_sum) {
+  *run_key = p->nb.run_key;
+  *run_sum = p->nb.run_delta;
+}
+void pass_want_get(Pass* p, GOs* want_key, LOs* want_owner) {
+  Pass::Numbering& n = p->nb;
+  LO const nw = LO(n.want_pos.size());
+  *want_key = GOs(nw);
+  *want_owner = LOs(nw);
+  GO* wk = want_key->data();
+  LO* wo = want_owner->data();
+  LO const* wp = n.want_pos.data();
+  LO const l1 = n.lo[1], l2 = n.lo[2], l3 = n.lo[3];
+  int const dim_ = n.dim;
+  GO const k0 = n.koff[0], k1 = n.koff[1], k2 = n.koff[2], k3 = n.koff[3];
+  GO const* g0 = n.gid[0].data();
+  GO const* g1 = n.gid[1].data();
+  GO const* g2 = n.dim >= 2 ? n.gid[2].data() : nullptr;
+  GO const* g3 = n.dim >= 3 ? n.gid[3].data() : nullptr;
+  LO const* r0 = n.rk[0].data();
+  LO const* r1 = n.rk[1].data();
+  LO const* r2 = n.dim >= 2 ? n.rk[2].data() : nullptr;
+  LO const* r3 = n.dim >= 3 ? n.rk[3].data() : nullptr;
+  parallel_for(nw, OSHB_LAMBDA(LO j) {
+    LO p = wp[j];
+    if (p < l1) wk[j] = g0[p] + k0, wo[j] = r0[p];
+    else if (p < l2 || dim_ < 2) wk[j] = g1[p - l1] + k1, wo[j] = r1[p - l1];
+    else if (p < l3 || dim_ < 3) wk[j] = g2[p - l2] + k2, wo[j] = r2[p - l2];
+    else wk[j] = g3[p - l3] + k3, wo[j] = r3[p - l3];
+  }, "numbering(want_get)");
+}
+void pass_runs_set_bases(Pass* p, GOs run_base, GO const* new_off) { p->runs_set_bases(run_base, new_off); }
+GOs pass_runs_lookup(Pass* p, GOs keys) { return p->runs_lookup(keys); }
+void pass_want_set(Pass* p, GOs values) { p->want_set(values); }
+void pass_runs_commit(Pass* p) { p->runs_commit(); }
+LO pass_nruns(Pass* p) { return LO(p->nb.run_pos.size()); }
+LO pass_nwant(Pass* p) { return LO(p->nb.want_pos.size()); }
 
 }  // namespace oshb

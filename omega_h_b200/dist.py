@@ -47,6 +47,7 @@ CHECK = bool(int(__import__("os").environ.get("OSHB_DIST_CHECK", "0")))  # consi
 import os as _os
 import time as _time
 TIMING = {} if _os.environ.get("OSHB_DIST_TIMING") else None
+TIMING_SYNC = _os.environ.get("OSHB_DIST_TIMING") == "1"   # "2": host clock only, no added synchronisation
 
 
 class _Section:
@@ -54,6 +55,8 @@ class _Section:
         self.dmesh, self.name = dmesh, name
 
     def _sync(self):
+        if not TIMING_SYNC:
+            return
         self.dmesh.lib.sync()
         if self.dmesh.device.type == "cuda":
             torch.cuda.synchronize(self.dmesh.device)
@@ -193,11 +196,73 @@ class _Pass:
         self.dm._post()
 
 
+    # values of a per-edge array at a list of edges
+    def gather(self, which, edges32):
+        out = self.dm.empty(edges32.numel(), _PASS_DTYPE[which])
+        self.dm._pre()
+        self.lib.check(self.lib.c.oshb_pass_gather(self.h, C.c_int(which), C.c_void_p(edges32.data_ptr()),
+                                                   C.c_int64(edges32.numel()), C.c_void_p(out.data_ptr()), C.c_int(0)))
+        self.dm._post()
+        return out
+
+    def scatter(self, which, edges32, values):
+        values = values.contiguous()
+        self.dm._pre()
+        self.lib.check(self.lib.c.oshb_pass_scatter(self.h, C.c_int(which), C.c_void_p(edges32.data_ptr()),
+                                                    C.c_int64(edges32.numel()), C.c_void_p(values.data_ptr()), C.c_int(0)))
+        self.dm._post()
+
+    # distributed numbering (include/oshb.h)
+    def runs_begin(self, me, trust, koff):
+        ko = (C.c_int64 * 5)(*[int(x) for x in koff])
+        nruns, nwant = C.c_int64(), C.c_int64()
+        newc = (C.c_int64 * 4)()
+        self.lib.check(self.lib.c.oshb_pass_runs_begin(self.h, C.c_int32(me), C.c_int32(trust), ko, C.byref(nruns),
+                                                       C.byref(nwant), newc))
+        return nruns.value, nwant.value, [int(x) for x in newc]
+
+    def runs_get(self, nruns):
+        k, s = self.dm.empty(nruns, torch.int64), self.dm.empty(nruns, torch.int64)
+        self.dm._pre()
+        self.lib.check(self.lib.c.oshb_pass_runs_get(self.h, C.c_void_p(k.data_ptr()), C.c_void_p(s.data_ptr()), C.c_int(0)))
+        return k, s
+
+    def runs_set_bases(self, run_base, new_off):
+        no = (C.c_int64 * 4)(*[int(x) for x in new_off])
+        run_base = run_base.contiguous()
+        self.dm._pre()
+        self.lib.check(self.lib.c.oshb_pass_runs_set_bases(self.h, C.c_void_p(run_base.data_ptr()), no, C.c_int(0)))
+        self.dm._post()
+
+    def want_get(self, nwant):
+        k, o = self.dm.empty(nwant, torch.int64), self.dm.empty(nwant, torch.int32)
+        self.dm._pre()
+        self.lib.check(self.lib.c.oshb_pass_want_get(self.h, C.c_void_p(k.data_ptr()), C.c_void_p(o.data_ptr()), C.c_int(0)))
+        return k, o
+
+    def runs_lookup(self, keys):
+        keys = keys.contiguous()
+        out = self.dm.empty(keys.numel(), torch.int64)
+        self.dm._pre()
+        self.lib.check(self.lib.c.oshb_pass_runs_lookup(self.h, C.c_void_p(keys.data_ptr()), C.c_int64(keys.numel()),
+                                                        C.c_void_p(out.data_ptr()), C.c_int(0)))
+        return out
+
+    def want_set(self, values):
+        values = values.contiguous()
+        self.dm._pre()
+        self.lib.check(self.lib.c.oshb_pass_want_set(self.h, C.c_void_p(values.data_ptr()), C.c_int(0)))
+        self.dm._post()
+
+    def runs_commit(self):
+        self.lib.check(self.lib.c.oshb_pass_runs_commit(self.h))
+
+
 # ---- collectives ------------------------------------------------------------------------------
 def _tick(name, t0, dev):
     if TIMING is None:
         return 0.0
-    if dev.type == "cuda":
+    if dev.type == "cuda" and TIMING_SYNC:
         torch.cuda.synchronize(dev)
     t1 = _time.perf_counter()
     if t0:
@@ -243,6 +308,16 @@ class FetchPlan:
         values[self.recv_idx] = recv
         return values
 
+    def pull_pass_array(self, ps, which):
+        """the same for one of the pass's per-edge arrays, touching only the listed edges"""
+        if not hasattr(self, "send32"):
+            self.send32 = self.send_idx.to(torch.int32)
+            self.recv32 = self.recv_idx.to(torch.int32)
+        out = ps.gather(which, self.send32)
+        recv = torch.empty(sum(self.recv_counts), dtype=out.dtype, device=out.device)
+        dist.all_to_all_single(recv, out, list(self.recv_counts), list(self.send_counts), group=self.group)
+        ps.scatter(which, self.recv32, recv)
+
 
 class DistMesh:
     def __init__(self, mesh, device, halo, group=None):
@@ -282,19 +357,31 @@ class DistMesh:
         idx = torch.nonzero(rank_tag == self.rank).flatten()
         return idx, gid[idx]
 
-    def _fetch_plan(self, want_idx, want_owner, want_gid, have_idx, have_gid):
+    def _fetch_plan(self, want_idx, want_owner, want_gid, have_idx, have_gid, runs=None):
         """want_*: local entities whose value lives on another rank (want_owner);
-        have_*: this rank's counted entities sorted by global number (the lookup table)."""
+        have_*: this rank's counted entities sorted by global number (the lookup table), or
+        runs = (first key of every run of counted entities, its local position, all local keys)."""
         P = self.size
         order = torch.argsort(want_owner, stable=True)
         want_idx, want_owner, want_gid = want_idx[order], want_owner[order], want_gid[order]
         counts = torch.bincount(want_owner, minlength=P).tolist()
         asked, asked_counts = _alltoallv(want_gid, counts, self.group)
-        pos = torch.searchsorted(have_gid, asked).clamp(max=max(have_gid.numel() - 1, 0))
+        if runs is not None:
+            run_key, run_pos, key = runs
+            if asked.numel() and run_key.numel():
+                r = (torch.searchsorted(run_key, asked, right=True) - 1).clamp(min=0)
+                pos = (run_pos[r] + (asked - run_key[r])).clamp(0, key.numel() - 1)
+            else:
+                pos = torch.zeros_like(asked)
+            found = key[pos] if asked.numel() else asked
+        else:
+            pos = torch.searchsorted(have_gid, asked).clamp(max=max(have_gid.numel() - 1, 0))
+            found = have_gid[pos] if have_gid.numel() else asked - 1
+            if have_idx is not None:
+                pos = have_idx[pos]
         if CHECK and asked.numel():
-            ok = bool((have_gid[pos] == asked).all().item()) if have_gid.numel() else False
-            assert ok, "a neighbour asked for an entity this rank does not answer for"
-        return FetchPlan(have_idx[pos], asked_counts, want_idx, counts, self.group)
+            assert bool((found == asked).all().item()), "a neighbour asked for an entity this rank does not answer for"
+        return FetchPlan(pos, asked_counts, want_idx, counts, self.group)
 
     # ---- the pass -------------------------------------------------------------------------------
     def refine_by_size(self, opts=None):
@@ -325,8 +412,7 @@ class DistMesh:
                 shell = torch.nonzero(edge_depth == trust + 1).flatten()
                 plan = self._fetch_plan(shell, edge_rank[shell].to(torch.int64), egid[shell], have_idx, have_gid)
             with _Section(dm, "qualities exchange"):
-                quals = plan.pull(ps.get(PASS_QUALITIES).view(torch.int64)).view(torch.float64)
-                ps.set(PASS_QUALITIES, quals)
+                plan.pull_pass_array(ps, PASS_QUALITIES)
                 ps.restate()
                 state = ps.get(PASS_STATES)
                 any_good = bool(((state == UNKNOWN) & mine).any().item())
@@ -337,8 +423,8 @@ class DistMesh:
                 with _Section(dm, "indset round(lib)"):
                     ps.indset_round()
                 with _Section(dm, "indset exchange"):
-                    state = plan.pull(ps.get(PASS_STATES))
-                    ps.set(PASS_STATES, state)
+                    plan.pull_pass_array(ps, PASS_STATES)
+                    state = ps.get(PASS_STATES)
                     rounds += 1
                     more = _any_rank(bool(((state == UNKNOWN) & mine).any().item()), dev, self.group)
                 if not more:
@@ -352,21 +438,9 @@ class DistMesh:
             if nkeys:
                 with _Section(dm, "number(lib)"):
                     ps.number(True)
-            with _Section(dm, "global bases"):
-                counts = []
-                for d in range(dim + 1):
-                    if nkeys:
-                        off = ps.get(PASS_OFFSETS, d)
-                        counts.append((off[1:] - off[:-1]).to(torch.int64))
-                    else:
-                        # nothing splits here, but every number shifts with the other ranks' products
-                        counts.append(torch.ones(mesh.nents(d), dtype=torch.int64, device=dev))
-                bases, nnext = self._global_bases(counts, trust)
-                for d in range(dim + 1):
-                    if nkeys:
-                        ps.set(PASS_GLOBAL_BASES, bases[d], d)
-                    else:
-                        dm.set_tag(d, "global", 1, bases[d])
+            # (a rank where nothing splits still renumbers: every number shifts with the others' products)
+            with _Section(dm, "global numbers"):
+                nnext = self._number_globally(ps, trust)
             if nkeys:
                 with _Section(dm, "finish(lib)"):
                     ps.finish()
@@ -376,58 +450,24 @@ class DistMesh:
         finally:
             ps.close()
 
-    def _global_bases(self, counts_per_dim, trust):
+    def _number_globally(self, ps, trust):
         """modify_globals (src/Omega_h_modify.cpp:406-444): exclusive scan, in global-number order, of
         how many new entities each old entity stands for -- all dimensions at once, on the key
         (dimension, old global number) flattened to one dense axis.
 
         Old numbers are dense, so a rank sees where its own stretch of the global order is
         interrupted: the entities it counts fall into runs of consecutive keys, inside a run the scan
-        is the local one, and only (first key, sum) of every run goes to the linear partition of
-        the key axis, which scans the runs of all ranks and answers with each run's base. The traffic
-        follows the partition boundary, not the mesh size. Entities counted by another rank get their
-        base from that rank."""
+        is the local one (library: oshb_pass_runs_begin), and only (first key, sum) of every run goes
+        to the linear partition of the key axis, which scans the runs of all ranks and answers with
+        each run's base. The traffic follows the partition boundary, not the mesh size. Entities
+        counted by another rank get their base from that rank."""
         P, dev, me = self.size, self.device, self.rank
-        dm, mesh = self.dm, self.mesh
-        dim = mesh.dim()
-        ns = [mesh.nents(d) for d in range(dim + 1)]
-        lo = [sum(ns[:d]) for d in range(dim + 2)]
-        koff = [sum(self.nglobal[:d]) for d in range(dim + 2)]
-        ntot, N = lo[-1], koff[-1]
+        dim = self.mesh.dim()
+        koff = [sum(self.nglobal[:d]) for d in range(5)]
+        N = koff[dim + 1]
         chunk = max((N + P - 1) // P, 1)
-        key = torch.empty(ntot, dtype=torch.int64, device=dev)
-        rk = torch.empty(ntot, dtype=torch.int32, device=dev)
-        dp = torch.empty(ntot, dtype=torch.int8, device=dev)
-        dm._pre()
-        for d in range(dim + 1):
-            dm.tag_into(d, "global", key[lo[d]:lo[d + 1]])
-            dm.tag_into(d, "own:rank", rk[lo[d]:lo[d + 1]])
-            dm.tag_into(d, "own:depth", dp[lo[d]:lo[d + 1]])
-        dm._post()
-        for d in range(1, dim + 1):
-            key[lo[d]:lo[d + 1]] += koff[d]
-        counts = torch.cat(counts_per_dim)
-        counted = rk == me
-        w = torch.where(counted, counts, 0)
-        incl = torch.cumsum(w, 0)
-        pre = incl - w
-        # new entity totals per dimension
-        edges = torch.tensor([x - 1 for x in lo[1:]], device=dev, dtype=torch.int64)
-        upto = incl[edges]
-        tot_d = upto - torch.cat([upto.new_zeros(1), upto[:-1]])
-        didx = torch.nonzero(counted).flatten()
-        dg = key[didx]
-        dpre = pre[didx]
-        nd = dg.numel()
-        if CHECK and nd > 1:
-            assert bool((dg[1:] > dg[:-1]).all().item()), "local order lost the global order"
-        start = torch.ones(nd, dtype=torch.bool, device=dev)
-        if nd > 1:
-            start[1:] = dg[1:] != dg[:-1] + 1
-        rfirst = torch.nonzero(start).flatten()
-        run_key = dg[rfirst]
-        run_pre = dpre[rfirst]
-        run_sum = torch.cat([run_pre[1:], incl[-1:]]) - run_pre
+        nruns, nwant, newc = ps.runs_begin(me, trust, koff)
+        run_key, run_sum = ps.runs_get(nruns)
         # runs -> linear partition of the key axis -> base of every run
         bounds = torch.searchsorted(run_key, torch.arange(P + 1, device=dev, dtype=torch.int64) * chunk)
         sc = (bounds[1:] - bounds[:-1]).tolist()
@@ -438,29 +478,34 @@ class DistMesh:
         rs_sorted = rs[order]
         cs = torch.cumsum(rs_sorted, 0)
         tot = cs[-1:] if cs.numel() else torch.zeros(1, dtype=torch.int64, device=dev)
-        gathered = torch.empty(P * (dim + 2), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, torch.cat([tot, tot_d]).contiguous(), group=self.group)
-        gathered = gathered.view(P, dim + 2)
-        below = int(gathered[:me, 0].sum().item())
-        nnext = [int(x) for x in gathered[:, 1:].sum(0).tolist()] + [0] * (3 - dim)
-        if CHECK:
-            assert int(gathered[:, 0].sum().item()) == sum(nnext)
+        mine = torch.cat([tot, torch.tensor(newc, dtype=torch.int64, device=dev)])
+        gathered = torch.empty(P * 5, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        gathered = gathered.view(P, 5)
+        sums = gathered.sum(0).tolist()
+        below = int(gathered[:me, 0].sum().item()) if me else 0
+        nnext = [int(x) for x in sums[1:]]
+        assert int(sums[0]) == sum(nnext), "an old entity was counted twice or by no rank"
         excl = torch.empty_like(rs)
         excl[order] = cs - rs_sorted + below
-        run_base = torch.empty(run_key.numel(), dtype=torch.int64, device=dev)
+        run_base = torch.empty(nruns, dtype=torch.int64, device=dev)
         dist.all_to_all_single(run_base, excl, sc, [c // 2 for c in rcounts], group=self.group)
-        rid = torch.cumsum(start.to(torch.int64), 0) - 1
-        bases = pre.clone()                      # uncounted, untrusted entities: any number will do
-        bases[didx] = run_base[rid] + (dpre - run_pre[rid])
+        ps.runs_set_bases(run_base, [sum(nnext[:d]) for d in range(4)])
         # entities another rank counts: everything this pass trusts, and one layer more -- the
         # representative (first triangle / tet) of a trusted key's cavity may lie in the shell
-        want = torch.nonzero((~counted) & (dp <= trust + 1)).flatten()
-        plan = self._fetch_plan(want, rk[want].to(torch.int64), key[want], didx, dg)
-        plan.pull(bases)
-        out = []
-        for d in range(dim + 1):
-            out.append(bases[lo[d]:lo[d + 1]] - sum(nnext[:d]))
-        return out, nnext
+        want_key, want_owner = ps.want_get(nwant)
+        order = torch.argsort(want_owner, stable=True)
+        counts = torch.bincount(want_owner[order].to(torch.int64), minlength=P).tolist()
+        asked, asked_counts = _alltoallv(want_key[order], counts, self.group)
+        answers = ps.runs_lookup(asked)
+        got = torch.empty(nwant, dtype=torch.int64, device=dev)
+        self.dm._post()
+        dist.all_to_all_single(got, answers, counts, asked_counts, group=self.group)
+        values = torch.empty_like(got)
+        values[order] = got
+        ps.want_set(values)
+        ps.runs_commit()
+        return nnext
 
 
 def distribute(base, halo, device, group=None):
