@@ -543,6 +543,7 @@ def main_b200_partitioned(args):
     lib = Lib(device=local_rank).init()
     if lib.is_emulation:
         raise SystemExit("bench.py refuses to run on the emulation build")
+    D.share_stream(lib, device)   # torch, NCCL and the library on one stream: no host syncs between them
     n = args.n
     shape = box_shape(world)
     base = build_box(float(shape[0]), float(shape[1]), float(shape[2]), shape[0] * n, shape[1] * n, shape[2] * n, lib=lib)
@@ -648,6 +649,20 @@ def main_b200_partitioned(args):
             "peak_device_bytes": lib.peak_bytes(),
         }
         print(json.dumps(line))
+    if D.TIMING is not None and rank == 0:
+        # the library's own kernels during one partitioned loop (CUDA events on its stream)
+        part = part0.clone()
+        lib.profile_begin(None)
+        loop(part)
+        agg = summarize_profile(lib.profile_end())
+        ksum = sum(v[1] for v in agg.values())
+        print("  library kernels in one partitioned loop: %.3f ms, %d launches" % (ksum, sum(v[0] for v in agg.values())),
+              file=sys.stderr)
+        for nm, (cnt, ms, b) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+            print("    %-34s n=%4d %8.3f ms" % (nm, cnt, ms), file=sys.stderr)
+        del part
+    elif D.TIMING is not None:
+        loop(part0.clone())
     if D.TIMING is not None:
         nloops = args.steps * (1 if args.no_e2e else 2) + max(args.warmup, 3) + (0 if args.no_e2e else 1)
         for r in range(world):

@@ -33,6 +33,10 @@ extern "C" {
 /* Library(argc, argv) device selection, src/Omega_h_library.cpp:152-167 */
 int oshb_init(int device);
 int oshb_sync(void);
+/* Run all further work on the caller's CUDA stream (a cudaStream_t; NULL = back to the library's
+ * own). A caller that interleaves its own kernels or collectives with library calls on device
+ * buffers then needs no host synchronisation in between: stream order does it. */
+int oshb_set_stream(void* cuda_stream);
 const char* oshb_last_error(void);
 /* 1 when built as the test-only host emulation (tests/emu); the product library returns 0 */
 int oshb_is_emulation(void);
@@ -192,7 +196,10 @@ enum {
 };
 int oshb_pass_create(oshb_mesh* m, const oshb_adapt_opts* opts, oshb_pass** out);
 int oshb_pass_destroy(oshb_pass* p);
-int oshb_pass_begin(oshb_pass* p, int keep_going, int* status); /* 0 no candidate, 1 none good, 2 work */
+/* keep_going 0: return at the first "nothing to do" like refine_by_size; 1: compute every array even
+ * then (a neighbouring rank may have work); 2: candidate marks only (then call again with 1).
+ * *status: 0 no candidate, 1 candidates but none good enough, 2 there is work */
+int oshb_pass_begin(oshb_pass* p, int keep_going, int* status);
 int oshb_pass_restate(oshb_pass* p, int* any_good);
 int oshb_pass_indset_round(oshb_pass* p, int* pending);
 int oshb_pass_select_keys(oshb_pass* p, int32_t* nkeys);

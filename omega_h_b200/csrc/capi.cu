@@ -67,6 +67,19 @@ int oshb_sync(void) {
   sync_stream();
   OSHB_CATCH
 }
+int oshb_set_stream(void* cuda_stream) {
+  OSHB_TRY
+#ifndef OSHB_EMU
+  Ctx& c = ctx();
+  if (!c.ready) init_ctx(-1);
+  // the caching allocator reuses freed blocks in stream order: drain the old stream first
+  sync_stream();
+  c.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c.own_stream;
+#else
+  (void)cuda_stream;
+#endif
+  OSHB_CATCH
+}
 const char* oshb_last_error(void) { return oshb::last_error_string().c_str(); }
 int oshb_is_emulation(void) {
 #ifdef OSHB_EMU
@@ -488,7 +501,7 @@ int oshb_pass_destroy(oshb_pass* p) {
 }
 int oshb_pass_begin(oshb_pass* p, int keep_going, int* status) {
   OSHB_TRY
-  *status = pass_begin(reinterpret_cast<Pass*>(p), keep_going != 0);
+  *status = pass_begin(reinterpret_cast<Pass*>(p), keep_going);
   OSHB_CATCH
 }
 int oshb_pass_restate(oshb_pass* p, int* any_good) {

@@ -186,7 +186,7 @@ void rebuild_discard(Rebuild* r);
 struct Pass;
 Pass* pass_create(Mesh* mesh, AdaptOpts const& opts);
 void pass_destroy(Pass* p);
-int pass_begin(Pass* p, bool keep_going);
+int pass_begin(Pass* p, int keep_going);
 int pass_restate(Pass* p);
 int pass_indset_round(Pass* p);
 void pass_select_keys(Pass* p);

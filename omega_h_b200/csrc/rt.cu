@@ -145,7 +145,8 @@ void init_ctx(int device) {
   }
   c.device = device;
   c.sms = prop.multiProcessorCount;
-  OSHB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  OSHB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+  c.stream = c.own_stream;
   // keep freed blocks in the pool: temporaries of one pass are reused by the next
   cudaMemPool_t pool;
   OSHB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));

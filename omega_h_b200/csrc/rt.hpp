@@ -63,7 +63,8 @@ struct Error : public std::runtime_error {
 
 struct Ctx {
 #ifndef OSHB_EMU
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // where everything is enqueued
+  cudaStream_t own_stream = nullptr;  // the library's stream (stream may be a caller's, oshb_set_stream)
 #endif
   int device = -1;
   int sms = 148;

@@ -238,7 +238,7 @@ struct Pass {
   ~Pass() {
     if (rb) rebuild_discard(rb);
   }
-  int begin(bool keep_going);
+  int begin(int keep_going);
   int restate();
   int indset_round();
   void select_keys();
@@ -248,8 +248,9 @@ struct Pass {
 
 // candidates + cavity qualities + initial set states. Returns 0: no candidate edge,
 // 1: candidates but none whose cavity is good enough, 2: there is work.
-// keep_going: compute every array even when this rank has nothing to do (its neighbours may).
-int Pass::begin(bool keep_going) {
+// keep_going 1: compute every array even when this rank has nothing to do (its neighbours may);
+// 2: stop after the candidate marks (a partitioned caller first asks all ranks whether any is left).
+int Pass::begin(int keep_going) {
   device_error_reset();
   g_stats = PassStats();
   dim = mesh->dim();
@@ -277,6 +278,7 @@ int Pass::begin(bool keep_going) {
   }
   bool const any_cand = read_scalar(flags3) != 0;
   if (!any_cand && !keep_going) return 0;
+  if (keep_going == 2) return any_cand ? 2 : 0;
   // ---- cavity qualities of the candidates (refine_qualities, :22)
   c2e = mesh->ask_down(dim, EDGE);
   cv2v = mesh->ask_verts_of(dim);
@@ -663,7 +665,7 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
   Pass p;
   p.mesh = mesh;
   p.opts = opts;
-  if (p.begin(false) != 2) return false;
+  if (p.begin(0) != 2) return false;
   while (p.indset_round()) {
   }
   p.select_keys();
@@ -680,7 +682,7 @@ Pass* pass_create(Mesh* mesh, AdaptOpts const& opts) {
   return p;
 }
 void pass_destroy(Pass* p) { delete p; }
-int pass_begin(Pass* p, bool keep_going) { return p->begin(keep_going); }
+int pass_begin(Pass* p, int keep_going) { return p->begin(keep_going); }
 int pass_restate(Pass* p) { return p->restate(); }
 int pass_indset_round(Pass* p) { return p->indset_round(); }
 void pass_select_keys(Pass* p) { p->select_keys(); }

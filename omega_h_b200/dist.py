@@ -72,6 +72,21 @@ class _Section:
             TIMING[self.name] = TIMING.get(self.name, 0.0) + (_time.perf_counter() - self.t0)
 
 
+_SHARED = {}
+
+
+def share_stream(lib, device):
+    """Put torch (and with it torch.distributed's collectives) and the library on ONE CUDA stream, so
+    buffers pass between them in stream order with no host synchronisation. Call once per process."""
+    device = torch.device(device)
+    if device.type != "cuda" or id(lib) in _SHARED:
+        return
+    stream = torch.cuda.Stream(device)
+    torch.cuda.set_stream(stream)
+    lib.check(lib.c.oshb_set_stream(C.c_void_p(stream.cuda_stream)))
+    _SHARED[id(lib)] = stream
+
+
 class DevMesh:
     """Tensor-level access to a library mesh: arrays go in and out by device pointer."""
 
@@ -79,12 +94,13 @@ class DevMesh:
         self.mesh, self.lib, self.device = mesh, mesh.lib, torch.device(device)
 
     def _pre(self):
-        # the library runs on its own stream: finish torch's work on the buffers first
-        if self.device.type == "cuda":
+        # the library on its own stream: finish torch's work on the buffers first
+        if self.device.type == "cuda" and id(self.lib) not in _SHARED:
             torch.cuda.current_stream(self.device).synchronize()
 
     def _post(self):
-        self.lib.sync()
+        if id(self.lib) not in _SHARED:
+            self.lib.sync()
 
     def empty(self, n, dtype):
         return torch.empty(int(n), dtype=dtype, device=self.device)
@@ -391,8 +407,8 @@ class DistMesh:
         trust = self.halo - self.passes - 1   # deepest layer whose entities see their whole star
         ps = _Pass(dm, opts)
         try:
-            with _Section(dm, "begin(lib)"):
-                ps.begin(True)
+            with _Section(dm, "candidates(lib)"):
+                ps.begin(2)
             with _Section(dm, "edge tags"):
                 edge_depth = dm.tag(EDGE, "own:depth")
                 mine = edge_depth == 0
@@ -403,6 +419,8 @@ class DistMesh:
             if trust < 0:
                 raise _lib.OshbError("halo of %d layers is used up after %d passes; re-ghosting is not implemented"
                                      % (self.halo, self.passes))
+            with _Section(dm, "begin(lib)"):
+                ps.begin(1)
             with _Section(dm, "shell plan"):
                 edge_rank = dm.tag(EDGE, "own:rank")
                 egid = dm.tag(EDGE, "global")

@@ -38,6 +38,8 @@ def main():
         device = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(device)
     lib = _lib.Lib(lib_path).init()
+    if os.environ.get("OSHB_SHARE_STREAM", "1") == "1":
+        D.share_stream(lib, device)
     base = M.build_box(1.0, 1.0, 1.0 if dim == 3 else 0.0, n, n, n if dim == 3 else 0, lib)
     add_metric(base, n, aniso)
     serial = base.copy()
