@@ -303,8 +303,9 @@ def _alltoallv(send, send_counts, group=None):
     return recv, rc_l
 
 
-def _any_rank(flag, device, group=None):
-    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+def _any_rank(flags, group=None):
+    """does any rank have a set entry in `flags` (a device tensor)? One collective, one read-back."""
+    t = flags.any().to(torch.int32).reshape(1)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return bool(t.item())
 
@@ -413,8 +414,8 @@ class DistMesh:
                 edge_depth = dm.tag(EDGE, "own:depth")
                 mine = edge_depth == 0
                 cand = ps.get(PASS_CANDIDATES)
-                any_cand = bool(((cand != 0) & mine).any().item())
-            if not _any_rank(any_cand, dev, self.group):
+                any_cand = _any_rank((cand != 0) & mine, self.group)
+            if not any_cand:
                 return False
             if trust < 0:
                 raise _lib.OshbError("halo of %d layers is used up after %d passes; re-ghosting is not implemented"
@@ -433,8 +434,8 @@ class DistMesh:
                 plan.pull_pass_array(ps, PASS_QUALITIES)
                 ps.restate()
                 state = ps.get(PASS_STATES)
-                any_good = bool(((state == UNKNOWN) & mine).any().item())
-            if not _any_rank(any_good, dev, self.group):
+                any_good = _any_rank((state == UNKNOWN) & mine, self.group)
+            if not any_good:
                 return False
             rounds = 0
             while True:
@@ -444,7 +445,7 @@ class DistMesh:
                     plan.pull_pass_array(ps, PASS_STATES)
                     state = ps.get(PASS_STATES)
                     rounds += 1
-                    more = _any_rank(bool(((state == UNKNOWN) & mine).any().item()), dev, self.group)
+                    more = _any_rank((state == UNKNOWN) & mine, self.group)
                 if not more:
                     break
             with _Section(dm, "select_keys(lib)"):
