@@ -451,6 +451,15 @@ def main_b200(args):
                 "launches": cnt, "avg_ms": (tms / cnt) if cnt else None,
                 "share_of_step": (tms / dev_ms) if dev_ms > 0 else None,
                 "algorithmic_bytes_per_launch": (tbytes / cnt) if cnt else None}
+    # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture of this
+    # same loop (profiles/ncu_r1b_gather.json); only valid for the configuration it was taken on
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_r1b_gather.json")))
+        if cap["kernel"] == top and args.n == 64 and args.workload == "iso":
+            roofline["traffic"] = cap["dram_bytes_per_launch"]
+            roofline["traffic_source"] = "profiles/ncu_r1b_gather.json (dram__bytes_read.sum + dram__bytes_write.sum, avg of the loop's 16 launches)"
+    except Exception:
+        pass
 
     # ---- end to end: host buffers in, host buffers out ---------------------------------------
     e2e = None
