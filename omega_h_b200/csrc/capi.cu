@@ -45,6 +45,15 @@ static void export_array(DArr<T> const& a, T* out, int host) {
     d2d(out, a.data(), size_t(a.size()) * sizeof(T));
 }
 
+// device-pointer outputs: a caller on another stream must see them finished; a caller sharing the
+// library's stream (oshb_set_stream) is ordered by the stream itself
+static void sync_unless_shared() {
+#ifndef OSHB_EMU
+  if (ctx().stream != ctx().own_stream) return;
+#endif
+  sync_stream();
+}
+
 template <class T>
 static void gather_scatter(T* arr, LO const* idx, int64_t n, T* buf, bool scatter) {
   if (scatter) {
@@ -633,7 +642,7 @@ int oshb_pass_runs_get(oshb_pass* p, int64_t* run_key, int64_t* run_sum, int hos
   pass_runs_get(reinterpret_cast<Pass*>(p), &k, &s);
   export_array(k, reinterpret_cast<GO*>(run_key), host);
   export_array(s, reinterpret_cast<GO*>(run_sum), host);
-  if (!host) sync_stream();
+  if (!host) sync_unless_shared();
   OSHB_CATCH
 }
 int oshb_pass_runs_set_bases(oshb_pass* p, const int64_t* run_base, const int64_t* new_offset, int host) {
@@ -651,14 +660,14 @@ int oshb_pass_want_get(oshb_pass* p, int64_t* want_key, int32_t* want_owner, int
   pass_want_get(reinterpret_cast<Pass*>(p), &k, &o);
   export_array(k, reinterpret_cast<GO*>(want_key), host);
   export_array(o, want_owner, host);
-  if (!host) sync_stream();
+  if (!host) sync_unless_shared();
   OSHB_CATCH
 }
 int oshb_pass_runs_lookup(oshb_pass* p, const int64_t* keys, int64_t n, int64_t* bases_out, int host) {
   OSHB_TRY
   GOs out = pass_runs_lookup(reinterpret_cast<Pass*>(p), import_array<GO>(reinterpret_cast<GO const*>(keys), n, host));
   export_array(out, reinterpret_cast<GO*>(bases_out), host);
-  if (!host) sync_stream();
+  if (!host) sync_unless_shared();
   OSHB_CATCH
 }
 int oshb_pass_want_set(oshb_pass* p, const int64_t* bases, int host) {

@@ -487,41 +487,49 @@ class DistMesh:
         chunk = max((N + P - 1) // P, 1)
         nruns, nwant, newc = ps.runs_begin(me, trust, koff)
         run_key, run_sum = ps.runs_get(nruns)
-        # runs -> linear partition of the key axis -> base of every run
+        want_key, want_owner = ps.want_get(nwant)
+        # ONE all_gather tells every rank all the sizes and totals of this stage: per destination of
+        # the linear partition the number of runs and their sum, per owner the number of wanted
+        # entities, and the new totals per dimension -> no further size exchange, one read-back
         bounds = torch.searchsorted(run_key, torch.arange(P + 1, device=dev, dtype=torch.int64) * chunk)
-        sc = (bounds[1:] - bounds[:-1]).tolist()
-        both, rcounts = _alltoallv(torch.stack([run_key, run_sum], 1).flatten(), [2 * c for c in sc], self.group)
+        inc = torch.cat([run_sum.new_zeros(1), torch.cumsum(run_sum, 0)])
+        worder = torch.argsort(want_owner, stable=True)
+        mine = torch.cat([bounds[1:] - bounds[:-1], inc[bounds[1:]] - inc[bounds[:-1]],
+                          torch.bincount(want_owner.to(torch.int64), minlength=P),
+                          torch.tensor(newc, dtype=torch.int64, device=dev)])
+        table = torch.empty(P * mine.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(table, mine, group=self.group)
+        table = table.view(P, 3 * P + 4).tolist()
+        run_send = table[me][0:P]                           # runs I send to each partition rank
+        run_recv = [table[r][me] for r in range(P)]         # runs I receive as partition rank
+        sums_to = [sum(table[r][P + q] for r in range(P)) for q in range(P)]   # total landing on q
+        want_send = table[me][2 * P:3 * P]
+        want_recv = [table[r][2 * P + me] for r in range(P)]
+        nnext = [sum(table[r][3 * P + d] for r in range(P)) for d in range(4)]
+        below = sum(sums_to[:me])
+        assert sum(sums_to) == sum(nnext), "an old entity was counted twice or by no rank"
+        # runs -> linear partition of the key axis -> base of every run
+        both = torch.empty(2 * sum(run_recv), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(both, torch.stack([run_key, run_sum], 1).flatten(), [2 * c for c in run_recv],
+                               [2 * c for c in run_send], group=self.group)
         both = both.view(-1, 2)
         rg, rs = both[:, 0], both[:, 1]
         order = torch.argsort(rg)
         rs_sorted = rs[order]
-        cs = torch.cumsum(rs_sorted, 0)
-        tot = cs[-1:] if cs.numel() else torch.zeros(1, dtype=torch.int64, device=dev)
-        mine = torch.cat([tot, torch.tensor(newc, dtype=torch.int64, device=dev)])
-        gathered = torch.empty(P * 5, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, mine, group=self.group)
-        gathered = gathered.view(P, 5)
-        sums = gathered.sum(0).tolist()
-        below = int(gathered[:me, 0].sum().item()) if me else 0
-        nnext = [int(x) for x in sums[1:]]
-        assert int(sums[0]) == sum(nnext), "an old entity was counted twice or by no rank"
         excl = torch.empty_like(rs)
-        excl[order] = cs - rs_sorted + below
+        excl[order] = torch.cumsum(rs_sorted, 0) - rs_sorted + below
         run_base = torch.empty(nruns, dtype=torch.int64, device=dev)
-        dist.all_to_all_single(run_base, excl, sc, [c // 2 for c in rcounts], group=self.group)
+        dist.all_to_all_single(run_base, excl, run_send, run_recv, group=self.group)
         ps.runs_set_bases(run_base, [sum(nnext[:d]) for d in range(4)])
         # entities another rank counts: everything this pass trusts, and one layer more -- the
         # representative (first triangle / tet) of a trusted key's cavity may lie in the shell
-        want_key, want_owner = ps.want_get(nwant)
-        order = torch.argsort(want_owner, stable=True)
-        counts = torch.bincount(want_owner[order].to(torch.int64), minlength=P).tolist()
-        asked, asked_counts = _alltoallv(want_key[order], counts, self.group)
+        asked = torch.empty(sum(want_recv), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(asked, want_key[worder], want_recv, want_send, group=self.group)
         answers = ps.runs_lookup(asked)
         got = torch.empty(nwant, dtype=torch.int64, device=dev)
-        self.dm._post()
-        dist.all_to_all_single(got, answers, counts, asked_counts, group=self.group)
+        dist.all_to_all_single(got, answers, want_send, want_recv, group=self.group)
         values = torch.empty_like(got)
-        values[order] = got
+        values[worder] = got
         ps.want_set(values)
         ps.runs_commit()
         return nnext
