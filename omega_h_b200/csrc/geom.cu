@@ -12,10 +12,13 @@ namespace oshb {
 // Algorithmic bytes per edge: 8 (ev2v) + 2*dim*8 (coords) + 2*ncomps*8 (metrics) + 8 out.
 // ---------------------------------------------------------------------------------------
 template <int dim, int mdim>
-static Reals measure_edges_tmpl(LO const* ev2v, Real const* coords, Real const* metrics, LO const* a2e, LO n) {
-  Reals out(n);
+static Reals measure_edges_tmpl(LO const* ev2v, Real const* coords, Real const* metrics, LO const* a2e, LO n,
+    I8 const* marks = nullptr, Reals into = Reals()) {
+  // marks: measure only the marked edges, in place into `into` (dense product sets: no list)
+  Reals out = marks ? into : Reals(n);
   Real* o = out.data();
   parallel_for(n, OSHB_LAMBDA(LO a) {
+    if (marks && !marks[a]) return;
     LO e = a2e ? a2e[a] : a;
     LO v0 = ev2v[int64_t(e) * 2 + 0];
     LO v1 = ev2v[int64_t(e) * 2 + 1];
@@ -41,6 +44,20 @@ Reals measure_edges_metric_raw(int dim, LOs ev2v, Reals coords, Reals metrics, i
   fail(__FILE__, __LINE__, "measure_edges_metric: unsupported (dim, metric ncomps)");
 }
 
+void measure_edges_metric_marked(Mesh* mesh, Bytes marks, Reals metrics, Reals into) {
+  LO n = mesh->nedges();
+  if (n == 0) return;
+  int ncomps = int(metrics.size() / mesh->nverts());
+  int dim = mesh->dim();
+  LO const* ev2v = mesh->ask_verts_of(EDGE).data();
+  Real const* c = mesh->coords().data();
+  if (dim == 3 && ncomps == 6) measure_edges_tmpl<3, 3>(ev2v, c, metrics.data(), nullptr, n, marks.data(), into);
+  else if (dim == 2 && ncomps == 3) measure_edges_tmpl<2, 2>(ev2v, c, metrics.data(), nullptr, n, marks.data(), into);
+  else if (dim == 3 && ncomps == 1) measure_edges_tmpl<3, 1>(ev2v, c, metrics.data(), nullptr, n, marks.data(), into);
+  else if (dim == 2 && ncomps == 1) measure_edges_tmpl<2, 1>(ev2v, c, metrics.data(), nullptr, n, marks.data(), into);
+  else fail(__FILE__, __LINE__, "measure_edges_metric: unsupported (dim, metric ncomps)");
+}
+
 Reals measure_edges_metric(Mesh* mesh, LOs a2e, Reals metrics) {
   LO n = a2e.exists() ? LO(a2e.size()) : mesh->nedges();
   int ncomps = int(metrics.size() / mesh->nverts());
@@ -52,10 +69,12 @@ Reals measure_edges_metric(Mesh* mesh, LOs a2e, Reals metrics) {
 // mean-ratio quality in that metric.
 // ---------------------------------------------------------------------------------------
 template <int dim, int mdim>
-static Reals measure_qualities_tmpl(LO const* cv2v, Real const* coords, Real const* metrics, LO const* a2e, LO n) {
-  Reals out(n);
+static Reals measure_qualities_tmpl(LO const* cv2v, Real const* coords, Real const* metrics, LO const* a2e, LO n,
+    I8 const* marks = nullptr, Reals into = Reals()) {
+  Reals out = marks ? into : Reals(n);
   Real* o = out.data();
   parallel_for(n, OSHB_LAMBDA(LO a) {
+    if (marks && !marks[a]) return;
     LO e = a2e ? a2e[a] : a;
     Vec<dim> p[dim + 1];
     Mat<mdim> ms[dim + 1];
@@ -78,6 +97,20 @@ Reals measure_qualities_raw(int dim, LOs cv2v, Reals coords, Reals metrics, int 
   if (dim == 3 && metric_ncomps == 1) return measure_qualities_tmpl<3, 1>(cv2v.data(), coords.data(), metrics.data(), a, n);
   if (dim == 2 && metric_ncomps == 1) return measure_qualities_tmpl<2, 1>(cv2v.data(), coords.data(), metrics.data(), a, n);
   fail(__FILE__, __LINE__, "measure_qualities: unsupported (dim, metric ncomps)");
+}
+
+void measure_qualities_marked(Mesh* mesh, Bytes marks, Reals metrics, Reals into) {
+  LO n = mesh->nelems();
+  if (n == 0) return;
+  int ncomps = int(metrics.size() / mesh->nverts());
+  int dim = mesh->dim();
+  LO const* cv2v = mesh->ask_verts_of(dim).data();
+  Real const* c = mesh->coords().data();
+  if (dim == 3 && ncomps == 6) measure_qualities_tmpl<3, 3>(cv2v, c, metrics.data(), nullptr, n, marks.data(), into);
+  else if (dim == 2 && ncomps == 3) measure_qualities_tmpl<2, 2>(cv2v, c, metrics.data(), nullptr, n, marks.data(), into);
+  else if (dim == 3 && ncomps == 1) measure_qualities_tmpl<3, 1>(cv2v, c, metrics.data(), nullptr, n, marks.data(), into);
+  else if (dim == 2 && ncomps == 1) measure_qualities_tmpl<2, 1>(cv2v, c, metrics.data(), nullptr, n, marks.data(), into);
+  else fail(__FILE__, __LINE__, "measure_qualities: unsupported (dim, metric ncomps)");
 }
 
 Reals measure_qualities(Mesh* mesh, LOs a2e, Reals metrics) {

@@ -436,7 +436,7 @@ struct Rebuild {
   LOs ev2v_old, fv2v, rv2v;
   Adj e2f, e2r, f2e, r2f, r2e;
   Topo tp;
-  LOs old2new[4], pbase[4], offsets[4], status[4];
+  LOs old2new[4], pbase[4], offsets[4], status[4], coarse[4];
   bool identity[4];
   GOs gbase[4], new_globals[4], lin_globals[4], ext_bases[4];
   LO nnew[4];
@@ -543,15 +543,36 @@ void Rebuild::number() {
     identity[ent_dim] = ident;
     GOs old_globals = mesh->globals(ent_dim);
     GO const* og = old_globals.data();
+    // coarse[i] = old entity representing new slot 256*i (the gather's per-thread search then only
+    // bisects the cache-resident stretch of offsets between two samples); every old entity files
+    // itself under the samples that fall into its stretch of new slots
+    LO const nnew_d = nnew[ent_dim];
+    LO const ncoarse = nnew_d / 256 + 2;
+    coarse[ent_dim] = LOs(ncoarse);
+    LO* cs = coarse[ent_dim].data();
     if (ident || ext_g) {
-      parallel_for(nold, OSHB_LAMBDA(LO e) { o2n[e] = (st && st[e] != -1) ? -1 : off[e]; }, "old2new");
+      parallel_for(nold, OSHB_LAMBDA(LO e) {
+        LO a0 = off[e], a1 = off[e + 1];
+        o2n[e] = (st && st[e] != -1) ? -1 : a0;
+        if (a1 > a0) {
+          for (LO i = (a0 + 255) >> 8; (int64_t(i) << 8) < a1; ++i) cs[i] = e;
+          if (a1 == nnew_d)
+            for (LO i = ((a1 - 1) >> 8) + 1; i < ncoarse; ++i) cs[i] = e;
+        }
+      }, "old2new");
     } else {
       lin_globals[ent_dim] = GOs(int64_t(nold) + 1);
       LOs lin_counts(nold);
       LO* lc = lin_counts.data();
       parallel_for(nold, OSHB_LAMBDA(LO e) {
-        o2n[e] = (st && st[e] != -1) ? -1 : off[e];
-        lc[og[e]] = off[e + 1] - off[e];
+        LO a0 = off[e], a1 = off[e + 1];
+        o2n[e] = (st && st[e] != -1) ? -1 : a0;
+        lc[og[e]] = a1 - a0;
+        if (a1 > a0) {
+          for (LO i = (a0 + 255) >> 8; (int64_t(i) << 8) < a1; ++i) cs[i] = e;
+          if (a1 == nnew_d)
+            for (LO i = ((a1 - 1) >> 8) + 1; i < ncoarse; ++i) cs[i] = e;
+        }
       }, "old2new+to_lin");
       scan_offsets(lin_counts.data(), nold, lin_globals[ent_dim].data());
     }
@@ -699,19 +720,7 @@ void Rebuild::finish() {
     ga.vkeys = vkeys;
     ga.stab = same_tab[d];
     ga.itab = inh_tab[d];
-    // coarse[i] = old entity representing new slot 256*i: the per-thread search then only
-    // bisects the (cache-resident) stretch of offsets between two coarse samples
-    LO const ncoarse = nnew[d] / 256 + 2;
-    LOs coarse(ncoarse);
-    LO* cs = coarse.data();
-    LO const nnew_d = nnew[d];
-    LO const nold_d = ga.nold;
-    LO const* off = ga.off;
-    parallel_for(ncoarse, OSHB_LAMBDA(LO i) {
-      int64_t slot = int64_t(i) * 256;
-      if (slot > nnew_d - 1) slot = nnew_d - 1;
-      cs[i] = upper_bound(off, nold_d + 1, LO(slot)) - 1;
-    }, "rebuild(coarse)");
+    LO const* cs = coarse[d].data();
     ga.cs = cs;
     int const deg = (d >= 1) ? simplex_degree(d, d - 1) : 0;
     int const nv = d + 1;
@@ -795,9 +804,17 @@ void Rebuild::finish() {
       }
     }
   }
+  // product sets are dense in a refining sweep (most entities of a split region are products):
+  // measure them in place by mark; sparse sets go through a compacted list
+  bool const dense = int64_t(nkeys) * 16 > int64_t(nnew[dim]);
   for (auto const& s : specials[EDGE]) {
     if (s.kind != 3) continue;
     // transfer_length (src/Omega_h_transfer.cpp:337-348): re-measure the product edges
+    if (dense) {
+      measure_edges_metric_marked(&new_mesh, prod_marks[EDGE], new_mesh.get_reals(VERT, "metric"),
+          new_tags[EDGE][s.new_index].f64);
+      continue;
+    }
     LOs list = collect_marked(prod_marks[EDGE]);
     Reals prod = measure_edges_metric(&new_mesh, list, new_mesh.get_reals(VERT, "metric"));
     scatter_by<Real>(prod.data(), new_tags[EDGE][s.new_index].f64.data(), list.data(), LO(list.size()), 1);
@@ -805,6 +822,11 @@ void Rebuild::finish() {
   for (auto const& s : specials[dim]) {
     if (s.kind != 4) continue;
     // transfer_quality (src/Omega_h_transfer.cpp:350-362)
+    if (dense) {
+      measure_qualities_marked(&new_mesh, prod_marks[dim], new_mesh.get_reals(VERT, "metric"),
+          new_tags[dim][s.new_index].f64);
+      continue;
+    }
     LOs list = collect_marked(prod_marks[dim]);
     Reals prod = measure_qualities(&new_mesh, list, new_mesh.get_reals(VERT, "metric"));
     scatter_by<Real>(prod.data(), new_tags[dim][s.new_index].f64.data(), list.data(), LO(list.size()), 1);
