@@ -53,17 +53,59 @@ __device__ __forceinline__ void atomic_min_u64(unsigned long long* p, unsigned l
 // src/Omega_h_refine_qualities.cpp:18-20 suggests
 // ---------------------------------------------------------------------------------------
 template <int mdim>
-static Reals edge_midpoint_metrics(LO const* ev2v, Real const* v2m, I8 const* cand, LO nedges) {
+static Reals edge_midpoint_metrics(LO const* ev2v, Real const* v2m, I8 const* cand, LO nedges, LO nverts) {
   Reals out(int64_t(nedges) * Symm<mdim>::ncomps);
   Real* o = out.data();
   int* err = device_error_cell();
+  if (mdim == 1) {
+    parallel_for(nedges, OSHB_LAMBDA(LO e) {
+      if (!cand[e]) return;
+      Mat<mdim> ms[2];
+      ms[0] = Symm<mdim>::get(v2m, ev2v[int64_t(e) * 2 + 0]);
+      ms[1] = Symm<mdim>::get(v2m, ev2v[int64_t(e) * 2 + 1]);
+      bool ok = true;
+      Mat<mdim> m = average_metric<mdim, 2>(ms, &ok);
+      if (!ok) atomic_or_i32(err, 2);
+      Symm<mdim>::set(o, e, m);
+    }, "edge_midpoint_metrics");
+    return out;
+  }
+  // tensors: average_metric = exp((log M0 + log M1) / 2) is three symmetric eigen-decompositions
+  // per edge, two of them repeated for every edge of a vertex (~14 edges). Take the logarithm once
+  // per vertex that a candidate edge touches (all mdim*mdim entries: q diag(l) q^T is not bitwise
+  // symmetric, and the sum feeds the third decomposition), then one decomposition per edge.
+  // Same operations on the same operands as average_metric => identical bits.
+  constexpr int nn = mdim * mdim;
+  Bytes vmark = filled<I8>(nverts, 0);
+  I8* vm = vmark.data();
   parallel_for(nedges, OSHB_LAMBDA(LO e) {
     if (!cand[e]) return;
-    Mat<mdim> ms[2];
-    ms[0] = Symm<mdim>::get(v2m, ev2v[int64_t(e) * 2 + 0]);
-    ms[1] = Symm<mdim>::get(v2m, ev2v[int64_t(e) * 2 + 1]);
+    vm[ev2v[int64_t(e) * 2 + 0]] = 1;
+    vm[ev2v[int64_t(e) * 2 + 1]] = 1;
+  }, "midpoint_metrics(mark verts)");
+  Reals logs(int64_t(nverts) * nn);
+  Real* lg = logs.data();
+  parallel_for(nverts, OSHB_LAMBDA(LO v) {
+    if (!vm[v]) return;
     bool ok = true;
-    Mat<mdim> m = average_metric<mdim, 2>(ms, &ok);
+    Mat<mdim> l = log_spd(Symm<mdim>::get(v2m, v), &ok);
+    if (!ok) atomic_or_i32(err, 2);
+    for (int i = 0; i < mdim; ++i)
+      for (int j = 0; j < mdim; ++j) lg[int64_t(v) * nn + i * mdim + j] = l[i][j];
+  }, "midpoint_metrics(vertex logs)");
+  parallel_for(nedges, OSHB_LAMBDA(LO e) {
+    if (!cand[e]) return;
+    Mat<mdim> am = zero_matrix<mdim>();
+    for (int k = 0; k < 2; ++k) {
+      LO v = ev2v[int64_t(e) * 2 + k];
+      Mat<mdim> l;
+      for (int i = 0; i < mdim; ++i)
+        for (int j = 0; j < mdim; ++j) l[i][j] = lg[int64_t(v) * nn + i * mdim + j];
+      am = am + l;
+    }
+    am = am / Real(2);
+    bool ok = true;
+    Mat<mdim> m = exp_spd(am, &ok);
     if (!ok) atomic_or_i32(err, 2);
     Symm<mdim>::set(o, e, m);
   }, "edge_midpoint_metrics");
@@ -294,7 +336,7 @@ int Pass::begin(int keep_going) {
   }
 #define OSHB_CQ(D, M)                                                                                       \
   {                                                                                                         \
-    sel.edge_mid_metrics = edge_midpoint_metrics<M>(ev2v.data(), vert_metrics.data(), cand, nedges);        \
+    sel.edge_mid_metrics = edge_midpoint_metrics<M>(ev2v.data(), vert_metrics.data(), cand, nedges, mesh->nverts()); \
     cavity_qualities_tmpl<D, M>(nelems, c2e.ab2b.data(), c2e.codes.data(), cv2v.data(), ev2v.data(), cand,  \
         coords.data(), vert_metrics.data(), sel.edge_mid_metrics.data(), qord);                             \
   }
