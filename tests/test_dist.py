@@ -23,6 +23,7 @@ def run_worker(nranks, lib_path, device, n, halo, aniso, dim, port, timeout=900)
 
 
 @pytest.mark.parametrize("nranks,n,halo,aniso,dim", [
+    (1, 4, 4, 0, 3),    # one rank: the staged pass + external numbering alone
     (2, 8, 4, 0, 3),    # 4 doubling passes, the halo exactly used up
     (3, 6, 5, 0, 3),    # uneven parts, 5 passes
     (2, 5, 8, 1, 3),    # anisotropic metric (ncomps 6), metric transfer

@@ -92,3 +92,45 @@ def test_permuted_globals_against_oracle(emu_lib, fixture, seed):
     fx = parity.load(os.path.join(parity.HERE, "golden", fixture + ".oshd.gz"))
     rep = parity.check_against_oracle(parity.jittered_input(fx, seed, False, permute_globals=True), emu_lib)
     rep.assert_ok()
+
+
+def test_staged_pass_equals_refine_by_size(emu_lib):
+    """oshb_pass_* run back to back (the cut points a partitioned caller synchronises at) must give
+    exactly what the one-call refine_by_size gives."""
+    import ctypes as C
+    from omega_h_b200 import mesh as M
+    import numpy as np
+    path = [p for p in golden_files() if "d3n3m0_pass1" in p][0]
+    fx = parity.load(path)
+    a = parity.mesh_from_fixture(fx, emu_lib)
+    b = a.copy()
+    opts = M.AdaptOpts(a, emu_lib)
+    opts.max_length_desired = float(fx["opts:max_length_desired"][0])
+    opts.min_quality_allowed = float(fx["opts:min_quality_allowed"][0])
+    assert M.refine_by_size(a, opts)
+    c = emu_lib.c
+    ps = C.c_void_p()
+    o = opts._c()
+    emu_lib.check(c.oshb_pass_create(b.h, C.byref(o), C.byref(ps)))
+    st = C.c_int()
+    emu_lib.check(c.oshb_pass_begin(ps, C.c_int(0), C.byref(st)))
+    assert st.value == 2
+    pending = C.c_int(1)
+    while pending.value:
+        emu_lib.check(c.oshb_pass_indset_round(ps, C.byref(pending)))
+    nkeys = C.c_int32()
+    emu_lib.check(c.oshb_pass_select_keys(ps, C.byref(nkeys)))
+    assert nkeys.value > 0
+    emu_lib.check(c.oshb_pass_number(ps, C.c_int(0)))
+    emu_lib.check(c.oshb_pass_finish(ps))
+    emu_lib.check(c.oshb_pass_destroy(ps))
+    for d in range(4):
+        assert a.nents(d) == b.nents(d)
+        for name, _, _ in a.tags(d):
+            assert np.array_equal(a.get_array(d, name), b.get_array(d, name)), (d, name)
+        if d >= 1:
+            x, xc = a.ask_down(d, d - 1)
+            y, yc = b.ask_down(d, d - 1)
+            assert np.array_equal(x, y)
+            if d >= 2:
+                assert np.array_equal(xc, yc)
