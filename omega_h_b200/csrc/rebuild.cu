@@ -43,6 +43,11 @@ struct TagTable {
   TagCopy t[8];
 };
 
+// one search sample every 2^CS_SHIFT new slots: 0.5 B per new entity buys a 3-step bisect
+// (the ncu source page put 15 % of the gather's stall samples on a 7-step one)
+constexpr int CS_SHIFT = 3;
+constexpr int CS_MASK = (1 << CS_SHIFT) - 1;
+
 OSHB_HD void copy_ent(void* dst, int64_t di, void const* src, int64_t si, int bytes) {
   if (bytes == 1) {
     static_cast<I8*>(dst)[di] = static_cast<I8 const*>(src)[si];
@@ -324,8 +329,8 @@ static void run_gather(GatherArgs const& ga, Topo const& t2) {
   LO const* ov2nv = t2.o2n[0];
   parallel_for(a.nnew, OSHB_LAMBDA(LO ne) {
     // the old entity that represents this slot: last e with off[e] <= ne
-    LO lo = a.cs[ne >> 8];
-    LO hi = a.cs[(ne >> 8) + 1];
+    LO lo = a.cs[ne >> CS_SHIFT];
+    LO hi = a.cs[(ne >> CS_SHIFT) + 1];
     LO e = lo + upper_bound(a.off + lo + 1, hi - lo, ne);
     LO local = ne - a.off[e];
     LO s = (D >= 1) ? a.st[e] : -1;
@@ -543,11 +548,11 @@ void Rebuild::number() {
     identity[ent_dim] = ident;
     GOs old_globals = mesh->globals(ent_dim);
     GO const* og = old_globals.data();
-    // coarse[i] = old entity representing new slot 256*i (the gather's per-thread search then only
+    // coarse[i] = old entity representing new slot (i << CS_SHIFT) (the gather's per-thread search then only
     // bisects the cache-resident stretch of offsets between two samples); every old entity files
     // itself under the samples that fall into its stretch of new slots
     LO const nnew_d = nnew[ent_dim];
-    LO const ncoarse = nnew_d / 256 + 2;
+    LO const ncoarse = (nnew_d >> CS_SHIFT) + 2;
     coarse[ent_dim] = LOs(ncoarse);
     LO* cs = coarse[ent_dim].data();
     if (ident || ext_g) {
@@ -555,9 +560,9 @@ void Rebuild::number() {
         LO a0 = off[e], a1 = off[e + 1];
         o2n[e] = (st && st[e] != -1) ? -1 : a0;
         if (a1 > a0) {
-          for (LO i = (a0 + 255) >> 8; (int64_t(i) << 8) < a1; ++i) cs[i] = e;
+          for (LO i = (a0 + CS_MASK) >> CS_SHIFT; (int64_t(i) << CS_SHIFT) < a1; ++i) cs[i] = e;
           if (a1 == nnew_d)
-            for (LO i = ((a1 - 1) >> 8) + 1; i < ncoarse; ++i) cs[i] = e;
+            for (LO i = ((a1 - 1) >> CS_SHIFT) + 1; i < ncoarse; ++i) cs[i] = e;
         }
       }, "old2new");
     } else {
@@ -569,9 +574,9 @@ void Rebuild::number() {
         o2n[e] = (st && st[e] != -1) ? -1 : a0;
         lc[og[e]] = a1 - a0;
         if (a1 > a0) {
-          for (LO i = (a0 + 255) >> 8; (int64_t(i) << 8) < a1; ++i) cs[i] = e;
+          for (LO i = (a0 + CS_MASK) >> CS_SHIFT; (int64_t(i) << CS_SHIFT) < a1; ++i) cs[i] = e;
           if (a1 == nnew_d)
-            for (LO i = ((a1 - 1) >> 8) + 1; i < ncoarse; ++i) cs[i] = e;
+            for (LO i = ((a1 - 1) >> CS_SHIFT) + 1; i < ncoarse; ++i) cs[i] = e;
         }
       }, "old2new+to_lin");
       scan_offsets(lin_counts.data(), nold, lin_globals[ent_dim].data());
