@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=64, help="box cells per axis (config[1] = 64)")
+    ap.add_argument("--n", "--box-n", dest="n", type=int, default=64,
+                    help="box cells per axis and GPU (config[1] = 64); under torchrun spell it --box-n")
     ap.add_argument("--workload", default="iso", choices=["iso", "aniso"],
                     help="iso = BASELINE config[1] (the metric's configuration); aniso = config[2] tanh shock layer")
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table to stderr and exit")
@@ -564,6 +565,7 @@ def main_b200_partitioned(args):
     part0 = D.distribute(base, halo, device)
     nglobal0 = base.nelems()
     del base
+    torch.cuda.empty_cache()   # the cut's temporaries: give them back before the library's pool grows
     opts = AdaptOpts(part0.mesh)
 
     def barrier():

@@ -118,6 +118,10 @@ int oshb_mesh_ntags(const oshb_mesh* m, int ent_dim, int* ntags);
 int oshb_mesh_tag_info(const oshb_mesh* m, int ent_dim, int i, char* name_out, int name_cap, int* type, int* ncomps);
 /* Mesh::get_array: copies the tag to h_out/d_out (nents*ncomps values) */
 int oshb_mesh_get_tag(const oshb_mesh* m, int ent_dim, const char* name, void* out, int host);
+/* values of a one-component tag at n listed entities (out has the tag's type): what a rank reads
+ * to talk about a few entities of a large part (read_subset / unmap, src/Omega_h_map.cpp:92-118) */
+int oshb_mesh_gather_tag(const oshb_mesh* m, int ent_dim, const char* name, const int32_t* ents, int64_t n, void* out,
+    int host);
 /* Mesh::ask_down / ask_verts_of (derives + caches): entries nents(from)*degree; codes may be
  * NULL; codes are absent when to==0 */
 int oshb_mesh_ask_down(oshb_mesh* m, int from, int to, int32_t* ab2b_out, int8_t* codes_out, int host);

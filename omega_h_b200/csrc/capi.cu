@@ -381,6 +381,44 @@ int oshb_mesh_get_tag(const oshb_mesh* m, int ent_dim, const char* name, void* o
   }
   OSHB_CATCH
 }
+int oshb_mesh_gather_tag(const oshb_mesh* m, int ent_dim, const char* name, const int32_t* ents, int64_t n, void* out,
+    int host) {
+  OSHB_TRY
+  Tag const* t = m->m.find_tag(ent_dim, name);
+  if (!t) fail(__FILE__, __LINE__, std::string("no tag ") + name);
+  OSHB_CHECK(t->ncomps == 1);
+  if (n) {
+    LOs idx = import_array<LO>(ents, n, host);
+    switch (t->type) {
+      case TAG_I8: {
+        Bytes b(n);
+        gather_scatter<I8>(t->i8.data(), idx.data(), n, b.data(), false);
+        export_array(b, static_cast<I8*>(out), host);
+        break;
+      }
+      case TAG_I32: {
+        LOs b(n);
+        gather_scatter<LO>(t->i32.data(), idx.data(), n, b.data(), false);
+        export_array(b, static_cast<LO*>(out), host);
+        break;
+      }
+      case TAG_I64: {
+        GOs b(n);
+        gather_scatter<GO>(t->i64.data(), idx.data(), n, b.data(), false);
+        export_array(b, static_cast<GO*>(out), host);
+        break;
+      }
+      default: {
+        Reals b(n);
+        gather_scatter<Real>(t->f64.data(), idx.data(), n, b.data(), false);
+        export_array(b, static_cast<Real*>(out), host);
+        break;
+      }
+    }
+  }
+  if (!host) sync_unless_shared();
+  OSHB_CATCH
+}
 int oshb_mesh_ask_down(oshb_mesh* m, int from, int to, int32_t* ab2b_out, int8_t* codes_out, int host) {
   OSHB_TRY
   OSHB_CHECK(from > to);

@@ -547,8 +547,17 @@ void Pass::runs_begin(int me, int trust, GO const* koff, int64_t* nruns, int64_t
   n.pre = GOs(int64_t(ntot) + 1);
   scan_offsets(w.data(), ntot, n.pre.data());
   n.rid = offset_scan(n.start);
-  LO nr = 0, nw = 0;
-  n.run_pos = collect_marked(n.start, &nr);
+  LO nr = last_of(n.rid), nw = 0;
+  n.run_pos = LOs(nr);
+  {
+    // the run list from the scan already taken (collect_marked would scan the marks again)
+    I8 const* sp = n.start.data();
+    LO const* rid = n.rid.data();
+    LO* rp = n.run_pos.data();
+    parallel_for(ntot, OSHB_LAMBDA(LO i) {
+      if (sp[i]) rp[rid[i]] = i;
+    }, "numbering(run list)");
+  }
   n.want_pos = collect_marked(wantm, &nw);
   n.run_key = GOs(nr);
   n.run_delta = GOs(nr);  // holds the run sums until set_bases

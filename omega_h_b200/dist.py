@@ -7,8 +7,8 @@ src/Omega_h_modify.cpp:406-444) happens here between the stages of the library's
 (include/oshb.h, oshb_pass_*), over torch.distributed: NCCL between GPUs, gloo in the CPU tests.
 
 Layout. Elements are owned by exactly one rank ("own:rank"); every rank also holds `halo`
-layers of vertex-adjacent elements of other ranks ("own:depth" = layer index, 0 for owned
-elements). Both element tags are inherited by the products of a split. Local entities keep the
+layers of vertex-adjacent elements of other ranks ("own:depth" = layer index; <= 0 for owned elements, negative in the
+band of own elements next to the partition boundary). Both element tags are inherited by the products of a split. Local entities keep the
 order of their global numbers, so every local row order -- and with it the numbering of the
 products -- equals the serial one. A pass can only trust what it sees completely:
 
@@ -115,6 +115,16 @@ class DevMesh:
                 self._post()
                 return out
         raise _lib.OshbError("no tag %s on dimension %d" % (name, ent_dim))
+
+    def tag_gather(self, ent_dim, name, idx32, dtype):
+        """values of a one-component tag at a list of entities"""
+        out = self.empty(idx32.numel(), dtype)
+        self._pre()
+        self.lib.check(self.lib.c.oshb_mesh_gather_tag(self.mesh.h, C.c_int(ent_dim), name.encode(),
+                                                       C.c_void_p(idx32.data_ptr()), C.c_int64(idx32.numel()),
+                                                       C.c_void_p(out.data_ptr()), C.c_int(0)))
+        self._post()
+        return out
 
     def tag_into(self, ent_dim, name, out):
         """copy a tag into a slice of a caller's buffer; the caller brackets a batch of these with
@@ -358,22 +368,12 @@ class DistMesh:
 
     def owned_mask(self, ent_dim):
         """entities in the closure of this rank's own elements"""
-        return self.dm.tag(ent_dim, "own:depth") == 0
+        return self.dm.tag(ent_dim, "own:depth") <= 0
 
     def owned_nelems(self):
         return int(self.owned_mask(self.mesh.dim()).sum().item())
 
     # ---- plans ------------------------------------------------------------------------------------
-    def _counted(self, ent_dim, rank_tag=None, gid=None):
-        """(local indices, global numbers) of the entities this rank counts and answers for: those
-        whose lowest adjacent owner rank ("own:rank") is this rank. In increasing global number."""
-        if rank_tag is None:
-            rank_tag = self.dm.tag(ent_dim, "own:rank")
-        if gid is None:
-            gid = self.dm.tag(ent_dim, "global")
-        idx = torch.nonzero(rank_tag == self.rank).flatten()
-        return idx, gid[idx]
-
     def _fetch_plan(self, want_idx, want_owner, want_gid, have_idx, have_gid, runs=None):
         """want_*: local entities whose value lives on another rank (want_owner);
         have_*: this rank's counted entities sorted by global number (the lookup table), or
@@ -412,7 +412,7 @@ class DistMesh:
                 ps.begin(2)
             with _Section(dm, "edge tags"):
                 edge_depth = dm.tag(EDGE, "own:depth")
-                mine = edge_depth == 0
+                mine = edge_depth <= 0
                 cand = ps.get(PASS_CANDIDATES)
                 any_cand = _any_rank((cand != 0) & mine, self.group)
             if not any_cand:
@@ -423,13 +423,17 @@ class DistMesh:
             with _Section(dm, "begin(lib)"):
                 ps.begin(1)
             with _Section(dm, "shell plan"):
-                edge_rank = dm.tag(EDGE, "own:rank")
-                egid = dm.tag(EDGE, "global")
-                have_idx, have_gid = self._counted(EDGE, edge_rank, egid)
+                # lookup table of the edges this rank answers for: counted here and inside the band
+                band = torch.nonzero(edge_depth < 0).flatten().to(torch.int32)
+                band = band[dm.tag_gather(EDGE, "own:rank", band, torch.int32) == self.rank]
+                have_idx = band.to(torch.int64)
+                have_gid = dm.tag_gather(EDGE, "global", band, torch.int64)
                 if CHECK and have_gid.numel() > 1:
                     assert bool((have_gid[1:] > have_gid[:-1]).all().item()), "local edge order lost the global order"
                 shell = torch.nonzero(edge_depth == trust + 1).flatten()
-                plan = self._fetch_plan(shell, edge_rank[shell].to(torch.int64), egid[shell], have_idx, have_gid)
+                shell32 = shell.to(torch.int32)
+                plan = self._fetch_plan(shell, dm.tag_gather(EDGE, "own:rank", shell32, torch.int32).to(torch.int64),
+                                        dm.tag_gather(EDGE, "global", shell32, torch.int64), have_idx, have_gid)
             with _Section(dm, "qualities exchange"):
                 plan.pull_pass_array(ps, PASS_QUALITIES)
                 ps.restate()
@@ -553,6 +557,17 @@ def distribute(base, halo, device, group=None):
         vmark[cv2v[depth < layer].flatten()] = True
         touched = vmark[cv2v].any(dim=1)
         depth = torch.where(touched & (depth == DEEP), layer, depth)
+    # the band: own elements within halo + 1 layers of a foreign one get depth -1, -2, ... (still
+    # "own" = depth <= 0). Everything a neighbour can ever ask this rank about lies in the band, so
+    # the per-pass lookup tables are built from the band instead of the whole part.
+    foreign = owner != rank
+    inner = torch.zeros_like(depth)
+    for layer in range(1, halo + 2):
+        vmark = torch.zeros(n[0], dtype=torch.bool, device=dev)
+        vmark[cv2v[foreign | (inner > 0)].flatten()] = True
+        touched = vmark[cv2v].any(dim=1) & (~foreign) & (inner == 0)
+        inner = torch.where(touched, layer, inner)
+    depth = torch.where(inner > 0, -inner, depth)
     keep = {dim: depth <= halo}
     for d in range(dim, 0, -1):
         deg = simplex_degree(d, d - 1)

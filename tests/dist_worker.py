@@ -57,8 +57,8 @@ def main():
     own = [part.owned_mask(d).cpu().numpy() for d in range(dim + 1)]
     erank = m.get_array(dim, "own:rank")
     edepth = m.get_array(dim, "own:depth")
-    assert np.array_equal(own[dim], edepth == 0)
-    assert np.all(erank[edepth == 0] == rank)
+    assert np.array_equal(own[dim], edepth <= 0)
+    assert np.all(erank[edepth <= 0] == rank)
     nown = np.array([int(own[dim].sum())], dtype=np.int64)
     t = torch.from_numpy(nown).to(device)
     dist.all_reduce(t)
