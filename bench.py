@@ -564,6 +564,10 @@ def main_b200_partitioned(args):
     halo = args.halo
     part0 = D.distribute(base, halo, device)
     nglobal0 = base.nelems()
+    # derive what the first pass asks for once, as the N = 1 arm's input has it cached
+    part0.mesh.ask_down(part0.mesh.dim(), 1)
+    part0.mesh.ask_verts_of(part0.mesh.dim())
+    part0.mesh.ask_verts_of(2)
     del base
     torch.cuda.empty_cache()   # the cut's temporaries: give them back before the library's pool grows
     opts = AdaptOpts(part0.mesh)

@@ -219,8 +219,9 @@ int oshb_pass_gather(oshb_pass* p, int which, const int32_t* edges, int64_t n, v
 int oshb_pass_scatter(oshb_pass* p, int which, const int32_t* edges, int64_t n, const void* in, int host);
 
 /* Distributed numbering, the volume work of modify_globals (src/Omega_h_modify.cpp:406-444) on
- * a partitioned mesh whose entities carry "own:rank" (int32: the rank that counts the entity)
- * and "own:depth" (int8) tags on every dimension; call between number and finish (or after
+ * a partitioned mesh whose entities carry the int32 tag "own:part" = (rank << 8) | (depth & 0xff)
+ * on every dimension (rank: the rank that counts the entity; depth: signed layer index, <= 0 on
+ * entities of own elements); call between number and finish (or after
  * select_keys returned 0 keys: every entity then counts once and commit renumbers in place).
  * Keys flatten (dimension, old global number) into one axis: key = number + key_offset[dim].
  *   runs_begin   scans the counts of the entities my_rank counts; lists the runs of consecutive

@@ -263,8 +263,7 @@ struct Pass {
     GO new_off[4] = {0, 0, 0, 0};
     LO lo[5] = {0, 0, 0, 0, 0};
     GOs gid[4];
-    LOs rk[4];
-    Bytes dp[4];
+    LOs own[4];  // "own:part" = (counting rank << 8) | (depth & 0xff)
     Bytes start;
     LOs rid;       // exclusive scan of start
     GOs pre;       // exclusive scan of the counted counts (ntot + 1)
@@ -501,7 +500,7 @@ void Pass::finish() {
 // ---- distributed numbering ------------------------------------------------------------------
 // modify_globals (src/Omega_h_modify.cpp:406-444) for a partitioned mesh, the volume work. The
 // caller (omega_h_b200/dist.py) owns the exchanges. Every entity is counted by one rank, the one
-// in its "own:rank" tag. Old global numbers are dense, so the entities a rank counts fall into
+// in its "own:part" tag (rank << 8 | depth). Old global numbers are dense, so the entities a rank counts fall into
 // runs of consecutive numbers at consecutive local positions; inside a run the global scan is
 // the local scan. runs_begin scans the counted counts and lists the runs (first key, sum); the
 // caller has them scanned across ranks and returns each run's base (runs_set_bases); entities
@@ -517,8 +516,7 @@ void Pass::runs_begin(int me, int trust, GO const* koff, int64_t* nruns, int64_t
     n.koff[d] = koff[d];
     n.lo[d + 1] = n.lo[d] + mesh->nents(d);
     n.gid[d] = mesh->globals(d);
-    n.rk[d] = mesh->get_los(d, "own:rank");
-    n.dp[d] = mesh->get_bytes(d, "own:depth");
+    n.own[d] = mesh->get_los(d, "own:part");
   }
   LO const ntot = n.lo[n.dim + 1];
   LOs w(ntot);
@@ -528,20 +526,21 @@ void Pass::runs_begin(int me, int trust, GO const* koff, int64_t* nruns, int64_t
     LO const nd = mesh->nents(d);
     LO const lo = n.lo[d];
     GO const* gid = n.gid[d].data();
-    LO const* rk = n.rk[d].data();
-    I8 const* dp = n.dp[d].data();
+    LO const* own = n.own[d].data();
     LO const* off = rb ? pass_offsets(this, d).data() : nullptr;
     LO* wp = w.data();
     I8* sp = n.start.data();
     I8* wm = wantm.data();
     parallel_for(nd, OSHB_LAMBDA(LO i) {
-      bool counted = (rk[i] == me);
+      LO o = own[i];
+      bool counted = ((o >> 8) == me);
+      int depth = int(I8(o & 0xff));
       LO cnt = off ? (off[i + 1] - off[i]) : 1;
       wp[lo + i] = counted ? cnt : 0;
       // continues a run iff the local predecessor is counted and holds the previous number
-      bool cont = counted && i > 0 && rk[i - 1] == me && gid[i - 1] + 1 == gid[i];
+      bool cont = counted && i > 0 && (own[i - 1] >> 8) == me && gid[i - 1] + 1 == gid[i];
       sp[lo + i] = (counted && !cont) ? 1 : 0;
-      wm[lo + i] = (!counted && dp[i] <= trust + 1) ? 1 : 0;
+      wm[lo + i] = (!counted && depth <= trust + 1) ? 1 : 0;
     }, "numbering(mark)");
   }
   n.pre = GOs(int64_t(ntot) + 1);
@@ -621,7 +620,7 @@ void Pass::runs_set_bases(GOs run_base, GO const* new_off) {
     LO const lo = n.lo[d];
     n.bases[d] = GOs(nd);
     GO* bp = n.bases[d].data();
-    LO const* rk = n.rk[d].data();
+    LO const* own = n.own[d].data();
     GO const* pre = n.pre.data();
     I8 const* sp = n.start.data();
     LO const* rid = n.rid.data();
@@ -631,7 +630,7 @@ void Pass::runs_set_bases(GOs run_base, GO const* new_off) {
     parallel_for(nd, OSHB_LAMBDA(LO i) {
       LO pos = lo + i;
       GO b = pre[pos];  // uncounted + untrusted: any number will do
-      if (rk[i] == me) b += delta[rid[pos] + sp[pos] - 1] - noff;
+      if ((own[i] >> 8) == me) b += delta[rid[pos] + sp[pos] - 1] - noff;
       bp[i] = b;
     }, "numbering(bases)");
   }
@@ -769,16 +768,16 @@ void pass_want_get(Pass* p, GOs* want_key, LOs* want_owner) {
   GO const* g1 = n.gid[1].data();
   GO const* g2 = n.dim >= 2 ? n.gid[2].data() : nullptr;
   GO const* g3 = n.dim >= 3 ? n.gid[3].data() : nullptr;
-  LO const* r0 = n.rk[0].data();
-  LO const* r1 = n.rk[1].data();
-  LO const* r2 = n.dim >= 2 ? n.rk[2].data() : nullptr;
-  LO const* r3 = n.dim >= 3 ? n.rk[3].data() : nullptr;
+  LO const* r0 = n.own[0].data();
+  LO const* r1 = n.own[1].data();
+  LO const* r2 = n.dim >= 2 ? n.own[2].data() : nullptr;
+  LO const* r3 = n.dim >= 3 ? n.own[3].data() : nullptr;
   parallel_for(nw, OSHB_LAMBDA(LO j) {
     LO p = wp[j];
-    if (p < l1) wk[j] = g0[p] + k0, wo[j] = r0[p];
-    else if (p < l2 || dim_ < 2) wk[j] = g1[p - l1] + k1, wo[j] = r1[p - l1];
-    else if (p < l3 || dim_ < 3) wk[j] = g2[p - l2] + k2, wo[j] = r2[p - l2];
-    else wk[j] = g3[p - l3] + k3, wo[j] = r3[p - l3];
+    if (p < l1) wk[j] = g0[p] + k0, wo[j] = r0[p] >> 8;
+    else if (p < l2 || dim_ < 2) wk[j] = g1[p - l1] + k1, wo[j] = r1[p - l1] >> 8;
+    else if (p < l3 || dim_ < 3) wk[j] = g2[p - l2] + k2, wo[j] = r2[p - l2] >> 8;
+    else wk[j] = g3[p - l3] + k3, wo[j] = r3[p - l3] >> 8;
   }, "numbering(want_get)");
 }
 void pass_runs_set_bases(Pass* p, GOs run_base, GO const* new_off) { p->runs_set_bases(run_base, new_off); }

@@ -6,9 +6,12 @@ src/Omega_h_indset_inline.hpp:38, modify_globals' scan over the linear partition
 src/Omega_h_modify.cpp:406-444) happens here between the stages of the library's pass
 (include/oshb.h, oshb_pass_*), over torch.distributed: NCCL between GPUs, gloo in the CPU tests.
 
-Layout. Elements are owned by exactly one rank ("own:rank"); every rank also holds `halo`
-layers of vertex-adjacent elements of other ranks ("own:depth" = layer index; <= 0 for owned elements, negative in the
-band of own elements next to the partition boundary). Both element tags are inherited by the products of a split. Local entities keep the
+Layout. Elements are owned by exactly one rank; every rank also holds `halo` layers of
+vertex-adjacent elements of other ranks. One int32 tag on every dimension, "own:part" =
+(rank << 8) | (depth & 0xff): rank = the lowest owner rank over the adjacent elements (the rank that
+counts the entity and answers for it), depth = the lowest layer index over them (<= 0 for own
+elements, negative in the band of own elements next to the partition boundary). The tag is
+inherited by the products of a split. Local entities keep the
 order of their global numbers, so every local row order -- and with it the numbering of the
 products -- equals the serial one. A pass can only trust what it sees completely:
 
@@ -85,6 +88,11 @@ def share_stream(lib, device):
     torch.cuda.set_stream(stream)
     lib.check(lib.c.oshb_set_stream(C.c_void_p(stream.cuda_stream)))
     _SHARED[id(lib)] = stream
+
+
+def _depth_of(own):
+    """signed low byte of an "own:part" tag"""
+    return (own << 24) >> 24
 
 
 class DevMesh:
@@ -368,7 +376,7 @@ class DistMesh:
 
     def owned_mask(self, ent_dim):
         """entities in the closure of this rank's own elements"""
-        return self.dm.tag(ent_dim, "own:depth") <= 0
+        return _depth_of(self.dm.tag(ent_dim, "own:part")) <= 0
 
     def owned_nelems(self):
         return int(self.owned_mask(self.mesh.dim()).sum().item())
@@ -411,7 +419,7 @@ class DistMesh:
             with _Section(dm, "candidates(lib)"):
                 ps.begin(2)
             with _Section(dm, "edge tags"):
-                edge_depth = dm.tag(EDGE, "own:depth")
+                edge_depth = _depth_of(dm.tag(EDGE, "own:part"))
                 mine = edge_depth <= 0
                 cand = ps.get(PASS_CANDIDATES)
                 any_cand = _any_rank((cand != 0) & mine, self.group)
@@ -425,14 +433,14 @@ class DistMesh:
             with _Section(dm, "shell plan"):
                 # lookup table of the edges this rank answers for: counted here and inside the band
                 band = torch.nonzero(edge_depth < 0).flatten().to(torch.int32)
-                band = band[dm.tag_gather(EDGE, "own:rank", band, torch.int32) == self.rank]
+                band = band[(dm.tag_gather(EDGE, "own:part", band, torch.int32) >> 8) == self.rank]
                 have_idx = band.to(torch.int64)
                 have_gid = dm.tag_gather(EDGE, "global", band, torch.int64)
                 if CHECK and have_gid.numel() > 1:
                     assert bool((have_gid[1:] > have_gid[:-1]).all().item()), "local edge order lost the global order"
                 shell = torch.nonzero(edge_depth == trust + 1).flatten()
                 shell32 = shell.to(torch.int32)
-                plan = self._fetch_plan(shell, dm.tag_gather(EDGE, "own:rank", shell32, torch.int32).to(torch.int64),
+                plan = self._fetch_plan(shell, (dm.tag_gather(EDGE, "own:part", shell32, torch.int32) >> 8).to(torch.int64),
                                         dm.tag_gather(EDGE, "global", shell32, torch.int64), have_idx, have_gid)
             with _Section(dm, "qualities exchange"):
                 plan.pull_pass_array(ps, PASS_QUALITIES)
@@ -590,7 +598,7 @@ def distribute(base, halo, device, group=None):
                 continue
             t = src.tag(d, name).view(n[d], nc)[keep[d]].flatten()
             pm.set_tag(d, name, nc, t, internal=(name != "global"))
-    # "own:rank" / "own:depth" on every dimension: the lowest owner rank / depth over the adjacent
+    # "own:part" (rank, depth) on every dimension: the lowest owner rank / depth over the adjacent
     # elements, from the FULL mesh; refinement inherits both (products of an entity are adjacent to
     # children of exactly the elements the entity was adjacent to)
     for d in range(dim + 1):
@@ -603,8 +611,7 @@ def distribute(base, halo, device, group=None):
             rk.scatter_reduce_(0, c2d, owner.repeat_interleave(deg), reduce="amin", include_self=True)
             dp = torch.full((n[d],), DEEP, dtype=torch.int64, device=dev)
             dp.scatter_reduce_(0, c2d, depth.repeat_interleave(deg), reduce="amin", include_self=True)
-        pm.set_tag(d, "own:rank", 1, rk[keep[d]].to(torch.int32))
-        pm.set_tag(d, "own:depth", 1, dp[keep[d]].to(torch.int8))
+        pm.set_tag(d, "own:part", 1, ((rk[keep[d]] << 8) | (dp[keep[d]] & 0xff)).to(torch.int32))
     out = DistMesh(part, device, halo, group)
     out.nglobal = n + [0] * (4 - len(n))
     return out

@@ -55,8 +55,9 @@ def main():
     m = part.mesh
     gl = [m.globals(d) for d in range(dim + 1)]
     own = [part.owned_mask(d).cpu().numpy() for d in range(dim + 1)]
-    erank = m.get_array(dim, "own:rank")
-    edepth = m.get_array(dim, "own:depth")
+    part_tag = m.get_array(dim, "own:part")
+    erank = part_tag >> 8
+    edepth = (part_tag << 24) >> 24
     assert np.array_equal(own[dim], edepth <= 0)
     assert np.all(erank[edepth <= 0] == rank)
     nown = np.array([int(own[dim].sum())], dtype=np.int64)
