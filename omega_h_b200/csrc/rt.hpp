@@ -4,8 +4,9 @@
 // Replaces the reference's array runtime + execution backends for this path
 // (Read/Write: src/Omega_h_array.hpp:23-228; parallel_for: src/Omega_h_for.hpp:20-101;
 //  atomics: src/Omega_h_atomics.hpp:12-37). One process drives one GPU; all work is
-// enqueued on one stream; device memory comes from the stream-ordered pool
-// (cudaMallocAsync) so temporaries cost no cudaMalloc and no implicit sync.
+// enqueued on one stream (the library's own, or the caller's after oshb_set_stream); device
+// memory comes from a stream-ordered best-fit caching allocator (alloc.cu) so temporaries
+// cost no cudaMalloc and no implicit sync.
 //
 // OSHB_EMU: a TEST-ONLY build mode (tests/emu/) that compiles the very same kernel
 // bodies as serial host loops so the mesh logic can be checked against the oracle on a

@@ -182,13 +182,6 @@ def load(path):
     return read_oshd(path)
 
 
-def random_case(seed, dim, n, aniso):
-    """Seeded irregular input for oracle-vs-CUDA parity: a reference-built box fixture whose
-    coordinates are jittered and whose metric is a random graded field (isotropic or SPD)."""
-    rng = np.random.default_rng(seed)
-    return rng
-
-
 def jittered_input(fx, seed, aniso, permute_globals=False):
     """copy of a fixture's input mesh with seeded jitter on interior coordinates and a random metric"""
     rng = np.random.default_rng(seed)
