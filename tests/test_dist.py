@@ -34,6 +34,13 @@ def test_partitioned_loop_matches_serial_gloo(emu_lib, nranks, n, halo, aniso, d
 
 
 @pytest.mark.gpu
+def test_partitioned_loop_one_gpu_nccl(gpu_lib):
+    """the whole partitioned path (staged pass, shared stream, numbering helpers, NCCL collectives
+    with itself) on a single GPU"""
+    run_worker(1, gpu_lib.path, "cuda", 16, 4, 0, 3, 29540)
+
+
+@pytest.mark.gpu
 def test_partitioned_loop_matches_serial_nccl(gpu_lib):
     import torch
     if torch.cuda.device_count() < 2:

@@ -134,3 +134,21 @@ def test_invert_adj_random_rows(lib, seed, nlow, maxdeg):
     assert np.array_equal(d_off.to_host(), want_off)
     assert np.array_equal(d_ab.to_host(), want_h)
     assert np.array_equal(d_oc.to_host(), want_c)
+
+
+def test_gather_tag(emu_lib):
+    """oshb_mesh_gather_tag: values of a one-component tag at listed entities, every tag type"""
+    import ctypes as C
+    import numpy as np
+    from omega_h_b200 import Mesh
+    m = Mesh(2, lib=emu_lib)
+    m.set_verts(5)
+    vals = {"a": np.arange(5, dtype=np.int8) * 3, "b": np.arange(5, dtype=np.int32) * 7,
+            "c": np.arange(5, dtype=np.int64) * 11, "d": np.arange(5, dtype=np.float64) * 0.5}
+    idx = np.array([4, 0, 2, 2], dtype=np.int32)
+    for name, v in vals.items():
+        m.add_tag(0, name, 1, v)
+        out = np.empty(4, dtype=v.dtype)
+        emu_lib.check(emu_lib.c.oshb_mesh_gather_tag(m.h, C.c_int(0), name.encode(), idx.ctypes.data_as(C.c_void_p),
+                                                     C.c_int64(4), out.ctypes.data_as(C.c_void_p), C.c_int(1)))
+        assert np.array_equal(out, v[idx])
