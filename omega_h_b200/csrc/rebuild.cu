@@ -535,9 +535,28 @@ void Rebuild::number() {
       rc[e] = (s == -1) ? 1 : ((s == -2) ? 0 : key_nprods(t1, ent_dim, s));
     }, "status+rep_counts");
     offsets[ent_dim] = offset_scan(rep_counts);
-    rep_counts.reset();
+  }
+  // the new entity counts of all dimensions in ONE read-back (each blocking read-back drains the
+  // stream; the pass has ~15 of them)
+  {
+    LO* cell = reinterpret_cast<LO*>(static_cast<char*>(ctx().dscratch) + 1280);
+    LO const* o0 = offsets[0].data();
+    LO const* o1 = offsets[1].data();
+    LO const* o2 = dim >= 2 ? offsets[2].data() : nullptr;
+    LO const* o3 = dim >= 3 ? offsets[3].data() : nullptr;
+    LO const n0 = mesh->nents(0), n1 = mesh->nents(1), n2 = dim >= 2 ? mesh->nents(2) : 0,
+             n3 = dim >= 3 ? mesh->nents(3) : 0;
+    parallel_for(4, OSHB_LAMBDA(LO d) {
+      cell[d] = (d == 0) ? o0[n0] : (d == 1) ? o1[n1] : (d == 2) ? (o2 ? o2[n2] : 0) : (o3 ? o3[n3] : 0);
+    }, "new_counts");
+    LO h[4];
+    d2h(h, cell, sizeof(h));
+    for (int d = 0; d < 4; ++d) nnew[d] = h[d];
+  }
+  for (int ent_dim = 0; ent_dim <= dim; ++ent_dim) {
+    LO const nold = mesh->nents(ent_dim);
+    LO* st = (ent_dim >= EDGE) ? status[ent_dim].data() : nullptr;
     LO const* off = offsets[ent_dim].data();
-    nnew[ent_dim] = last_of(offsets[ent_dim]);
     old2new[ent_dim] = LOs(nold);
     LO* o2n = old2new[ent_dim].data();
     // globals of the old entities on the linear partition (modify_globals,

@@ -202,9 +202,10 @@ static Adj key_rows(LO nelems, int nce, LO const* ce2e, I8 const* ce_codes, LO c
   }, "key_rows(count)");
   LOs offsets = offset_scan(counts);
   LO const* off = offsets.data();
-  LO const total = last_of(offsets);
-  LOs ents(total);
-  Bytes codes(total);
+  // an element lies in at most one key's cavity (keys are an independent set), so nelems bounds
+  // the number of entries: sizing the arrays by the bound saves a blocking read-back of the total
+  LOs ents(nelems);
+  Bytes codes(nelems);
   LO* en = ents.data();
   I8* co = codes.data();
   parallel_for(nelems, OSHB_LAMBDA(LO c) {
