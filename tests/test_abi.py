@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from omega_h_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -32,3 +34,29 @@ def test_product_library_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.PRODUCT_LIB], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+CORNER_KEYS = "keys per pass: 63 195 123 184 441 261 414 813 93"
+
+
+def _run_example(name):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "examples"), "all", "emu"], check=True,
+                   stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(root, "examples", "_build", name)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+def test_cpp_caller_corner_trace_emulation(emu_lib):
+    """examples/corner_refine.cpp -- the reference's corner_test driver written against the C ABI in
+    C++ -- splits the same number of edges per pass as the reference."""
+    out = _run_example("corner_refine_emu")
+    assert CORNER_KEYS in out and "host emulation" in out
+
+
+@pytest.mark.gpu
+def test_cpp_caller_corner_trace_gpu(gpu_lib):
+    out = _run_example("corner_refine")
+    assert CORNER_KEYS in out and "sm_100a" in out
