@@ -4,6 +4,7 @@
 // but the algorithms are re-designed for HBM: no materialised use lists, no per-use
 // linear search through vertex stars.
 #include "mesh.hpp"
+#include "sortnet.hpp"
 
 namespace oshb {
 
@@ -97,63 +98,7 @@ Adj invert_adj(Adj const& down, int nlows_per_high, LO nlows) {
     LO const b = off[l];
     LO const e = off[l + 1];
     LO const len = e - b;
-    // rows are short (~5 for E->F/E->R, ~14 for V->E, ~35 for V->F): rows of <= 8 go through
-    // a fixed 19-comparator network in registers, <= 16 through a 16-wide odd-even merge
-    // network, longer ones through an in-place insertion sort
-    if (len <= 8) {
-      LO r[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) r[k] = (k < len) ? slots[b + k] : 0x7fffffff;
-#define OSHB_CE(i, j)       \
-  {                         \
-    LO lo_ = min_lo(r[i], r[j]); \
-    LO hi_ = max_lo(r[i], r[j]); \
-    r[i] = lo_;             \
-    r[j] = hi_;             \
-  }
-      OSHB_CE(0, 1) OSHB_CE(2, 3) OSHB_CE(4, 5) OSHB_CE(6, 7)
-      OSHB_CE(0, 2) OSHB_CE(1, 3) OSHB_CE(4, 6) OSHB_CE(5, 7)
-      OSHB_CE(1, 2) OSHB_CE(5, 6) OSHB_CE(0, 4) OSHB_CE(3, 7)
-      OSHB_CE(1, 5) OSHB_CE(2, 6)
-      OSHB_CE(1, 4) OSHB_CE(3, 6)
-      OSHB_CE(2, 4) OSHB_CE(3, 5)
-      OSHB_CE(3, 4)
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (k < len) slots[b + k] = r[k];
-    } else if (len <= 16) {
-      LO r[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) r[k] = (k < len) ? slots[b + k] : 0x7fffffff;
-      // Batcher odd-even merge sort, n = 16 (fully unrolled: indices are compile-time)
-#pragma unroll
-      for (int p = 1; p < 16; p <<= 1) {
-#pragma unroll
-        for (int k = p; k >= 1; k >>= 1) {
-#pragma unroll
-          for (int j = k % p; j + k < 16; j += 2 * k) {
-#pragma unroll
-            for (int i = 0; i < k; ++i) {
-              if (i + j + k < 16 && ((i + j) / (p * 2)) == ((i + j + k) / (p * 2))) OSHB_CE(i + j, i + j + k)
-            }
-          }
-        }
-      }
-#undef OSHB_CE
-#pragma unroll
-      for (int k = 0; k < 16; ++k)
-        if (k < len) slots[b + k] = r[k];
-    } else {
-      for (LO i = b + 1; i < e; ++i) {
-        LO x = slots[i];
-        LO j = i - 1;
-        while (j >= b && slots[j] > x) {
-          slots[j + 1] = slots[j];
-          --j;
-        }
-        slots[j + 1] = x;
-      }
-    }
+    sort_small_row(slots + b, len);  // sortnet.hpp: register networks up to 64 entries
     for (LO i = b; i < e; ++i) {
       LO hl = slots[i];
       LO h = hl / deg_h;

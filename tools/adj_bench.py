@@ -50,6 +50,15 @@ def main():
             lib.timer_start()
             fn()
             best = min(best, lib.timer_stop())
+        if "--profile" in sys.argv:
+            # per-kernel split of one more call (CUDA events around every launch)
+            lib.profile_begin(None)
+            fn()
+            agg = {}
+            for name, ms in lib.profile_end():
+                k = name.split("\t")[0]
+                agg[k] = agg.get(k, 0.0) + ms
+            print("    " + "  ".join("%s %.2f" % kv for kv in sorted(agg.items(), key=lambda kv: -kv[1])), file=sys.stderr)
         return best
 
     def report(name, ms, nbytes):
