@@ -218,6 +218,11 @@ def build_input(n, lib, workload="iso"):
     else:
         h = 1.0 / n / 2.0
         m.add_tag(VERT, "metric", 1, np.full(m.nverts(), 1.0 / (h * h)))
+    if os.environ.get("OSHB_BENCH_EXTRA_TAG"):
+        # diagnosis only: what one more inherited int32 tag on every dimension costs the rebuild
+        # (the partitioned path carries "own:part")
+        for d in range(4):
+            m.add_tag(d, "own:part", 1, np.zeros(m.nents(d), dtype=np.int32))
     m.ask_lengths()
     m.ask_qualities()
     lib.sync()
