@@ -547,18 +547,26 @@ class DistMesh:
         return nnext
 
 
-def distribute(base, halo, device, group=None):
-    """Cut a mesh that every rank holds in full (e.g. each built the same box) into parts:
-    contiguous ranges of the element order + `halo` layers of vertex-adjacent elements. Local
-    entities are the kept ones in increasing global number."""
+def _chain_min(dim, n, down, elem_values, fill):
+    """per entity of every dimension: the minimum of elem_values over its adjacent elements, passed
+    down the stored adjacencies (every element around an entity contains a face around it, ...)"""
+    out = {dim: elem_values}
+    for d in range(dim, 0, -1):
+        deg = simplex_degree(d, d - 1)
+        v = torch.full((n[d - 1],), fill, dtype=torch.int64, device=elem_values.device)
+        v.scatter_reduce_(0, down[d][0].to(torch.int64), out[d].repeat_interleave(deg), reduce="amin", include_self=True)
+        out[d - 1] = v
+    return out
+
+
+def _build_part(lib, device, group, dim, n, down, cv2v, tags, gids, owner, halo, nglobal):
+    """From a mesh that contains this rank's own elements and at least `halo` + 1 layers around
+    them (arrays as tensors, entities in increasing global number): the part = own elements +
+    `halo` layers, with "own:part" on every dimension.
+      down[d] = (entity -> d-1 entities int32, codes int8 or None), cv2v = element -> vertices,
+      tags[d] = [(name, ncomps, values)], gids[d] = global numbers, owner = owner rank per element"""
     rank, P = dist.get_rank(group), dist.get_world_size(group)
-    src = DevMesh(base, device)
-    dev = src.device
-    dim = base.dim()
-    n = [base.nents(d) for d in range(dim + 1)]
-    down = {d: src.down(d, d - 1) for d in range(1, dim + 1)}
-    cv2v = src.down(dim, VERT)[0].to(torch.int64).view(n[dim], dim + 1)
-    owner = (torch.arange(n[dim], device=dev, dtype=torch.int64) * P) // n[dim]
+    dev = torch.device(device)
     depth = torch.where(owner == rank, 0, DEEP).to(torch.int64)
     for layer in range(1, halo + 1):
         vmark = torch.zeros(n[0], dtype=torch.bool, device=dev)
@@ -567,7 +575,7 @@ def distribute(base, halo, device, group=None):
         depth = torch.where(touched & (depth == DEEP), layer, depth)
     # the band: own elements within halo + 1 layers of a foreign one get depth -1, -2, ... (still
     # "own" = depth <= 0). Everything a neighbour can ever ask this rank about lies in the band, so
-    # the per-pass lookup tables are built from the band instead of the whole part.
+    # the per-pass lookup tables -- and what a re-ghosting sends -- come from the band.
     foreign = owner != rank
     inner = torch.zeros_like(depth)
     for layer in range(1, halo + 2):
@@ -583,7 +591,7 @@ def distribute(base, halo, device, group=None):
         k[down[d][0].view(n[d], deg)[keep[d]].flatten().to(torch.int64)] = True
         keep[d - 1] = k
     o2n = {d: (torch.cumsum(keep[d].to(torch.int64), 0) - 1).to(torch.int32) for d in range(dim + 1)}
-    part = Mesh(dim, base.lib)
+    part = Mesh(dim, lib)
     pm = DevMesh(part, device)
     part.set_verts(int(keep[0].sum().item()))
     for d in range(1, dim + 1):
@@ -593,25 +601,36 @@ def distribute(base, halo, device, group=None):
         codes = down[d][1].view(n[d], deg)[keep[d]].flatten() if d > 1 else None
         pm.set_ents(d, new_down, codes)
     for d in range(dim + 1):
-        for name, ttype, nc in base.tags(d):
-            if name.startswith("own:"):
-                continue
-            t = src.tag(d, name).view(n[d], nc)[keep[d]].flatten()
-            pm.set_tag(d, name, nc, t, internal=(name != "global"))
+        pm.set_tag(d, "global", 1, gids[d][keep[d]])
+        for name, nc, t in tags[d]:
+            pm.set_tag(d, name, nc, t.view(n[d], nc)[keep[d]].flatten())
     # "own:part" (rank, depth) on every dimension: the lowest owner rank / depth over the adjacent
-    # elements, from the FULL mesh; refinement inherits both (products of an entity are adjacent to
-    # children of exactly the elements the entity was adjacent to)
+    # elements, taken BEFORE the cut (the layer beyond the halo still counts); refinement inherits
+    # both (products of an entity are adjacent to children of exactly the elements it was adjacent to)
+    rk = _chain_min(dim, n, down, owner, P)
+    dp = _chain_min(dim, n, down, depth, DEEP)
     for d in range(dim + 1):
-        if d == dim:
-            rk, dp = owner, depth
-        else:
-            c2d = src.down(dim, d)[0].to(torch.int64)
-            deg = simplex_degree(dim, d)
-            rk = torch.full((n[d],), P, dtype=torch.int64, device=dev)
-            rk.scatter_reduce_(0, c2d, owner.repeat_interleave(deg), reduce="amin", include_self=True)
-            dp = torch.full((n[d],), DEEP, dtype=torch.int64, device=dev)
-            dp.scatter_reduce_(0, c2d, depth.repeat_interleave(deg), reduce="amin", include_self=True)
-        pm.set_tag(d, "own:part", 1, ((rk[keep[d]] << 8) | (dp[keep[d]] & 0xff)).to(torch.int32))
+        pm.set_tag(d, "own:part", 1, ((rk[d][keep[d]] << 8) | (dp[d][keep[d]] & 0xff)).to(torch.int32))
     out = DistMesh(part, device, halo, group)
-    out.nglobal = n + [0] * (4 - len(n))
+    out.nglobal = list(nglobal) + [0] * (4 - len(nglobal))
     return out
+
+
+def distribute(base, halo, device, group=None):
+    """Cut a mesh that every rank holds in full (e.g. each built the same box) into parts:
+    contiguous ranges of the element order + `halo` layers of vertex-adjacent elements. Local
+    entities are the kept ones in increasing global number."""
+    P = dist.get_world_size(group)
+    src = DevMesh(base, device)
+    dev = src.device
+    dim = base.dim()
+    n = [base.nents(d) for d in range(dim + 1)]
+    down = {d: src.down(d, d - 1) for d in range(1, dim + 1)}
+    cv2v = src.down(dim, VERT)[0].to(torch.int64).view(n[dim], dim + 1)
+    owner = (torch.arange(n[dim], device=dev, dtype=torch.int64) * P) // n[dim]
+    tags = {}
+    for d in range(dim + 1):
+        tags[d] = [(name, nc, src.tag(d, name)) for name, _, nc in base.tags(d)
+                   if name != "global" and not name.startswith("own:")]
+    gids = {d: src.tag(d, "global") for d in range(dim + 1)}
+    return _build_part(base.lib, device, group, dim, n, down, cv2v, tags, gids, owner, halo, n)
