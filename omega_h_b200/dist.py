@@ -20,9 +20,9 @@ products -- equals the serial one. A pass can only trust what it sees completely
            ignores                 anything deeper (stale, never sent to anyone)
 
 so `halo` layers carry `halo` passes without moving any mesh data between ranks; only the shell's
-per-edge qualities / set states and the global-number scan cross NVLink. Re-ghosting (the
-reference's ghost_mesh + migrate, src/Omega_h_ghost.cpp, src/Omega_h_migrate.cpp) to continue
-beyond that is not built yet; `refine_by_size` raises when the halo is used up.
+per-edge qualities / set states and the global-number scan cross NVLink. When the halo is used up,
+`reghost()` fetches a fresh one from the owners (the reference's ghost_mesh + migrate,
+src/Omega_h_ghost.cpp, src/Omega_h_migrate.cpp -- once per `halo` passes instead of twice per pass).
 
 torch is plumbing here: device buffers handed to the C ABI by pointer, and the collectives.
 """
@@ -426,8 +426,11 @@ class DistMesh:
             if not any_cand:
                 return False
             if trust < 0:
-                raise _lib.OshbError("halo of %d layers is used up after %d passes; re-ghosting is not implemented"
-                                     % (self.halo, self.passes))
+                # the halo is used up: fetch a fresh one from the owners and run this pass on it
+                ps.close()
+                with _Section(dm, "reghost"):
+                    self.reghost()
+                return self.refine_by_size(opts)
             with _Section(dm, "begin(lib)"):
                 ps.begin(1)
             with _Section(dm, "shell plan"):
@@ -480,6 +483,116 @@ class DistMesh:
             return True
         finally:
             ps.close()
+
+    # ---- a fresh halo ---------------------------------------------------------------------------
+    def reghost(self):
+        """Replace the worn halo by a fresh one (what ghost_mesh + migrate_mesh do in the reference,
+        src/Omega_h_ghost.cpp:102-141, src/Omega_h_migrate.cpp:15-225, once per `halo` passes instead
+        of twice per pass). Every rank keeps the closure of its own elements and receives the bands of
+        its neighbours (their own elements within halo + 1 layers of the partition boundary, closure
+        and tags included, entities named by global number); the union is merged by global number --
+        which keeps the local order equal to the global one -- and cut to `halo` layers."""
+        mesh, dm, dev = self.mesh, self.dm, self.device
+        dim, P, me = mesh.dim(), self.size, self.rank
+        nloc = [mesh.nents(d) for d in range(dim + 1)]
+        own = [dm.tag(d, "own:part") for d in range(dim + 1)]
+        depth = [_depth_of(o) for o in own]
+        gid = [dm.tag(d, "global") for d in range(dim + 1)]
+        down = {d: dm.down(d, d - 1) for d in range(1, dim + 1)}
+        cv2v = dm.down(dim, VERT)[0].to(torch.int64).view(nloc[dim], dim + 1)
+        tagdefs = {d: [(name, nc) for name, _, nc in mesh.tags(d) if name != "global" and not name.startswith("own:")]
+                   for d in range(dim + 1)}
+        elem_rank = (own[dim] >> 8).to(torch.int64)
+
+        def records(d, idx):
+            """everything that defines the entities idx of dimension d, by global number"""
+            rec = [gid[d][idx]]
+            if d >= 1:
+                deg = simplex_degree(d, d - 1)
+                rec.append(gid[d - 1][down[d][0].view(nloc[d], deg)[idx].to(torch.int64)].flatten())
+                if d >= 2:
+                    rec.append(down[d][1].view(nloc[d], deg)[idx].flatten())
+            for name, nc in tagdefs[d]:
+                rec.append(dm.tag(d, name).view(nloc[d], nc)[idx].flatten())
+            if d == dim:
+                rec.append(elem_rank[idx])
+                rec.append(gid[0][cv2v[idx]].flatten())
+            return rec
+
+        keep_idx = [torch.nonzero(depth[d] <= 0).flatten() for d in range(dim + 1)]
+        band_idx = [torch.nonzero(depth[d] < 0).flatten() for d in range(dim + 1)]
+        mine = [records(d, keep_idx[d]) for d in range(dim + 1)]
+        band = [records(d, band_idx[d]) for d in range(dim + 1)]
+        # who exchanges with whom: ranks whose elements I hold, and theirs (an element one layer
+        # beyond my halo may belong to a rank I have not met yet; it decides "own:part" at the rim)
+        seen = torch.zeros(P, dtype=torch.int64, device=dev)
+        seen[torch.unique(elem_rank)] = 1
+        table = torch.empty(P * (P + dim + 1), dtype=torch.int64, device=dev)
+        counts = torch.tensor([int(b.numel()) for b in band_idx], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(table, torch.cat([seen, counts]), group=self.group)
+        table = table.view(P, P + dim + 1)
+        adj = table[:, :P].cpu().numpy() != 0
+        adj = adj | adj.T
+        two = adj | ((adj.astype(np.int64) @ adj.astype(np.int64)) > 0)
+        nbrs = [r for r in range(P) if r != me and two[me, r]]
+        their = table[:, P:].tolist()
+        # the same band goes to every neighbour: point-to-point, array by array
+        got = {r: [[] for _ in range(dim + 1)] for r in nbrs}
+        for d in range(dim + 1):
+            width = [rec.numel() // max(band_idx[d].numel(), 1) for rec in band[d]]
+            for k, rec in enumerate(band[d]):
+                ops = []
+                for r in nbrs:
+                    if rec.numel():
+                        ops.append(dist.P2POp(dist.isend, rec.contiguous(), r, group=self.group))
+                    nr = int(their[r][d]) * width[k] if band_idx[d].numel() else None
+                    if nr is None:
+                        # my own band is empty in this dimension: the width comes from the kept set
+                        nr = int(their[r][d]) * (mine[d][k].numel() // max(keep_idx[d].numel(), 1))
+                    buf = torch.empty(nr, dtype=rec.dtype, device=dev)
+                    got[r][d].append(buf)
+                    if nr:
+                        ops.append(dist.P2POp(dist.irecv, buf, r, group=self.group))
+                if ops:
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
+        # merge by global number
+        n, uniq, new_down, new_tags, first = [0] * (dim + 1), {}, {}, {}, {}
+        for d in range(dim + 1):
+            parts = [mine[d]] + [got[r][d] for r in nbrs]
+            G = torch.cat([p[0] for p in parts])
+            uniq[d], inv = torch.unique(G, sorted=True, return_inverse=True)
+            n[d] = int(uniq[d].numel())
+            f = torch.full((n[d],), G.numel(), dtype=torch.int64, device=dev)
+            f.scatter_reduce_(0, inv, torch.arange(G.numel(), device=dev), reduce="amin", include_self=True)
+            first[d] = f
+            k = 1
+            if d >= 1:
+                deg = simplex_degree(d, d - 1)
+                dg = torch.cat([p[k] for p in parts]).view(-1, deg)[f]
+                idx = torch.searchsorted(uniq[d - 1], dg.flatten())
+                if CHECK:
+                    assert bool((uniq[d - 1][idx.clamp(max=n[d - 1] - 1)] == dg.flatten()).all().item()), \
+                        "re-ghosting: a bounding entity is missing"
+                k += 1
+                codes = None
+                if d >= 2:
+                    codes = torch.cat([p[k] for p in parts]).view(-1, deg)[f].flatten()
+                    k += 1
+                new_down[d] = (idx.to(torch.int32), codes)
+            new_tags[d] = []
+            for name, nc in tagdefs[d]:
+                new_tags[d].append((name, nc, torch.cat([p[k] for p in parts]).view(-1, nc)[f].flatten()))
+                k += 1
+            if d == dim:
+                owner = torch.cat([p[k] for p in parts])[f]
+                vg = torch.cat([p[k + 1] for p in parts]).view(-1, dim + 1)[f]
+                new_cv2v = torch.searchsorted(uniq[0], vg.flatten()).view(-1, dim + 1)
+        fresh = _build_part(mesh.lib, dev, self.group, dim, n, new_down, new_cv2v, new_tags, uniq, owner, self.halo,
+                            self.nglobal[:dim + 1])
+        self.mesh, self.dm = fresh.mesh, fresh.dm
+        self.passes = 0
+        self.reghosts = getattr(self, "reghosts", 0) + 1
 
     def _number_globally(self, ps, trust):
         """modify_globals (src/Omega_h_modify.cpp:406-444): exclusive scan, in global-number order, of

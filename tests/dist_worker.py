@@ -87,8 +87,8 @@ def main():
     lv = gl[0][m.ask_verts_of(dim).reshape(-1, dim + 1)[own[dim]]]
     assert np.array_equal(sv, lv)
     if rank == 0:
-        print("DIST_OK passes=%d ranks=%d serial_elems=%d local_elems=%d owned=%d" % (
-            npass, P, serial.nelems(), m.nelems(), int(own[dim].sum())))
+        print("DIST_OK passes=%d ranks=%d serial_elems=%d local_elems=%d owned=%d reghosts=%d" % (
+            npass, P, serial.nelems(), m.nelems(), int(own[dim].sum()), getattr(part, "reghosts", 0)))
     dist.barrier()
     dist.destroy_process_group()
 

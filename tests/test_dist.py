@@ -33,11 +33,25 @@ def test_partitioned_loop_matches_serial_gloo(emu_lib, nranks, n, halo, aniso, d
     run_worker(nranks, emu_lib.path, "cpu", n, halo, aniso, dim, 29530 + nranks + n)
 
 
+@pytest.mark.parametrize("nranks,n,halo,aniso,dim", [
+    (2, 8, 2, 0, 3),    # 4 passes on a 2-layer halo: one re-ghosting
+    (3, 6, 1, 0, 3),    # a 1-layer halo: a fresh halo before every pass but the first
+    (2, 6, 2, 1, 3),    # anisotropic, 8 passes, 3 re-ghostings
+    (2, 16, 1, 0, 2),   # triangles
+])
+def test_reghosting_gloo(emu_lib, nranks, n, halo, aniso, dim):
+    """loops longer than the halo: DistMesh.reghost() must hand every rank a halo on which the
+    remaining passes again equal the serial ones"""
+    out = run_worker(nranks, emu_lib.path, "cpu", n, halo, aniso, dim, 29560 + nranks + n + halo)
+    assert int(out.split("reghosts=")[1].split()[0]) >= 1
+
+
 @pytest.mark.gpu
 def test_partitioned_loop_one_gpu_nccl(gpu_lib):
     """the whole partitioned path (staged pass, shared stream, numbering helpers, NCCL collectives
     with itself) on a single GPU"""
     run_worker(1, gpu_lib.path, "cuda", 16, 4, 0, 3, 29540)
+    run_worker(1, gpu_lib.path, "cuda", 16, 2, 0, 3, 29539)    # with a re-ghosting (no neighbours: a re-cut)
 
 
 @pytest.mark.gpu
@@ -48,3 +62,5 @@ def test_partitioned_loop_matches_serial_nccl(gpu_lib):
     run_worker(2, gpu_lib.path, "cuda", 16, 4, 0, 3, 29541)
     run_worker(2, gpu_lib.path, "cuda", 24, 5, 0, 3, 29542)
     run_worker(2, gpu_lib.path, "cuda", 10, 10, 1, 3, 29543)
+    out = run_worker(2, gpu_lib.path, "cuda", 16, 2, 0, 3, 29544)    # re-ghosting over NCCL point-to-point
+    assert int(out.split("reghosts=")[1].split()[0]) >= 1
