@@ -600,10 +600,18 @@ def main_b200_partitioned(args):
     last = dict(part.last)
     del part
 
+    # pick the dominant library kernel (outside the timed region)
+    part = part0.clone()
+    lib.profile_begin(None)
+    loop(part)
+    agg = summarize_profile(lib.profile_end())
+    top = max(agg.items(), key=lambda kv: kv[1][1])[0]
+    del part
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     launches0 = lib.launch_count()
+    lib.profile_begin(top)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -613,9 +621,25 @@ def main_b200_partitioned(args):
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
+    top_recs = lib.profile_end()
     launches = lib.launch_count() - launches0
     clocks = sampler.stop()
     del part
+    # roofline of the dominant library kernel on rank 0 (timed live with CUDA events, as at N = 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    cnt, tms, tbytes = summarize_profile(top_recs).get(top, (0, 0.0, 0))
+    achieved = (tbytes / 1e9) / (tms / 1e3) if tms > 0 and tbytes else None
+    roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "launches": cnt, "avg_ms": (tms / cnt) if cnt else None,
+                "share_of_step": (tms / dev_ms) if dev_ms > 0 else None,
+                "algorithmic_bytes_per_launch": (tbytes / cnt) if cnt else None, "rank": 0}
     tm = torch.tensor([dev_ms], device=device, dtype=torch.float64)
     dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     dev_ms_max = float(tm[0])
@@ -665,7 +689,7 @@ def main_b200_partitioned(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
             "peak_device_bytes": lib.peak_bytes(),
         }
         print(json.dumps(line))
