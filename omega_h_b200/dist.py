@@ -134,13 +134,6 @@ class DevMesh:
         self._post()
         return out
 
-    def tag_into(self, ent_dim, name, out):
-        """copy a tag into a slice of a caller's buffer; the caller brackets a batch of these with
-        _pre() / _post()"""
-        assert out.is_contiguous()
-        self.lib.check(self.lib.c.oshb_mesh_get_tag(self.mesh.h, C.c_int(ent_dim), name.encode(),
-                                                    C.c_void_p(out.data_ptr()), C.c_int(0)))
-
     def set_tag(self, ent_dim, name, ncomps, t, internal=True):
         t = t.contiguous()
         assert t.numel() == self.mesh.nents(ent_dim) * ncomps, (name, t.numel(), self.mesh.nents(ent_dim), ncomps)
@@ -336,15 +329,8 @@ class FetchPlan:
         self.recv_idx, self.recv_counts = recv_idx, recv_counts
         self.group = group
 
-    def pull(self, values):
-        out = values[self.send_idx]
-        recv = torch.empty(sum(self.recv_counts), dtype=values.dtype, device=values.device)
-        dist.all_to_all_single(recv, out, list(self.recv_counts), list(self.send_counts), group=self.group)
-        values[self.recv_idx] = recv
-        return values
-
     def pull_pass_array(self, ps, which):
-        """the same for one of the pass's per-edge arrays, touching only the listed edges"""
+        """the owners' values of one of the pass's per-edge arrays, touching only the listed edges"""
         if not hasattr(self, "send32"):
             self.send32 = self.send_idx.to(torch.int32)
             self.recv32 = self.recv_idx.to(torch.int32)
