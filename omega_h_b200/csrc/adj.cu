@@ -8,8 +8,6 @@
 
 namespace oshb {
 
-OSHB_HD LO min_lo(LO a, LO b) { return (b < a) ? b : a; }
-OSHB_HD LO max_lo(LO a, LO b) { return (b < a) ? a : b; }
 
 // ---------------------------------------------------------------------------------------
 // device error cell
