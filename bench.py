@@ -693,6 +693,19 @@ def main_b200_partitioned(args):
             "peak_device_bytes": lib.peak_bytes(),
         }
         print(json.dumps(line))
+    if os.environ.get("OSHB_DIST_CPROFILE") and rank == 0:
+        # diagnosis only: where the host spends its time in the partitioned loop
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(3):
+            loop(part0.clone())
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(28)
+    elif os.environ.get("OSHB_DIST_CPROFILE"):
+        for _ in range(3):
+            loop(part0.clone())
     if D.TIMING is not None and rank == 0:
         # the library's own kernels during one partitioned loop (CUDA events on its stream)
         part = part0.clone()

@@ -547,18 +547,49 @@ void Pass::runs_begin(int me, int trust, GO const* koff, int64_t* nruns, int64_t
   n.pre = GOs(int64_t(ntot) + 1);
   scan_offsets(w.data(), ntot, n.pre.data());
   n.rid = offset_scan(n.start);
-  LO nr = last_of(n.rid), nw = 0;
-  n.run_pos = LOs(nr);
+  LOs wscan = offset_scan(wantm);
+  // the sizes of both lists and the counted totals per dimension in ONE read-back
+  LO nr = 0, nw = 0;
   {
-    // the run list from the scan already taken (collect_marked would scan the marks again)
-    I8 const* sp = n.start.data();
+    GOs cnts(6);
+    GO* cp = cnts.data();
+    GO const* pre = n.pre.data();
     LO const* rid = n.rid.data();
+    LO const* ws = wscan.data();
+    LO const l0 = n.lo[0], l1 = n.lo[1], l2 = n.lo[2], l3 = n.lo[3], l4 = n.lo[4];
+    int const dim_ = n.dim;
+    parallel_for(6, OSHB_LAMBDA(LO d) {
+      if (d == 4) {
+        cp[d] = rid[ntot];
+      } else if (d == 5) {
+        cp[d] = ws[ntot];
+      } else {
+        LO a = (d == 0) ? l0 : (d == 1 ? l1 : (d == 2 ? l2 : l3));
+        LO b = (d == 0) ? l1 : (d == 1 ? l2 : (d == 2 ? l3 : l4));
+        cp[d] = (d <= dim_) ? pre[b] - pre[a] : 0;
+      }
+    }, "numbering(totals)");
+    GO h[6];
+    d2h(h, cnts.data(), sizeof(h));
+    for (int d = 0; d < 4; ++d) new_counts[d] = h[d];
+    nr = LO(h[4]);
+    nw = LO(h[5]);
+  }
+  n.run_pos = LOs(nr);
+  n.want_pos = LOs(nw);
+  {
+    // both lists from the scans already taken
+    I8 const* sp = n.start.data();
+    I8 const* wm = wantm.data();
+    LO const* rid = n.rid.data();
+    LO const* ws = wscan.data();
     LO* rp = n.run_pos.data();
+    LO* wp = n.want_pos.data();
     parallel_for(ntot, OSHB_LAMBDA(LO i) {
       if (sp[i]) rp[rid[i]] = i;
-    }, "numbering(run list)");
+      if (wm[i]) wp[ws[i]] = i;
+    }, "numbering(lists)");
   }
-  n.want_pos = collect_marked(wantm, &nw);
   n.run_key = GOs(nr);
   n.run_delta = GOs(nr);  // holds the run sums until set_bases
   {
@@ -585,20 +616,6 @@ void Pass::runs_begin(int me, int trust, GO const* koff, int64_t* nruns, int64_t
       LO next = (r + 1 < nr) ? rp[r + 1] : ntot;
       rsum[r] = pre[next] - pre[pos];
     }, "numbering(runs)");
-  }
-  // counted new entities per dimension
-  {
-    GOs cnts(4);
-    GO* cp = cnts.data();
-    GO const* pre = n.pre.data();
-    LO const l0 = n.lo[0], l1 = n.lo[1], l2 = n.lo[2], l3 = n.lo[3], l4 = n.lo[4];
-    int const dim_ = n.dim;
-    parallel_for(4, OSHB_LAMBDA(LO d) {
-      LO a = (d == 0) ? l0 : (d == 1 ? l1 : (d == 2 ? l2 : l3));
-      LO b = (d == 0) ? l1 : (d == 1 ? l2 : (d == 2 ? l3 : l4));
-      cp[d] = (d <= dim_) ? pre[b] - pre[a] : 0;
-    }, "numbering(totals)");
-    d2h(new_counts, cnts.data(), 4 * sizeof(GO));
   }
   *nruns = nr;
   *nwant = nw;

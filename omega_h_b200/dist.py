@@ -402,13 +402,19 @@ class DistMesh:
         trust = self.halo - self.passes - 1   # deepest layer whose entities see their whole star
         ps = _Pass(dm, opts)
         try:
-            with _Section(dm, "candidates(lib)"):
-                ps.begin(2)
+            # candidates, cavity qualities and set states of what this rank sees; the qualities of
+            # its own edges (depth <= 0) are final, so ONE collective settles both "any candidate?"
+            # and "any good candidate?" for all ranks
+            with _Section(dm, "begin(lib)"):
+                ps.begin(1)
             with _Section(dm, "edge tags"):
                 edge_depth = _depth_of(dm.tag(EDGE, "own:part"))
                 mine = edge_depth <= 0
                 cand = ps.get(PASS_CANDIDATES)
-                any_cand = _any_rank((cand != 0) & mine, self.group)
+                state = ps.get(PASS_STATES)
+                flags = torch.stack([((cand != 0) & mine).any(), ((state == UNKNOWN) & mine).any()]).to(torch.int32)
+                dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
+                any_cand, any_good = (bool(x) for x in flags.tolist())
             if not any_cand:
                 return False
             if trust < 0:
@@ -417,8 +423,8 @@ class DistMesh:
                 with _Section(dm, "reghost"):
                     self.reghost()
                 return self.refine_by_size(opts)
-            with _Section(dm, "begin(lib)"):
-                ps.begin(1)
+            if not any_good:
+                return False
             with _Section(dm, "shell plan"):
                 # lookup table of the edges this rank answers for: counted here and inside the band
                 band = torch.nonzero(edge_depth < 0).flatten().to(torch.int32)
@@ -434,10 +440,6 @@ class DistMesh:
             with _Section(dm, "qualities exchange"):
                 plan.pull_pass_array(ps, PASS_QUALITIES)
                 ps.restate()
-                state = ps.get(PASS_STATES)
-                any_good = _any_rank((state == UNKNOWN) & mine, self.group)
-            if not any_good:
-                return False
             rounds = 0
             while True:
                 with _Section(dm, "indset round(lib)"):
