@@ -402,19 +402,15 @@ class DistMesh:
         trust = self.halo - self.passes - 1   # deepest layer whose entities see their whole star
         ps = _Pass(dm, opts)
         try:
-            # candidates, cavity qualities and set states of what this rank sees; the qualities of
-            # its own edges (depth <= 0) are final, so ONE collective settles both "any candidate?"
-            # and "any good candidate?" for all ranks
-            with _Section(dm, "begin(lib)"):
-                ps.begin(1)
+            # the cheap question first: is any edge of any rank still too long? (the last call of a
+            # loop ends here, before any cavity is evaluated)
+            with _Section(dm, "candidates(lib)"):
+                ps.begin(2)
             with _Section(dm, "edge tags"):
                 edge_depth = _depth_of(dm.tag(EDGE, "own:part"))
                 mine = edge_depth <= 0
                 cand = ps.get(PASS_CANDIDATES)
-                state = ps.get(PASS_STATES)
-                flags = torch.stack([((cand != 0) & mine).any(), ((state == UNKNOWN) & mine).any()]).to(torch.int32)
-                dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
-                any_cand, any_good = (bool(x) for x in flags.tolist())
+                any_cand = _any_rank((cand != 0) & mine, self.group)
             if not any_cand:
                 return False
             if trust < 0:
@@ -423,6 +419,11 @@ class DistMesh:
                 with _Section(dm, "reghost"):
                     self.reghost()
                 return self.refine_by_size(opts)
+            with _Section(dm, "begin(lib)"):
+                ps.begin(1)
+                # the qualities of this rank's own edges (depth <= 0) are final before any exchange
+                state = ps.get(PASS_STATES)
+                any_good = _any_rank((state == UNKNOWN) & mine, self.group)
             if not any_good:
                 return False
             with _Section(dm, "shell plan"):
