@@ -38,6 +38,7 @@ def test_partitioned_loop_matches_serial_gloo(emu_lib, nranks, n, halo, aniso, d
     (3, 6, 1, 0, 3),    # a 1-layer halo: a fresh halo before every pass but the first
     (2, 6, 2, 1, 3),    # anisotropic, 8 passes, 3 re-ghostings
     (2, 16, 1, 0, 2),   # triangles
+    (4, 8, 1, 0, 3),    # four ranks: neighbours of neighbours take part in the exchange
 ])
 def test_reghosting_gloo(emu_lib, nranks, n, halo, aniso, dim):
     """loops longer than the halo: DistMesh.reghost() must hand every rank a halo on which the
