@@ -72,7 +72,10 @@ class Mesh:
         """Shallow copy sharing the immutable arrays (Mesh copy-assignment)."""
         h = C.c_void_p()
         self.lib.check(self.lib.c.oshb_mesh_clone(self.h, C.byref(h)))
-        return Mesh(self.dim(), self.lib, h)
+        c = Mesh(self.dim(), self.lib, h)
+        if hasattr(self, "class_sets"):
+            c.class_sets = {k: list(v) for k, v in self.class_sets.items()}  # host metadata of .osh files
+        return c
 
     # ---- sizes -------------------------------------------------------------------------
     def dim(self):

@@ -12,11 +12,14 @@
 //   time   <dim> <n> <metric> [maxpasses]                              JSON timing line (CPU baseline)
 //   box    <dim> <n> <out>                                             build_box dump only
 //   adjtime <n>                                                        invert_adj / reflect_down timing
+//   writeosh <dim> <n> <metric> <npasses> <path.osh> <dump>            binary::write + dump of the same mesh
+//   readosh <path.osh> <dump>                                          binary::read + dump
 // metric: 0 iso h=1/(2n) | 1 tanh layer hx=hy | 2 tanh layer hy=0.7hx | 3 corner_test graded iso
 #include <Omega_h_adapt.hpp>
 #include <Omega_h_adj.hpp>
 #include <Omega_h_array_ops.hpp>
 #include <Omega_h_build.hpp>
+#include <Omega_h_file.hpp>
 #include <Omega_h_for.hpp>
 #include <Omega_h_indset.hpp>
 #include <Omega_h_map.hpp>
@@ -297,6 +300,38 @@ static int mode_adjtime(Library* lib, int, char** argv) {
   return 0;
 }
 
+// writeosh <dim> <n> <metric> <npasses> <path.osh> <dump>: box + metric, npasses refine passes, then
+// binary::write (src/Omega_h_file.cpp:518-540) of the mesh and an OSHD dump of the same mesh
+static int mode_writeosh(Library* lib, int, char** argv) {
+  int dim = atoi(argv[2]);
+  int n = atoi(argv[3]);
+  int kind = atoi(argv[4]);
+  int npasses = atoi(argv[5]);
+  auto mesh = make_box(lib, dim, n);
+  set_metric(&mesh, n, kind);
+  auto opts = AdaptOpts(&mesh);
+  opts.verbosity = SILENT;
+  mesh.ask_lengths();
+  mesh.ask_qualities();
+  for (int pass = 0; pass < npasses; ++pass) {
+    if (!refine_by_size(&mesh, opts)) break;
+  }
+  binary::write(argv[6], &mesh);
+  Dump d(argv[7]);
+  dump_mesh(d, "in:", &mesh);
+  return 0;
+}
+
+// readosh <path.osh> <dump>: binary::read (src/Omega_h_file.cpp:574-590) of a mesh somebody else
+// wrote, then an OSHD dump of what the reference understood
+static int mode_readosh(Library* lib, int, char** argv) {
+  Mesh mesh(lib);
+  binary::read(argv[2], lib->world(), &mesh);
+  Dump d(argv[3]);
+  dump_mesh(d, "in:", &mesh);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   auto lib = Library(&argc, &argv);
   if (argc < 2) {
@@ -308,6 +343,8 @@ int main(int argc, char** argv) {
   if (mode == "time") return mode_time(&lib, argc, argv);
   if (mode == "box") return mode_box(&lib, argc, argv);
   if (mode == "adjtime") return mode_adjtime(&lib, argc, argv);
+  if (mode == "writeosh") return mode_writeosh(&lib, argc, argv);
+  if (mode == "readosh") return mode_readosh(&lib, argc, argv);
   fprintf(stderr, "unknown mode %s\n", mode.c_str());
   return 1;
 }
