@@ -583,6 +583,69 @@ class DistMesh:
         self.passes = 0
         self.reghosts = getattr(self, "reghosts", 0) + 1
 
+    # ---- the whole mesh on one rank ----------------------------------------------------------------
+    def gather(self, root=0):
+        """Assemble the partitioned mesh on `root` as one mesh (None elsewhere): every entity is sent
+        once, by the rank that counts it, named by global number; since the numbers are dense and
+        the serial order IS the global order, position = number and the result equals the mesh the
+        serial loop produces, array by array. For writing results out (osh_file.write_osh) and for
+        checking; it needs the whole mesh to fit on one GPU."""
+        mesh, dm, dev = self.mesh, self.dm, self.device
+        dim, P, me = mesh.dim(), self.size, self.rank
+        nloc = [mesh.nents(d) for d in range(dim + 1)]
+        tagdefs = {d: [(name, nc) for name, _, nc in mesh.tags(d) if name != "global" and not name.startswith("own:")]
+                   for d in range(dim + 1)}
+        gid = [dm.tag(d, "global") for d in range(dim + 1)]
+        sizes = torch.empty(P * (dim + 1), dtype=torch.int64, device=dev)
+        idx = [torch.nonzero((dm.tag(d, "own:part") >> 8) == me).flatten() for d in range(dim + 1)]
+        dist.all_gather_into_tensor(sizes, torch.tensor([int(i.numel()) for i in idx], dtype=torch.int64, device=dev),
+                                    group=self.group)
+        sizes = sizes.view(P, dim + 1).tolist()
+        out = Mesh(dim, mesh.lib) if me == root else None
+        om = DevMesh(out, dev) if me == root else None
+
+        def collect(mine, width, dtype):
+            """concatenation over ranks of `mine` (width values per entity) on root"""
+            if me != root:
+                if mine.numel():
+                    dist.send(mine.contiguous(), root, group=self.group)
+                return None
+            parts = []
+            for r in range(P):
+                if r == me:
+                    parts.append(mine)
+                else:
+                    buf = torch.empty(int(sizes[r][d]) * width, dtype=dtype, device=dev)
+                    if buf.numel():
+                        dist.recv(buf, r, group=self.group)
+                    parts.append(buf)
+            return torch.cat(parts)
+
+        for d in range(dim + 1):
+            g = collect(gid[d][idx[d]], 1, torch.int64)
+            if me == root:
+                order = torch.argsort(g)
+                n = int(g.numel())
+                assert bool((g[order] == torch.arange(n, device=dev)).all().item()), "global numbers are not dense"
+                if d == 0:
+                    out.set_verts(n)
+            if d >= 1:
+                deg = simplex_degree(d, d - 1)
+                ab2b, codes = dm.down(d, d - 1)
+                dg = collect(gid[d - 1][ab2b.view(nloc[d], deg)[idx[d]].to(torch.int64)].flatten(), deg, torch.int64)
+                dc = collect(codes.view(nloc[d], deg)[idx[d]].flatten(), deg, torch.int8) if d >= 2 else None
+                if me == root:
+                    om.set_ents(d, dg.view(-1, deg)[order].flatten().to(torch.int32),
+                                dc.view(-1, deg)[order].flatten() if d >= 2 else None)
+            if me == root:
+                om.set_tag(d, "global", 1, g[order])
+            for name, nc in tagdefs[d]:
+                t = dm.tag(d, name)
+                v = collect(t.view(nloc[d], nc)[idx[d]].flatten(), nc, t.dtype)
+                if me == root:
+                    om.set_tag(d, name, nc, v.view(-1, nc)[order].flatten())
+        return out
+
     def _number_globally(self, ps, trust):
         """modify_globals (src/Omega_h_modify.cpp:406-444): exclusive scan, in global-number order, of
         how many new entities each old entity stands for -- all dimensions at once, on the key

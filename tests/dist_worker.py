@@ -86,6 +86,23 @@ def main():
     sv = serial.ask_verts_of(dim).reshape(-1, dim + 1)[gl[dim][own[dim]]]
     lv = gl[0][m.ask_verts_of(dim).reshape(-1, dim + 1)[own[dim]]]
     assert np.array_equal(sv, lv)
+    # ---- the gathered mesh equals the serial one, array by array
+    whole = part.gather(0)
+    if rank == 0:
+        for d in range(dim + 1):
+            assert whole.nents(d) == serial.nents(d)
+            names = sorted(t[0] for t in serial.tags(d))
+            assert names == sorted(t[0] for t in whole.tags(d)), (names, whole.tags(d))
+            for name in names:
+                assert np.array_equal(serial.get_array(d, name), whole.get_array(d, name)), (d, name)
+            if d >= 1:
+                a, ac = serial.ask_down(d, d - 1)
+                b, bc = whole.ask_down(d, d - 1)
+                assert np.array_equal(a, b), (d, "down")
+                if d >= 2:
+                    assert np.array_equal(ac, bc), (d, "codes")
+    else:
+        assert whole is None
     if rank == 0:
         print("DIST_OK passes=%d ranks=%d serial_elems=%d local_elems=%d owned=%d reghosts=%d" % (
             npass, P, serial.nelems(), m.nelems(), int(own[dim].sum()), getattr(part, "reghosts", 0)))
