@@ -60,3 +60,27 @@ def test_osh_after_our_refine_is_readable_by_reference(emu_lib, ref_driver, tmp_
             assert np.allclose(fx[k], fb[k], rtol=1e-12, atol=0), k
         else:
             assert np.array_equal(fx[k], fb[k]), k
+
+
+def test_partitioned_refine_of_a_file_equals_serial(emu_lib, ref_driver, tmp_path):
+    """examples/partitioned_refine.py on 2 ranks (gloo, emulation build): .osh in, .osh out, and the
+    output is byte-identical to what the serial loop writes"""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = str(tmp_path / "in.osh")
+    subprocess.run([ref_driver, "writeosh", "3", "6", "0", "0", src, str(tmp_path / "in.oshd")], check=True,
+                   stdout=subprocess.DEVNULL)
+    m = read_osh(src, emu_lib)
+    while refine_by_size(m):
+        pass
+    serial = str(tmp_path / "serial.osh")
+    write_osh(serial, m)
+    out = str(tmp_path / "out.osh")
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = "1"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29581",
+                        os.path.join(root, "examples", "partitioned_refine.py"), src, out, "2",
+                        "--emulation", emu_lib.path], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert filecmp.cmp(os.path.join(serial, "0.osh"), os.path.join(out, "0.osh"), shallow=False)
