@@ -97,6 +97,12 @@ int oshb_measure_edges_metric(int dim, int metric_ncomps, const int32_t* d_ev2v,
 int oshb_measure_qualities(int dim, int metric_ncomps, const int32_t* d_cv2v, const double* d_coords,
     const double* d_metrics, const int32_t* d_a2e, int32_t n, double* d_out);
 
+/* The libm the path computes with: out[i] = f(x[i]) for f = 0 cbrt, 1 log, 2 exp, 3 acos, 4 cos, evaluated
+ * by the device re-statements of glibc 2.39's functions (csrc/glibm.hpp) that the geometry kernels use
+ * in place of std::cbrt/log/exp/acos/cos (src/Omega_h_eigen.hpp:38-54,473-488, src/Omega_h_shape.hpp:112-117).
+ * Lets a caller check bit-equality with the host libm the reference links. */
+int oshb_libm_eval(int fn, const double* d_x, int64_t n, double* d_out);
+
 /* ---- mesh handle: the Omega_h::Mesh contract (src/Omega_h_mesh.hpp:36-177) ------------------ */
 typedef struct oshb_mesh oshb_mesh;
 enum { OSHB_I8 = 0, OSHB_I32 = 1, OSHB_I64 = 2, OSHB_F64 = 3 };

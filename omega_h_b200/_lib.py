@@ -50,7 +50,7 @@ SYMBOLS = [
     "oshb_offset_scan_i8", "oshb_offset_scan_i32", "oshb_offset_scan_i32_i64", "oshb_collect_marked",
     "oshb_max_i8", "oshb_minmax_f64", "oshb_sort_by_keys_i32", "oshb_sort_by_keys_i64",
     "oshb_invert_adj", "oshb_transit", "oshb_reflect_down", "oshb_find_unique",
-    "oshb_measure_edges_metric", "oshb_measure_qualities",
+    "oshb_measure_edges_metric", "oshb_measure_qualities", "oshb_libm_eval",
     "oshb_mesh_create", "oshb_mesh_destroy", "oshb_mesh_clone", "oshb_mesh_dim", "oshb_mesh_nents",
     "oshb_mesh_set_verts", "oshb_mesh_set_ents", "oshb_mesh_add_tag", "oshb_mesh_remove_tag", "oshb_mesh_ntags",
     "oshb_mesh_tag_info", "oshb_mesh_get_tag", "oshb_mesh_gather_tag", "oshb_mesh_ask_down", "oshb_mesh_ask_up", "oshb_mesh_ask_star",

@@ -18,7 +18,7 @@ struct oshb_mesh {
 #define OSHB_CATCH                                  \
   }                                                 \
   catch (std::exception const& e) {                 \
-    if (oshb::last_error_string().empty()) oshb::last_error_string() = e.what(); \
+    oshb::last_error_string() = e.what();           \
     return 1;                                       \
   }                                                 \
   return 0;
@@ -252,6 +252,13 @@ int oshb_measure_edges_metric(int dim, int metric_ncomps, const int32_t* d_ev2v,
   Reals r = measure_edges_metric_raw(dim, LOs::view(d_ev2v, 1), Reals::view(d_coords, 1), Reals::view(d_metrics, 1),
       metric_ncomps, a2e, n);
   d2d(d_out, r.data(), size_t(n) * sizeof(Real));
+  sync_stream();
+  OSHB_CATCH
+}
+int oshb_libm_eval(int fn, const double* d_x, int64_t n, double* d_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  libm_eval(fn, d_x, n, d_out);
   sync_stream();
   OSHB_CATCH
 }

@@ -58,6 +58,23 @@ void measure_edges_metric_marked(Mesh* mesh, Bytes marks, Reals metrics, Reals i
   else fail(__FILE__, __LINE__, "measure_edges_metric: unsupported (dim, metric ncomps)");
 }
 
+// the five transcendental functions of the path, elementwise (oshb_libm_eval)
+void libm_eval(int fn, Real const* x, int64_t n, Real* out) {
+  OSHB_CHECK(fn >= 0 && fn <= 4);
+  parallel_for(n, OSHB_LAMBDA(LO i) {
+    Real v = x[i];
+    Real r;
+    switch (fn) {
+      case 0: r = glibm::cbrt(v); break;
+      case 1: r = glibm::log(v); break;
+      case 2: r = glibm::exp(v); break;
+      case 3: r = glibm::acos(v); break;
+      default: r = glibm::cos(v); break;
+    }
+    out[i] = r;
+  }, "libm_eval");
+}
+
 Reals measure_edges_metric(Mesh* mesh, LOs a2e, Reals metrics) {
   LO n = a2e.exists() ? LO(a2e.size()) : mesh->nedges();
   int ncomps = int(metrics.size() / mesh->nverts());

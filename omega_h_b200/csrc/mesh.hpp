@@ -140,6 +140,7 @@ LOs offset_scan(LOs a);
 LO last_of(LOs a);
 
 // ---- geometry / metric kernels (geom.cu) ------------------------------------------------
+void libm_eval(int fn, Real const* x, int64_t n, Real* out);  // glibm.hpp functions elementwise (parity check entry)
 Reals measure_edges_metric(Mesh* mesh, LOs a2e, Reals metrics);     // src/Omega_h_shape.cpp:7-37 (a2e may be absent = all)
 Reals measure_edges_metric_raw(int dim, LOs ev2v, Reals coords, Reals metrics, int metric_ncomps, LOs a2e, LO n);
 Reals measure_qualities(Mesh* mesh, LOs a2e, Reals metrics);        // src/Omega_h_quality.cpp:7-52

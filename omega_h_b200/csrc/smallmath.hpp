@@ -6,11 +6,13 @@
 // (src/Omega_h_vector.hpp, src/Omega_h_matrix.hpp, src/Omega_h_eigen.hpp,
 //  src/Omega_h_metric.hpp, src/Omega_h_shape.hpp, src/Omega_h_quality.hpp); the library is
 // compiled with --fmad=false so no multiply-add is contracted (the oracle of record is the
-// reference built with -ffp-contract=off).
+// reference built with -ffp-contract=off), and cbrt/log/exp/acos/cos are
+// the bit-exact glibc re-statements of glibm.hpp, not CUDA libdevice.
 #pragma once
 #include <cmath>
 
 #include "rt.hpp"
+#include "glibm.hpp"
 
 namespace oshb {
 
@@ -275,8 +277,8 @@ OSHB_HD Roots3 find_cubic_roots(Real a_0, Real a_1, Real a_2, Real eps) {
   Real D = cube(Q) + square(R);
   Real shift = -a_2 / 3.;
   if (D >= 0.0) {
-    Real S = cbrt(R + sqrt(D));
-    Real T = cbrt(R - sqrt(D));
+    Real S = glibm::cbrt(R + sqrt(D));
+    Real T = glibm::cbrt(R - sqrt(D));
     Real B = S + T;
     Real z_1 = shift + B;
     Real z_23_real = shift - (1. / 2.) * B;
@@ -284,11 +286,11 @@ OSHB_HD Roots3 find_cubic_roots(Real a_0, Real a_1, Real a_2, Real eps) {
     r.values[1] = r.values[2] = z_23_real;
   } else {
     Real cos_theta = R / sqrt(-cube(Q));
-    Real theta = acos(clamp(cos_theta, -1.0, 1.0));
+    Real theta = glibm::acos(clamp(cos_theta, -1.0, 1.0));
     Real radius = 2. * sqrt(-Q);
-    Real z_1 = radius * cos((theta) / 3.) + shift;
-    Real z_2 = radius * cos((theta + 2. * OSHB_PI) / 3.) + shift;
-    Real z_3 = radius * cos((theta - 2. * OSHB_PI) / 3.) + shift;
+    Real z_1 = radius * glibm::cos((theta) / 3.) + shift;
+    Real z_2 = radius * glibm::cos((theta + 2. * OSHB_PI) / 3.) + shift;
+    Real z_3 = radius * glibm::cos((theta - 2. * OSHB_PI) / 3.) + shift;
     r.values[0] = z_1;
     r.values[1] = z_2;
     r.values[2] = z_3;
@@ -471,13 +473,13 @@ OSHB_HD Mat<N> compose_ortho(Mat<N> q, Vec<N> l) {
 template <int N>
 OSHB_HD Mat<N> log_spd(Mat<N> m, bool* ok) {
   DiagDecomp<N> d = decompose_eigen(m, ok);
-  for (int i = 0; i < N; ++i) d.l[i] = log(d.l[i]);
+  for (int i = 0; i < N; ++i) d.l[i] = glibm::log(d.l[i]);
   return compose_ortho(d.q, d.l);
 }
 template <int N>
 OSHB_HD Mat<N> exp_spd(Mat<N> m, bool* ok) {
   DiagDecomp<N> d = decompose_eigen(m, ok);
-  for (int i = 0; i < N; ++i) d.l[i] = exp(d.l[i]);
+  for (int i = 0; i < N; ++i) d.l[i] = glibm::exp(d.l[i]);
   return compose_ortho(d.q, d.l);
 }
 
@@ -507,7 +509,7 @@ OSHB_HD Real metric_product(Mat<1> m, Vec<1> v) { return dot(v, m * v); }
 
 OSHB_HD Real anisotropic_edge_length(Real l_a, Real l_b) {
   if (fabs(l_a - l_b) > 1e-3) {
-    return (l_a - l_b) / (log(l_a / l_b));
+    return (l_a - l_b) / (glibm::log(l_a / l_b));
   }
   return (l_a + l_b) / 2.;
 }
@@ -566,7 +568,7 @@ OSHB_HD Real metric_element_quality(Vec<dim> const* p, Mat<mdim> metric) {
   msl = msl / ne;
   Real x = s / ((dim == 3) ? 0.1178511301977579 : 0.4330127018922193);
   if constexpr (dim == 3) {
-    return cbrt(x * (x * 1.0)) / msl;
+    return glibm::cbrt(x * (x * 1.0)) / msl;
   } else {
     return x / msl;
   }
