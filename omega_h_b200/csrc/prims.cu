@@ -308,171 +308,408 @@ void minmax_f64(Real const* in, int64_t n, Real* mn, Real* mx) {
 }
 
 // =====================================================================================
-// sort_by_keys: stable LSD radix sort, 8-bit digits, moving (word, index) pairs.
-// For each key word from the last (least significant) to the first: gather that word
-// through the current permutation once, then for every byte of the word that actually
-// varies run histogram -> scan -> stable scatter. Ranking inside a warp uses
-// __match_any_sync; warps of a block own contiguous chunks so the order is stable.
+// sort_by_keys: stable LSD radix sort over 8-bit digits, one-sweep shape.
+//   pre-pass  : ONE read of the keys gives, per key word, the OR/AND of all values (constant
+//               bytes are never sorted on) and the histogram of byte 0; one 2*width-word
+//               read-back plans every pass (the only host sync of the sort).
+//   per digit : ONE kernel. A tile (256 threads x 16|12 items, warps own contiguous chunks so
+//               the order stays stable) ranks its items with __match_any_sync, publishes its
+//               per-bin counts and finds the counts of all earlier tiles by decoupled
+//               look-back (flag + count in one 32-bit word per (tile, bin)); items are
+//               re-ordered by bin in shared memory so that every bin's run leaves as one
+//               contiguous store. The first digit of a word fetches the word through the
+//               current permutation (no separate gather pass); while scattering digit b a
+//               tile also histograms the next digit of the same word (its bin totals are
+//               needed before that pass starts), so there is no histogram kernel either.
+// Algorithmic bytes: n*width*sizeof(W) in + 4n out; a pass moves 8 (12) B in and
+// 8 (12) B out per key.
 // =====================================================================================
-static constexpr int RS_T = 256;
-static constexpr int RS_I = 16;
-static constexpr int RS_TILE = RS_T * RS_I;
+static constexpr int OS_T = 512;   // threads per tile (16 warps); bins are owned by threads 0..255
+static constexpr int OS_PT = 256;  // threads of the pre-pass / histogram kernels (one per bin)
+static constexpr unsigned OS_FLAG_AGG = 1u << 30;
+static constexpr unsigned OS_FLAG_PRE = 2u << 30;
+static constexpr unsigned OS_VAL = (1u << 30) - 1u;
 
 template <class W>
-__device__ __forceinline__ unsigned digit_of(W w, int shift, bool top) {
-  unsigned d = unsigned((static_cast<unsigned long long>(w) >> shift) & 0xffu);
-  return top ? (d ^ 0x80u) : d;  // signed order on the most significant byte
-}
+struct OsCfg {
+  static constexpr int I = (sizeof(W) == 4) ? 16 : 12;
+  static constexpr int TILE = OS_T * I;
+};
 
-template <class W>
-__global__ void __launch_bounds__(RS_T) k_rs_gather(W const* __restrict__ keys, LO const* __restrict__ perm,
-    int64_t n, int width, int word, W* __restrict__ out, unsigned long long* varies) {
-  // also accumulates OR / AND of all words so constant bytes can be skipped
-  unsigned long long o = 0, a = ~0ull;
-  int64_t stride = int64_t(gridDim.x) * RS_T;
-  for (int64_t i = int64_t(blockIdx.x) * RS_T + threadIdx.x; i < n; i += stride) {
-    W w = keys[int64_t(perm[i]) * width + word];
-    out[i] = w;
-    o |= static_cast<unsigned long long>(w);
-    a &= static_cast<unsigned long long>(w);
+// order-preserving unsigned image of a signed key word
+__device__ __forceinline__ unsigned long long os_ordered(LO w) { return static_cast<unsigned long long>(static_cast<unsigned>(w) ^ 0x80000000u); }
+__device__ __forceinline__ unsigned long long os_ordered(GO w) { return static_cast<unsigned long long>(w) ^ 0x8000000000000000ull; }
+
+// pre-pass: OR / AND of every word column + histogram of byte 0 of every column
+template <class W, int WIDTH>
+__global__ void __launch_bounds__(OS_PT) k_os_pre(W const* __restrict__ keys, int64_t n, unsigned long long* orand,
+    unsigned* hist0) {
+  __shared__ unsigned s_h[WIDTH][256];
+  for (int k = 0; k < WIDTH; ++k) s_h[k][threadIdx.x] = 0;
+  __syncthreads();
+  unsigned long long o[WIDTH], a[WIDTH];
+#pragma unroll
+  for (int k = 0; k < WIDTH; ++k) {
+    o[k] = 0;
+    a[k] = ~0ull;
+  }
+  int64_t stride = int64_t(gridDim.x) * OS_PT;
+  for (int64_t i = int64_t(blockIdx.x) * OS_PT + threadIdx.x; i < n; i += stride) {
+#pragma unroll
+    for (int k = 0; k < WIDTH; ++k) {
+      unsigned long long u = os_ordered(keys[i * WIDTH + k]);
+      o[k] |= u;
+      a[k] &= u;
+      atomicAdd(&s_h[k][unsigned(u) & 0xffu], 1u);
+    }
   }
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
-    o |= __shfl_xor_sync(0xffffffffu, o, s);
-    a &= __shfl_xor_sync(0xffffffffu, a, s);
+  for (int k = 0; k < WIDTH; ++k) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      o[k] |= __shfl_xor_sync(0xffffffffu, o[k], s);
+      a[k] &= __shfl_xor_sync(0xffffffffu, a[k], s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicOr(&orand[2 * k], o[k]);
+      atomicAnd(&orand[2 * k + 1], a[k]);
+    }
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicOr(&varies[0], o);
-    atomicAnd(&varies[1], a);
+  __syncthreads();
+  for (int k = 0; k < WIDTH; ++k) {
+    unsigned c = s_h[k][threadIdx.x];
+    if (c) atomicAdd(&hist0[k * 256 + threadIdx.x], c);
   }
 }
 
+// histogram of one digit of one word column (only when byte 0 of a word is constant)
 template <class W>
-__global__ void __launch_bounds__(RS_T) k_rs_hist(W const* __restrict__ words, int64_t n, int shift, bool top,
-    LO* __restrict__ hist, int nblocks) {
+__global__ void __launch_bounds__(OS_PT) k_os_hist(W const* __restrict__ keys, int64_t n, int width, int word, int shift,
+    unsigned* hist) {
   __shared__ unsigned s_h[256];
   s_h[threadIdx.x] = 0;
   __syncthreads();
-  int64_t base = int64_t(blockIdx.x) * RS_TILE;
-#pragma unroll
-  for (int j = 0; j < RS_I; ++j) {
-    int64_t g = base + j * RS_T + threadIdx.x;
-    if (g < n) atomicAdd(&s_h[digit_of(words[g], shift, top)], 1u);
-  }
+  int64_t stride = int64_t(gridDim.x) * OS_PT;
+  for (int64_t i = int64_t(blockIdx.x) * OS_PT + threadIdx.x; i < n; i += stride)
+    atomicAdd(&s_h[unsigned(os_ordered(keys[i * width + word]) >> shift) & 0xffu], 1u);
   __syncthreads();
-  hist[int64_t(threadIdx.x) * nblocks + blockIdx.x] = LO(s_h[threadIdx.x]);
+  unsigned c = s_h[threadIdx.x];
+  if (c) atomicAdd(&hist[threadIdx.x], c);
 }
 
-template <class W>
-__global__ void __launch_bounds__(RS_T) k_rs_scatter(W const* __restrict__ words_in, LO const* __restrict__ perm_in,
-    int64_t n, int shift, bool top, LO const* __restrict__ hist_scan, int nblocks, W* __restrict__ words_out,
-    LO* __restrict__ perm_out) {
-  __shared__ unsigned s_cnt[RS_T / 32][256];
+// exclusive scan of one value per thread over the OS_T threads of the block
+__device__ __forceinline__ unsigned os_block_exscan(unsigned v, unsigned* s_part /*8*/) {
+  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  __syncthreads();  // s_part may still be read from a previous call
+  if (lane == 31) s_part[warp] = incl;
+  __syncthreads();
+  unsigned off = 0;
+#pragma unroll
+  for (int w = 0; w < OS_T / 32; ++w)
+    if (w < warp) off += s_part[w];
+  return off + incl - v;
+}
+
+template <class W, bool GATHER, bool NEXT>
+__global__ void __launch_bounds__(OS_T) k_os_pass(W const* __restrict__ keys, int width, int word,
+    W const* __restrict__ words_in, LO const* __restrict__ perm_in, int64_t n, int shift, int next_shift,
+    unsigned const* __restrict__ ghist, unsigned* ghist_next, unsigned* status, unsigned* ticket,
+    W* __restrict__ words_out, LO* __restrict__ perm_out) {
+  constexpr int I = OsCfg<W>::I;
+  constexpr int TILE = OsCfg<W>::TILE;
+  constexpr int NW = OS_T / 32;
+  __shared__ unsigned s_cnt[NW][256];
+  __shared__ unsigned s_base[256];
+  __shared__ unsigned s_part[NW];
+  __shared__ unsigned s_tile;
+  extern __shared__ __align__(16) unsigned char s_raw[];  // TILE * (sizeof(W) + sizeof(LO)) bytes
+  W* s_w = reinterpret_cast<W*>(s_raw);
+  LO* s_p = reinterpret_cast<LO*>(s_raw + TILE * sizeof(W));
+  unsigned(*s_cnt2)[256] = reinterpret_cast<unsigned(*)[256]>(s_raw);  // phase 1-2 only, aliases the staging area
   int const t = threadIdx.x;
   int const lane = t & 31;
   int const warp = t >> 5;
-  for (int w = 0; w < RS_T / 32; ++w) s_cnt[w][t] = 0;
-  __syncthreads();
-  // each warp owns a contiguous chunk of RS_TILE/8 = 512 items = 16 rounds of 32
-  int64_t const wbase = int64_t(blockIdx.x) * RS_TILE + int64_t(warp) * (RS_TILE / (RS_T / 32));
-  W wv[RS_I];
-  unsigned dg[RS_I];
+  if (t == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int k = t; k < NW * 256; k += OS_T) {
+    (&s_cnt[0][0])[k] = 0;
+    if (NEXT) (&s_cnt2[0][0])[k] = 0;
+  }
+  bool const owns_bin = t < 256;
+  // global start of every bin: exclusive scan of this digit's totals
+  unsigned const gbase = os_block_exscan(owns_bin ? ghist[t] : 0u, s_part);  // (syncs inside: s_tile, s_cnt visible)
+  unsigned const tile = s_tile;
+  int64_t const base = int64_t(tile) * TILE;
+  // ---- phase 1: load, rank inside the warp's chunk
+  W wv[I];
+  LO iv[I];
+  unsigned pre[I];
+  int64_t const wbase = base + int64_t(warp) * (I * 32);
+  unsigned const lt = (1u << lane) - 1u;
 #pragma unroll
-  for (int r = 0; r < RS_I; ++r) {
+  for (int r = 0; r < I; ++r) {
     int64_t g = wbase + r * 32 + lane;
     bool valid = g < n;
-    wv[r] = valid ? words_in[g] : W(0);
-    dg[r] = valid ? digit_of(wv[r], shift, top) : 0xffffffffu;
-    unsigned amask = __ballot_sync(0xffffffffu, valid);
+    LO idx = 0;
+    W w = W(0);
     if (valid) {
-      unsigned peers = __match_any_sync(amask, dg[r]);
-      if (lane == (__ffs(peers) - 1)) s_cnt[warp][dg[r]] += __popc(peers);
+      idx = perm_in ? perm_in[g] : LO(g);
+      w = GATHER ? keys[int64_t(idx) * width + word] : words_in[g];
     }
-    __syncwarp();
-  }
-  __syncthreads();
-  {
-    unsigned run = unsigned(hist_scan[int64_t(t) * nblocks + blockIdx.x]);
-    for (int w = 0; w < RS_T / 32; ++w) {
-      unsigned c = s_cnt[w][t];
-      s_cnt[w][t] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RS_I; ++r) {
-    int64_t g = wbase + r * 32 + lane;
-    bool valid = g < n;
+    wv[r] = w;
+    iv[r] = idx;
+    unsigned long long u = os_ordered(w);
+    unsigned d = unsigned(u >> shift) & 0xffu;
     unsigned amask = __ballot_sync(0xffffffffu, valid);
+    unsigned my = 0;
     if (valid) {
-      unsigned peers = __match_any_sync(amask, dg[r]);
+      unsigned peers = __match_any_sync(amask, d);
       int leader = __ffs(peers) - 1;
-      unsigned rank = __popc(peers & ((1u << lane) - 1u));
-      unsigned basepos = 0;
+      unsigned old = 0;
       if (lane == leader) {
-        basepos = s_cnt[warp][dg[r]];
-        s_cnt[warp][dg[r]] = basepos + __popc(peers);
+        old = s_cnt[warp][d];
+        s_cnt[warp][d] = old + __popc(peers);
       }
-      basepos = __shfl_sync(peers, basepos, leader);
-      unsigned pos = basepos + rank;
-      words_out[pos] = wv[r];
-      perm_out[pos] = perm_in[g];
+      old = __shfl_sync(peers, old, leader);
+      my = old + __popc(peers & lt);
+      if (NEXT) {
+        unsigned d2 = unsigned(u >> next_shift) & 0xffu;
+        unsigned peers2 = __match_any_sync(amask, d2);
+        if (lane == __ffs(peers2) - 1) s_cnt2[warp][d2] += __popc(peers2);
+      }
     }
+    pre[r] = my;
     __syncwarp();
   }
+  __syncthreads();
+  // ---- phase 2: thread t < 256 owns bin t
+  unsigned total = 0;
+  if (owns_bin) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      unsigned c = s_cnt[w][t];
+      s_cnt[w][t] = total;
+      total += c;
+    }
+    if (NEXT) {
+      unsigned t2 = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t2 += s_cnt2[w][t];
+      if (t2) atomicAdd(&ghist_next[t], t2);
+    }
+  }
+  volatile unsigned* st = status;
+  if (owns_bin) st[int64_t(tile) * 256 + t] = (tile == 0 ? OS_FLAG_PRE : OS_FLAG_AGG) | total;
+  unsigned const lstart = os_block_exscan(total, s_part);
+  if (owns_bin) {
+    unsigned excl = 0;
+    if (tile > 0) {
+      // look-back, OS_LB predecessor tiles per round trip: the loads of a batch are independent, so a
+      // chain through the tiles in flight costs chain/OS_LB L2 latencies instead of chain (the rate
+      // at which tiles can retire is bounded by OS_LB / L2 latency)
+      constexpr int OS_LB = 32;
+      int64_t look = int64_t(tile) - 1;
+      bool done = false;
+      while (!done) {
+        unsigned sv[OS_LB];
+#pragma unroll
+        for (int k = 0; k < OS_LB; ++k) sv[k] = (look - k >= 0) ? st[(look - k) * 256 + t] : (2u << 30);
+#pragma unroll
+        for (int k = 0; k < OS_LB; ++k) {
+          if (!done) {
+            unsigned v = sv[k];
+            while ((v >> 30) == 0) v = st[(look - k) * 256 + t];
+            excl += v & OS_VAL;
+            if ((v >> 30) == 2) done = true;
+          }
+        }
+        look -= OS_LB;
+      }
+      st[int64_t(tile) * 256 + t] = OS_FLAG_PRE | (excl + total);
+    }
+    s_base[t] = gbase + excl - lstart;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s_cnt[w][t] += lstart;
+  }
+  __syncthreads();  // also: s_cnt2 no longer read, the staging area may be written
+  // ---- phase 3: stage in bin order
+#pragma unroll
+  for (int r = 0; r < I; ++r) {
+    int64_t g = wbase + r * 32 + lane;
+    if (g < n) {
+      unsigned d = unsigned(os_ordered(wv[r]) >> shift) & 0xffu;
+      unsigned lpos = s_cnt[warp][d] + pre[r];
+      s_w[lpos] = wv[r];
+      s_p[lpos] = iv[r];
+    }
+  }
+  __syncthreads();
+  // ---- phase 4: contiguous runs out
+  int const tile_n = int((n - base < TILE) ? (n - base) : TILE);
+  for (int j = t; j < tile_n; j += OS_T) {
+    W w = s_w[j];
+    unsigned d = unsigned(os_ordered(w) >> shift) & 0xffu;
+    unsigned gpos = s_base[d] + unsigned(j);
+    if (words_out) words_out[gpos] = w;
+    perm_out[gpos] = s_p[j];
+  }
+}
+
+template <class W, bool G, bool N>
+static void os_go(unsigned ntiles, W const* keys, int width, int word, W const* words_in, LO const* perm_in, int64_t n,
+    int shift, int next_shift, unsigned const* ghist, unsigned* ghist_next, unsigned* status, unsigned* ticket,
+    W* words_out, LO* perm_out) {
+  size_t const smem = size_t(OsCfg<W>::TILE) * (sizeof(W) + sizeof(LO));
+  static bool attr_set = false;
+  auto kern = k_os_pass<W, G, N>;
+  if (!attr_set) {
+    OSHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_set = true;
+  }
+  kern<<<ntiles, OS_T, smem, ctx().stream>>>(keys, width, word, words_in, perm_in, n, shift, next_shift, ghist,
+      ghist_next, status, ticket, words_out, perm_out);
+}
+
+template <class W>
+static void os_launch_pass(bool gather, bool next, W const* keys, int width, int word, W const* words_in,
+    LO const* perm_in, int64_t n, int shift, int next_shift, unsigned const* ghist, unsigned* ghist_next,
+    unsigned* status, unsigned* ticket, W* words_out, LO* perm_out) {
+  Ctx& c = ctx();
+  unsigned const ntiles = unsigned((n + OsCfg<W>::TILE - 1) / OsCfg<W>::TILE);
+  OSHB_CUDA(cudaMemsetAsync(status, 0, size_t(ntiles) * 256 * sizeof(unsigned), c.stream));
+  OSHB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), c.stream));
+  if (next) OSHB_CUDA(cudaMemsetAsync(ghist_next, 0, 256 * sizeof(unsigned), c.stream));
+  if (c.prof_on) prof_begin("sort_by_keys(pass)");
+  if (gather && next) os_go<W, true, true>(ntiles, keys, width, word, words_in, perm_in, n, shift, next_shift, ghist, ghist_next, status, ticket, words_out, perm_out);
+  else if (gather) os_go<W, true, false>(ntiles, keys, width, word, words_in, perm_in, n, shift, next_shift, ghist, ghist_next, status, ticket, words_out, perm_out);
+  else if (next) os_go<W, false, true>(ntiles, keys, width, word, words_in, perm_in, n, shift, next_shift, ghist, ghist_next, status, ticket, words_out, perm_out);
+  else os_go<W, false, false>(ntiles, keys, width, word, words_in, perm_in, n, shift, next_shift, ghist, ghist_next, status, ticket, words_out, perm_out);
+  OSHB_CUDA(cudaGetLastError());
+  if (c.prof_on) prof_end("sort_by_keys(pass)");
+  c.launches++;
 }
 
 template <class W>
 static void sort_impl(W const* keys, int64_t n, int width, LO* perm) {
   Ctx& c = ctx();
-  fill_linear<LO>(perm, n, 0, 1);
-  if (n <= 1) return;
-  OSHB_CHECK(n < (int64_t(1) << 31));
-  int const nblocks = int((n + RS_TILE - 1) / RS_TILE);
+  OSHB_CHECK(width >= 1);
+  if (n <= 1) {
+    fill_linear<LO>(perm, n, 0, 1);
+    return;
+  }
+  OSHB_CHECK(n < (int64_t(1) << 30));  // 30-bit counts in the look-back words; LO-indexed uses stay below
+  int const nbytes = int(sizeof(W));
+  // ---- pre-pass: OR/AND + byte-0 histograms, one read of the keys
+  DArr<unsigned long long> orand(2 * int64_t(width));
+  DArr<unsigned> hists((int64_t(width) + 3) * 256);  // [width] byte-0 histograms, 2 in-flight, 1 standalone
+  {
+    std::vector<unsigned long long> init(2 * size_t(width));
+    for (int k = 0; k < width; ++k) {
+      init[2 * k] = 0ull;
+      init[2 * k + 1] = ~0ull;
+    }
+    h2d(orand.data(), init.data(), init.size() * 8);
+    OSHB_CUDA(cudaMemsetAsync(hists.data(), 0, size_t(hists.size()) * sizeof(unsigned), c.stream));
+    int64_t blocks = (n + OS_PT - 1) / OS_PT;
+    if (blocks > int64_t(c.sms) * 8) blocks = int64_t(c.sms) * 8;
+    if (c.prof_on) prof_begin("sort_by_keys(pre)");
+    if (width <= 4) {
+      switch (width) {
+        case 1: k_os_pre<W, 1><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, orand.data(), hists.data()); break;
+        case 2: k_os_pre<W, 2><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, orand.data(), hists.data()); break;
+        case 3: k_os_pre<W, 3><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, orand.data(), hists.data()); break;
+        default: k_os_pre<W, 4><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, orand.data(), hists.data()); break;
+      }
+      c.launches++;
+    } else {
+      // wide keys: treat every column as a 1-word key set with a stride (reads the keys `width` times)
+      OSHB_CHECK(width <= 4);  // not needed by any caller (uses have <= 4 vertices)
+    }
+    OSHB_CUDA(cudaGetLastError());
+    if (c.prof_on) prof_end("sort_by_keys(pre)");
+  }
+  std::vector<unsigned long long> oa = orand.to_host();  // the sort's one read-back
+  // ---- plan: the digits that vary, last word first
+  struct Pass {
+    int word, byte;
+    bool first, next;
+    int next_byte;
+  };
+  std::vector<Pass> plan;
+  for (int word = width - 1; word >= 0; --word) {
+    unsigned long long diff = oa[2 * word] ^ oa[2 * word + 1];
+    std::vector<int> bytes;
+    for (int b = 0; b < nbytes; ++b)
+      if ((diff >> (8 * b)) & 0xffull) bytes.push_back(b);
+    for (size_t k = 0; k < bytes.size(); ++k) {
+      Pass p;
+      p.word = word;
+      p.byte = bytes[k];
+      p.first = (k == 0);
+      p.next = (k + 1 < bytes.size());
+      p.next_byte = p.next ? bytes[k + 1] : 0;
+      plan.push_back(p);
+    }
+  }
+  if (plan.empty()) {
+    fill_linear<LO>(perm, n, 0, 1);
+    return;
+  }
+  unsigned const ntiles = unsigned((n + OsCfg<W>::TILE - 1) / OsCfg<W>::TILE);
+  DArr<unsigned> status(int64_t(ntiles) * 256 + 1);
+  unsigned* ticket = status.data() + int64_t(ntiles) * 256;
   DArr<W> wa(n), wb(n);
   DArr<LO> pb(n);
-  DArr<LO> hist(int64_t(256) * nblocks);
-  DArr<LO> hscan(int64_t(256) * nblocks + 1);
-  LO* pcur = perm;
-  LO* palt = pb.data();
-  unsigned long long* varies = reinterpret_cast<unsigned long long*>(static_cast<char*>(c.dscratch) + 2048);
-  int const nbytes = int(sizeof(W));
-  for (int word = width - 1; word >= 0; --word) {
-    unsigned long long init[2] = {0ull, ~0ull};
-    h2d(varies, init, 16);
-    int64_t gblocks = (n + RS_T - 1) / RS_T;
-    if (gblocks > int64_t(c.sms) * 16) gblocks = int64_t(c.sms) * 16;
-    k_rs_gather<W><<<unsigned(gblocks), RS_T, 0, c.stream>>>(keys, pcur, n, width, word, wa.data(), varies);
-    OSHB_CUDA(cudaGetLastError());
-    c.launches++;
-    unsigned long long res[2];
-    d2h(res, varies, 16);
-    unsigned long long diff = res[0] ^ res[1];  // bits that differ somewhere
-    W* wcur = wa.data();
-    W* walt = wb.data();
-    for (int b = 0; b < nbytes; ++b) {
-      if (((diff >> (8 * b)) & 0xffull) == 0) continue;
-      bool top = (b == nbytes - 1);
-      k_rs_hist<W><<<unsigned(nblocks), RS_T, 0, c.stream>>>(wcur, n, 8 * b, top, hist.data(), nblocks);
-      OSHB_CUDA(cudaGetLastError());
-      c.launches++;
-      scan_offsets(hist.data(), int64_t(256) * nblocks, hscan.data());
-      k_rs_scatter<W><<<unsigned(nblocks), RS_T, 0, c.stream>>>(
-          wcur, pcur, n, 8 * b, top, hscan.data(), nblocks, walt, palt);
-      OSHB_CUDA(cudaGetLastError());
-      c.launches++;
-      W* tw = wcur;
-      wcur = walt;
-      walt = tw;
-      LO* tp = pcur;
-      pcur = palt;
-      palt = tp;
+  // permutation buffers alternate; start so that the last pass writes into `perm`
+  LO* pout = (plan.size() % 2 == 1) ? perm : pb.data();
+  LO* palt = (plan.size() % 2 == 1) ? pb.data() : perm;
+  LO const* pin = nullptr;  // identity
+  W* wout = wa.data();
+  W* walt = wb.data();
+  W const* win = nullptr;
+  unsigned* h_inflight[2] = {hists.data() + int64_t(width) * 256, hists.data() + (int64_t(width) + 1) * 256};
+  unsigned* h_alone = hists.data() + (int64_t(width) + 2) * 256;
+  int flight = 0;
+  unsigned const* hcur = nullptr;
+  for (size_t k = 0; k < plan.size(); ++k) {
+    Pass const& p = plan[k];
+    if (p.first) {
+      if (p.byte == 0) {
+        hcur = hists.data() + int64_t(p.word) * 256;
+      } else {
+        OSHB_CUDA(cudaMemsetAsync(h_alone, 0, 256 * sizeof(unsigned), c.stream));
+        int64_t blocks = (n + OS_PT - 1) / OS_PT;
+        if (blocks > int64_t(c.sms) * 8) blocks = int64_t(c.sms) * 8;
+        k_os_hist<W><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, width, p.word, 8 * p.byte, h_alone);
+        OSHB_CUDA(cudaGetLastError());
+        c.launches++;
+        hcur = h_alone;
+      }
     }
-    // keep wa as the gather target of the next word; nothing to do if wcur==wb
+    unsigned* hnext = h_inflight[flight];
+    os_launch_pass<W>(p.first, p.next, keys, width, p.word, win, pin, n, 8 * p.byte, 8 * p.next_byte, hcur, hnext,
+        status.data(), ticket, p.next ? wout : nullptr, pout);
+    if (p.next) {
+      hcur = hnext;
+      flight ^= 1;
+      win = wout;
+      W* tw = wout;
+      wout = walt;
+      walt = tw;
+    } else {
+      win = nullptr;
+    }
+    pin = pout;
+    LO* tp = pout;
+    pout = palt;
+    palt = tp;
   }
-  if (pcur != perm) d2d(perm, pcur, size_t(n) * sizeof(LO));
-  sync_stream();  // temporaries are released stream-ordered, but keep host view simple
+  sync_stream();  // temporaries are released stream-ordered, but keep the host view simple
 }
 
 void sort_by_keys(LO const* keys, int64_t n, int width, LO* perm) { sort_impl<LO>(keys, n, width, perm); }

@@ -37,6 +37,10 @@ typedef double Real;
 #define OSHB_HD inline
 #define OSHB_LAMBDA [=]
 #define OSHB_CONSTANT static const
+struct int4 {
+  int x, y, z, w;
+};
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 #else
 #define OSHB_HD __host__ __device__ __forceinline__
 #define OSHB_LAMBDA [=] __device__
