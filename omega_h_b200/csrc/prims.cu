@@ -308,28 +308,28 @@ void minmax_f64(Real const* in, int64_t n, Real* mn, Real* mx) {
 }
 
 // =====================================================================================
-// sort_by_keys: stable LSD radix sort over 8-bit digits, one-sweep shape.
-//   pre-pass  : ONE read of the keys gives, per key word, the OR/AND of all values (constant
-//               bytes are never sorted on) and the histogram of byte 0; one 2*width-word
-//               read-back plans every pass (the only host sync of the sort).
-//   per digit : ONE kernel. A tile (256 threads x 16|12 items, warps own contiguous chunks so
-//               the order stays stable) ranks its items with __match_any_sync, publishes its
-//               per-bin counts and finds the counts of all earlier tiles by decoupled
-//               look-back (flag + count in one 32-bit word per (tile, bin)); items are
-//               re-ordered by bin in shared memory so that every bin's run leaves as one
-//               contiguous store. The first digit of a word fetches the word through the
-//               current permutation (no separate gather pass); while scattering digit b a
-//               tile also histograms the next digit of the same word (its bin totals are
-//               needed before that pass starts), so there is no histogram kernel either.
-// Algorithmic bytes: n*width*sizeof(W) in + 4n out; a pass moves 8 (12) B in and
-// 8 (12) B out per key.
+// sort_by_keys: stable LSD radix sort over 8-bit digits.
+//   pre-pass  : ONE read of the keys gives, per key word, the OR/AND of all values; constant
+//               bytes are never sorted on, and one 2*width-word read-back plans every pass (the
+//               only host sync of the sort).
+//   per digit : histogram -> scan -> scatter.
+//     histogram: per-tile digit counts into a bin-major matrix (shared-memory atomics: counting
+//                needs no order). The first digit of a word fetches the word through the current
+//                permutation and leaves it as a stream, so later digits and the scatter read
+//                sequentially.
+//     scan     : the library's single-pass scan over the 256 x ntiles matrix = global position of
+//                every (bin, tile) run. No look-back chain between scatter tiles: a one-sweep
+//                version (tile aggregates + decoupled look-back per bin) was built and measured at
+//                a flat 54 G keys/s whatever the tile size, occupancy or look-back width -- all
+//                tiles in flight reach the look-back together and the chain to the nearest finished
+//                tile costs ~30 L2 round trips (profiles/r2_sort_notes.md).
+//     scatter  : a tile (256 threads x 16|12 items, warps own contiguous chunks so the order stays
+//                stable) ranks its items with eight ballots per round (MATCH.ANY costs one step per
+//                distinct value on sm_100), re-orders them by bin in shared memory and writes every
+//                bin's run as one contiguous store.
+// Algorithmic bytes: n*width*sizeof(W) in + 4n out; a pass moves 20-24 B per key.
 // =====================================================================================
-static constexpr int OS_T = 512;   // threads per tile (16 warps); bins are owned by threads 0..255
-static constexpr int OS_PT = 256;  // threads of the pre-pass / histogram kernels (one per bin)
-static constexpr unsigned OS_FLAG_AGG = 1u << 30;
-static constexpr unsigned OS_FLAG_PRE = 2u << 30;
-static constexpr unsigned OS_VAL = (1u << 30) - 1u;
-
+static constexpr int OS_T = 256;
 template <class W>
 struct OsCfg {
   static constexpr int I = (sizeof(W) == 4) ? 16 : 12;
@@ -340,27 +340,22 @@ struct OsCfg {
 __device__ __forceinline__ unsigned long long os_ordered(LO w) { return static_cast<unsigned long long>(static_cast<unsigned>(w) ^ 0x80000000u); }
 __device__ __forceinline__ unsigned long long os_ordered(GO w) { return static_cast<unsigned long long>(w) ^ 0x8000000000000000ull; }
 
-// pre-pass: OR / AND of every word column + histogram of byte 0 of every column
+// pre-pass: OR / AND of every word column
 template <class W, int WIDTH>
-__global__ void __launch_bounds__(OS_PT) k_os_pre(W const* __restrict__ keys, int64_t n, unsigned long long* orand,
-    unsigned* hist0) {
-  __shared__ unsigned s_h[WIDTH][256];
-  for (int k = 0; k < WIDTH; ++k) s_h[k][threadIdx.x] = 0;
-  __syncthreads();
+__global__ void __launch_bounds__(OS_T) k_os_pre(W const* __restrict__ keys, int64_t n, unsigned long long* orand) {
   unsigned long long o[WIDTH], a[WIDTH];
 #pragma unroll
   for (int k = 0; k < WIDTH; ++k) {
     o[k] = 0;
     a[k] = ~0ull;
   }
-  int64_t stride = int64_t(gridDim.x) * OS_PT;
-  for (int64_t i = int64_t(blockIdx.x) * OS_PT + threadIdx.x; i < n; i += stride) {
+  int64_t stride = int64_t(gridDim.x) * OS_T;
+  for (int64_t i = int64_t(blockIdx.x) * OS_T + threadIdx.x; i < n; i += stride) {
 #pragma unroll
     for (int k = 0; k < WIDTH; ++k) {
       unsigned long long u = os_ordered(keys[i * WIDTH + k]);
       o[k] |= u;
       a[k] &= u;
-      atomicAdd(&s_h[k][unsigned(u) & 0xffu], 1u);
     }
   }
 #pragma unroll
@@ -375,100 +370,84 @@ __global__ void __launch_bounds__(OS_PT) k_os_pre(W const* __restrict__ keys, in
       atomicAnd(&orand[2 * k + 1], a[k]);
     }
   }
-  __syncthreads();
-  for (int k = 0; k < WIDTH; ++k) {
-    unsigned c = s_h[k][threadIdx.x];
-    if (c) atomicAdd(&hist0[k * 256 + threadIdx.x], c);
-  }
 }
 
-// histogram of one digit of one word column (only when byte 0 of a word is constant)
-template <class W>
-__global__ void __launch_bounds__(OS_PT) k_os_hist(W const* __restrict__ keys, int64_t n, int width, int word, int shift,
-    unsigned* hist) {
+// per-tile histogram of one digit; GATHER: fetch the word through the permutation and stream it out
+template <class W, bool GATHER>
+__global__ void __launch_bounds__(OS_T) k_os_hist(W const* __restrict__ keys, int width, int word,
+    W const* __restrict__ words_in, LO const* __restrict__ perm_in, int64_t n, int shift, W* __restrict__ words_out,
+    LO* __restrict__ hist, int ntiles) {
+  constexpr int I = OsCfg<W>::I;
+  constexpr int TILE = OsCfg<W>::TILE;
   __shared__ unsigned s_h[256];
   s_h[threadIdx.x] = 0;
   __syncthreads();
-  int64_t stride = int64_t(gridDim.x) * OS_PT;
-  for (int64_t i = int64_t(blockIdx.x) * OS_PT + threadIdx.x; i < n; i += stride)
-    atomicAdd(&s_h[unsigned(os_ordered(keys[i * width + word]) >> shift) & 0xffu], 1u);
-  __syncthreads();
-  unsigned c = s_h[threadIdx.x];
-  if (c) atomicAdd(&hist[threadIdx.x], c);
-}
-
-// exclusive scan of one value per thread over the OS_T threads of the block
-__device__ __forceinline__ unsigned os_block_exscan(unsigned v, unsigned* s_part /*8*/) {
-  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned incl = v;
+  int64_t const base = int64_t(blockIdx.x) * TILE;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += o;
+  for (int j = 0; j < I; ++j) {
+    int64_t g = base + j * OS_T + threadIdx.x;
+    if (g < n) {
+      W w;
+      if (GATHER) {
+        LO idx = perm_in ? perm_in[g] : LO(g);
+        w = keys[int64_t(idx) * width + word];
+        words_out[g] = w;
+      } else {
+        w = words_in[g];
+      }
+      atomicAdd(&s_h[unsigned(os_ordered(w) >> shift) & 0xffu], 1u);
+    }
   }
-  __syncthreads();  // s_part may still be read from a previous call
-  if (lane == 31) s_part[warp] = incl;
   __syncthreads();
-  unsigned off = 0;
-#pragma unroll
-  for (int w = 0; w < OS_T / 32; ++w)
-    if (w < warp) off += s_part[w];
-  return off + incl - v;
+  hist[int64_t(threadIdx.x) * ntiles + blockIdx.x] = LO(s_h[threadIdx.x]);
 }
 
-template <class W, bool GATHER, bool NEXT>
-__global__ void __launch_bounds__(OS_T) k_os_pass(W const* __restrict__ keys, int width, int word,
-    W const* __restrict__ words_in, LO const* __restrict__ perm_in, int64_t n, int shift, int next_shift,
-    unsigned const* __restrict__ ghist, unsigned* ghist_next, unsigned* status, unsigned* ticket,
-    W* __restrict__ words_out, LO* __restrict__ perm_out) {
+template <class W>
+__global__ void __launch_bounds__(OS_T, 3) k_os_scatter(W const* __restrict__ words_in, LO const* __restrict__ perm_in,
+    int64_t n, int shift, LO const* __restrict__ hist_scan, int ntiles, W* __restrict__ words_out,
+    LO* __restrict__ perm_out) {
   constexpr int I = OsCfg<W>::I;
   constexpr int TILE = OsCfg<W>::TILE;
   constexpr int NW = OS_T / 32;
   __shared__ unsigned s_cnt[NW][256];
   __shared__ unsigned s_base[256];
   __shared__ unsigned s_part[NW];
-  __shared__ unsigned s_tile;
-  extern __shared__ __align__(16) unsigned char s_raw[];  // TILE * (sizeof(W) + sizeof(LO)) bytes
+  __shared__ __align__(16) unsigned char s_raw[TILE * (sizeof(W) + sizeof(LO))];
   W* s_w = reinterpret_cast<W*>(s_raw);
   LO* s_p = reinterpret_cast<LO*>(s_raw + TILE * sizeof(W));
-  unsigned(*s_cnt2)[256] = reinterpret_cast<unsigned(*)[256]>(s_raw);  // phase 1-2 only, aliases the staging area
   int const t = threadIdx.x;
   int const lane = t & 31;
   int const warp = t >> 5;
-  if (t == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int k = t; k < NW * 256; k += OS_T) {
-    (&s_cnt[0][0])[k] = 0;
-    if (NEXT) (&s_cnt2[0][0])[k] = 0;
-  }
-  bool const owns_bin = t < 256;
-  // global start of every bin: exclusive scan of this digit's totals
-  unsigned const gbase = os_block_exscan(owns_bin ? ghist[t] : 0u, s_part);  // (syncs inside: s_tile, s_cnt visible)
-  unsigned const tile = s_tile;
-  int64_t const base = int64_t(tile) * TILE;
-  // ---- phase 1: load, rank inside the warp's chunk
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s_cnt[w][t] = 0;
+  __syncthreads();
+  int64_t const base = int64_t(blockIdx.x) * TILE;
+  // ---- phase 1: all loads first (2*I independent requests per thread in flight), then rank inside
+  // the warp's chunk
   W wv[I];
   LO iv[I];
-  unsigned pre[I];
+  unsigned short pre[I];
   int64_t const wbase = base + int64_t(warp) * (I * 32);
   unsigned const lt = (1u << lane) - 1u;
 #pragma unroll
   for (int r = 0; r < I; ++r) {
     int64_t g = wbase + r * 32 + lane;
     bool valid = g < n;
-    LO idx = 0;
-    W w = W(0);
-    if (valid) {
-      idx = perm_in ? perm_in[g] : LO(g);
-      w = GATHER ? keys[int64_t(idx) * width + word] : words_in[g];
+    wv[r] = valid ? words_in[g] : W(0);
+    iv[r] = valid ? (perm_in ? perm_in[g] : LO(g)) : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < I; ++r) {
+    bool valid = wbase + r * 32 + lane < n;
+    unsigned d = unsigned(os_ordered(wv[r]) >> shift) & 0xffu;
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      unsigned vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+      peers &= ((d >> b) & 1u) ? vote : ~vote;
     }
-    wv[r] = w;
-    iv[r] = idx;
-    unsigned long long u = os_ordered(w);
-    unsigned d = unsigned(u >> shift) & 0xffu;
-    unsigned amask = __ballot_sync(0xffffffffu, valid);
     unsigned my = 0;
     if (valid) {
-      unsigned peers = __match_any_sync(amask, d);
       int leader = __ffs(peers) - 1;
       unsigned old = 0;
       if (lane == leader) {
@@ -477,66 +456,37 @@ __global__ void __launch_bounds__(OS_T) k_os_pass(W const* __restrict__ keys, in
       }
       old = __shfl_sync(peers, old, leader);
       my = old + __popc(peers & lt);
-      if (NEXT) {
-        unsigned d2 = unsigned(u >> next_shift) & 0xffu;
-        unsigned peers2 = __match_any_sync(amask, d2);
-        if (lane == __ffs(peers2) - 1) s_cnt2[warp][d2] += __popc(peers2);
-      }
     }
-    pre[r] = my;
+    pre[r] = (unsigned short)my;
     __syncwarp();
   }
   __syncthreads();
-  // ---- phase 2: thread t < 256 owns bin t
+  // ---- phase 2: thread t owns bin t
   unsigned total = 0;
-  if (owns_bin) {
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      unsigned c = s_cnt[w][t];
-      s_cnt[w][t] = total;
-      total += c;
-    }
-    if (NEXT) {
-      unsigned t2 = 0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) t2 += s_cnt2[w][t];
-      if (t2) atomicAdd(&ghist_next[t], t2);
-    }
+  for (int w = 0; w < NW; ++w) {
+    unsigned c = s_cnt[w][t];
+    s_cnt[w][t] = total;
+    total += c;
   }
-  volatile unsigned* st = status;
-  if (owns_bin) st[int64_t(tile) * 256 + t] = (tile == 0 ? OS_FLAG_PRE : OS_FLAG_AGG) | total;
-  unsigned const lstart = os_block_exscan(total, s_part);
-  if (owns_bin) {
-    unsigned excl = 0;
-    if (tile > 0) {
-      // look-back, OS_LB predecessor tiles per round trip: the loads of a batch are independent, so a
-      // chain through the tiles in flight costs chain/OS_LB L2 latencies instead of chain (the rate
-      // at which tiles can retire is bounded by OS_LB / L2 latency)
-      constexpr int OS_LB = 32;
-      int64_t look = int64_t(tile) - 1;
-      bool done = false;
-      while (!done) {
-        unsigned sv[OS_LB];
+  // exclusive scan of the tile's bin totals = start of every bin in the staging order
+  unsigned incl = total;
 #pragma unroll
-        for (int k = 0; k < OS_LB; ++k) sv[k] = (look - k >= 0) ? st[(look - k) * 256 + t] : (2u << 30);
-#pragma unroll
-        for (int k = 0; k < OS_LB; ++k) {
-          if (!done) {
-            unsigned v = sv[k];
-            while ((v >> 30) == 0) v = st[(look - k) * 256 + t];
-            excl += v & OS_VAL;
-            if ((v >> 30) == 2) done = true;
-          }
-        }
-        look -= OS_LB;
-      }
-      st[int64_t(tile) * 256 + t] = OS_FLAG_PRE | (excl + total);
-    }
-    s_base[t] = gbase + excl - lstart;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) s_cnt[w][t] += lstart;
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
   }
-  __syncthreads();  // also: s_cnt2 no longer read, the staging area may be written
+  if (lane == 31) s_part[warp] = incl;
+  __syncthreads();
+  unsigned off = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w)
+    if (w < warp) off += s_part[w];
+  unsigned const lstart = off + incl - total;
+  s_base[t] = unsigned(hist_scan[int64_t(t) * ntiles + blockIdx.x]) - lstart;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s_cnt[w][t] += lstart;
+  __syncthreads();
   // ---- phase 3: stage in bin order
 #pragma unroll
   for (int r = 0; r < I; ++r) {
@@ -560,53 +510,18 @@ __global__ void __launch_bounds__(OS_T) k_os_pass(W const* __restrict__ keys, in
   }
 }
 
-template <class W, bool G, bool N>
-static void os_go(unsigned ntiles, W const* keys, int width, int word, W const* words_in, LO const* perm_in, int64_t n,
-    int shift, int next_shift, unsigned const* ghist, unsigned* ghist_next, unsigned* status, unsigned* ticket,
-    W* words_out, LO* perm_out) {
-  size_t const smem = size_t(OsCfg<W>::TILE) * (sizeof(W) + sizeof(LO));
-  static bool attr_set = false;
-  auto kern = k_os_pass<W, G, N>;
-  if (!attr_set) {
-    OSHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr_set = true;
-  }
-  kern<<<ntiles, OS_T, smem, ctx().stream>>>(keys, width, word, words_in, perm_in, n, shift, next_shift, ghist,
-      ghist_next, status, ticket, words_out, perm_out);
-}
-
-template <class W>
-static void os_launch_pass(bool gather, bool next, W const* keys, int width, int word, W const* words_in,
-    LO const* perm_in, int64_t n, int shift, int next_shift, unsigned const* ghist, unsigned* ghist_next,
-    unsigned* status, unsigned* ticket, W* words_out, LO* perm_out) {
-  Ctx& c = ctx();
-  unsigned const ntiles = unsigned((n + OsCfg<W>::TILE - 1) / OsCfg<W>::TILE);
-  OSHB_CUDA(cudaMemsetAsync(status, 0, size_t(ntiles) * 256 * sizeof(unsigned), c.stream));
-  OSHB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), c.stream));
-  if (next) OSHB_CUDA(cudaMemsetAsync(ghist_next, 0, 256 * sizeof(unsigned), c.stream));
-  if (c.prof_on) prof_begin("sort_by_keys(pass)");
-  if (gather && next) os_go<W, true, true>(ntiles, keys, width, word, words_in, perm_in, n, shift, next_shift, ghist, ghist_next, status, ticket, words_out, perm_out);
-  else if (gather) os_go<W, true, false>(ntiles, keys, width, word, words_in, perm_in, n, shift, next_shift, ghist, ghist_next, status, ticket, words_out, perm_out);
-  else if (next) os_go<W, false, true>(ntiles, keys, width, word, words_in, perm_in, n, shift, next_shift, ghist, ghist_next, status, ticket, words_out, perm_out);
-  else os_go<W, false, false>(ntiles, keys, width, word, words_in, perm_in, n, shift, next_shift, ghist, ghist_next, status, ticket, words_out, perm_out);
-  OSHB_CUDA(cudaGetLastError());
-  if (c.prof_on) prof_end("sort_by_keys(pass)");
-  c.launches++;
-}
-
 template <class W>
 static void sort_impl(W const* keys, int64_t n, int width, LO* perm) {
   Ctx& c = ctx();
-  OSHB_CHECK(width >= 1);
+  OSHB_CHECK(width >= 1 && width <= 4);  // uses have <= 4 vertices
   if (n <= 1) {
     fill_linear<LO>(perm, n, 0, 1);
     return;
   }
-  OSHB_CHECK(n < (int64_t(1) << 30));  // 30-bit counts in the look-back words; LO-indexed uses stay below
+  OSHB_CHECK(n < (int64_t(1) << 31));
   int const nbytes = int(sizeof(W));
-  // ---- pre-pass: OR/AND + byte-0 histograms, one read of the keys
+  // ---- pre-pass: OR/AND of every column, one read of the keys
   DArr<unsigned long long> orand(2 * int64_t(width));
-  DArr<unsigned> hists((int64_t(width) + 3) * 256);  // [width] byte-0 histograms, 2 in-flight, 1 standalone
   {
     std::vector<unsigned long long> init(2 * size_t(width));
     for (int k = 0; k < width; ++k) {
@@ -614,31 +529,24 @@ static void sort_impl(W const* keys, int64_t n, int width, LO* perm) {
       init[2 * k + 1] = ~0ull;
     }
     h2d(orand.data(), init.data(), init.size() * 8);
-    OSHB_CUDA(cudaMemsetAsync(hists.data(), 0, size_t(hists.size()) * sizeof(unsigned), c.stream));
-    int64_t blocks = (n + OS_PT - 1) / OS_PT;
+    int64_t blocks = (n + OS_T - 1) / OS_T;
     if (blocks > int64_t(c.sms) * 8) blocks = int64_t(c.sms) * 8;
     if (c.prof_on) prof_begin("sort_by_keys(pre)");
-    if (width <= 4) {
-      switch (width) {
-        case 1: k_os_pre<W, 1><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, orand.data(), hists.data()); break;
-        case 2: k_os_pre<W, 2><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, orand.data(), hists.data()); break;
-        case 3: k_os_pre<W, 3><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, orand.data(), hists.data()); break;
-        default: k_os_pre<W, 4><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, orand.data(), hists.data()); break;
-      }
-      c.launches++;
-    } else {
-      // wide keys: treat every column as a 1-word key set with a stride (reads the keys `width` times)
-      OSHB_CHECK(width <= 4);  // not needed by any caller (uses have <= 4 vertices)
+    switch (width) {
+      case 1: k_os_pre<W, 1><<<unsigned(blocks), OS_T, 0, c.stream>>>(keys, n, orand.data()); break;
+      case 2: k_os_pre<W, 2><<<unsigned(blocks), OS_T, 0, c.stream>>>(keys, n, orand.data()); break;
+      case 3: k_os_pre<W, 3><<<unsigned(blocks), OS_T, 0, c.stream>>>(keys, n, orand.data()); break;
+      default: k_os_pre<W, 4><<<unsigned(blocks), OS_T, 0, c.stream>>>(keys, n, orand.data()); break;
     }
     OSHB_CUDA(cudaGetLastError());
     if (c.prof_on) prof_end("sort_by_keys(pre)");
+    c.launches++;
   }
   std::vector<unsigned long long> oa = orand.to_host();  // the sort's one read-back
-  // ---- plan: the digits that vary, last word first
+  // ---- plan: the bytes that vary, last word first
   struct Pass {
     int word, byte;
-    bool first, next;
-    int next_byte;
+    bool first, last_of_word;
   };
   std::vector<Pass> plan;
   for (int word = width - 1; word >= 0; --word) {
@@ -646,63 +554,44 @@ static void sort_impl(W const* keys, int64_t n, int width, LO* perm) {
     std::vector<int> bytes;
     for (int b = 0; b < nbytes; ++b)
       if ((diff >> (8 * b)) & 0xffull) bytes.push_back(b);
-    for (size_t k = 0; k < bytes.size(); ++k) {
-      Pass p;
-      p.word = word;
-      p.byte = bytes[k];
-      p.first = (k == 0);
-      p.next = (k + 1 < bytes.size());
-      p.next_byte = p.next ? bytes[k + 1] : 0;
-      plan.push_back(p);
-    }
+    for (size_t k = 0; k < bytes.size(); ++k) plan.push_back(Pass{word, bytes[k], k == 0, k + 1 == bytes.size()});
   }
   if (plan.empty()) {
     fill_linear<LO>(perm, n, 0, 1);
     return;
   }
-  unsigned const ntiles = unsigned((n + OsCfg<W>::TILE - 1) / OsCfg<W>::TILE);
-  DArr<unsigned> status(int64_t(ntiles) * 256 + 1);
-  unsigned* ticket = status.data() + int64_t(ntiles) * 256;
+  int const ntiles = int((n + OsCfg<W>::TILE - 1) / OsCfg<W>::TILE);
+  DArr<LO> hist(int64_t(256) * ntiles);
+  DArr<LO> hscan(int64_t(256) * ntiles + 1);
   DArr<W> wa(n), wb(n);
   DArr<LO> pb(n);
   // permutation buffers alternate; start so that the last pass writes into `perm`
   LO* pout = (plan.size() % 2 == 1) ? perm : pb.data();
   LO* palt = (plan.size() % 2 == 1) ? pb.data() : perm;
   LO const* pin = nullptr;  // identity
-  W* wout = wa.data();
+  W* wcur = wa.data();
   W* walt = wb.data();
-  W const* win = nullptr;
-  unsigned* h_inflight[2] = {hists.data() + int64_t(width) * 256, hists.data() + (int64_t(width) + 1) * 256};
-  unsigned* h_alone = hists.data() + (int64_t(width) + 2) * 256;
-  int flight = 0;
-  unsigned const* hcur = nullptr;
   for (size_t k = 0; k < plan.size(); ++k) {
     Pass const& p = plan[k];
-    if (p.first) {
-      if (p.byte == 0) {
-        hcur = hists.data() + int64_t(p.word) * 256;
-      } else {
-        OSHB_CUDA(cudaMemsetAsync(h_alone, 0, 256 * sizeof(unsigned), c.stream));
-        int64_t blocks = (n + OS_PT - 1) / OS_PT;
-        if (blocks > int64_t(c.sms) * 8) blocks = int64_t(c.sms) * 8;
-        k_os_hist<W><<<unsigned(blocks), OS_PT, 0, c.stream>>>(keys, n, width, p.word, 8 * p.byte, h_alone);
-        OSHB_CUDA(cudaGetLastError());
-        c.launches++;
-        hcur = h_alone;
-      }
-    }
-    unsigned* hnext = h_inflight[flight];
-    os_launch_pass<W>(p.first, p.next, keys, width, p.word, win, pin, n, 8 * p.byte, 8 * p.next_byte, hcur, hnext,
-        status.data(), ticket, p.next ? wout : nullptr, pout);
-    if (p.next) {
-      hcur = hnext;
-      flight ^= 1;
-      win = wout;
-      W* tw = wout;
-      wout = walt;
+    if (c.prof_on) prof_begin("sort_by_keys(hist)");
+    if (p.first)
+      k_os_hist<W, true><<<unsigned(ntiles), OS_T, 0, c.stream>>>(keys, width, p.word, nullptr, pin, n, 8 * p.byte, wcur, hist.data(), ntiles);
+    else
+      k_os_hist<W, false><<<unsigned(ntiles), OS_T, 0, c.stream>>>(keys, width, p.word, wcur, pin, n, 8 * p.byte, nullptr, hist.data(), ntiles);
+    OSHB_CUDA(cudaGetLastError());
+    if (c.prof_on) prof_end("sort_by_keys(hist)");
+    c.launches++;
+    scan_offsets(hist.data(), int64_t(256) * ntiles, hscan.data());
+    if (c.prof_on) prof_begin("sort_by_keys(scatter)");
+    k_os_scatter<W><<<unsigned(ntiles), OS_T, 0, c.stream>>>(wcur, pin, n, 8 * p.byte, hscan.data(), ntiles,
+        p.last_of_word ? nullptr : walt, pout);
+    OSHB_CUDA(cudaGetLastError());
+    if (c.prof_on) prof_end("sort_by_keys(scatter)");
+    c.launches++;
+    if (!p.last_of_word) {
+      W* tw = wcur;
+      wcur = walt;
       walt = tw;
-    } else {
-      win = nullptr;
     }
     pin = pout;
     LO* tp = pout;
