@@ -43,15 +43,10 @@ struct TagTable {
   TagCopy t[8];
 };
 
-// The gather's SOURCE STREAM: for every new entity, written by the numbering sweep that already
-// walks the old entities in order (coalesced, 6 B per new entity):
-//   src[ne]  = the surviving old entity that lands on slot ne, or the KEY whose product it is
-//   srct[ne] = 0xffff for a survivor, else the product number t inside its key (midpoint vertices:
-//              the key's rank among the keys of its first vertex)
-// so a gather thread knows what it builds after two coalesced loads -- no search over the scanned
-// counts, no offsets[e], no status[e] (round 1: 3-step bisect + 2 samples + offset + status = a
-// chain of 7 dependent loads in front of the real work; ncu put 15-20 % of the stalls there).
-constexpr unsigned SRC_SURVIVOR = 0xffffu;
+// one search sample every 2^CS_SHIFT new slots: 0.5 B per new entity buys a 3-step bisect
+// (the ncu source page put 15 % of the gather's stall samples on a 7-step one)
+constexpr int CS_SHIFT = 3;
+constexpr int CS_MASK = (1 << CS_SHIFT) - 1;
 
 OSHB_HD void copy_ent(void* dst, int64_t di, void const* src, int64_t si, int bytes) {
   if (bytes == 1) {
@@ -308,13 +303,14 @@ struct GatherArgs {
   LO const* od;     // old downward rows
   I8 const* oc;     // old codes
   LO const* ovo;    // old entity -> vertices (dims 2, 3)
-  LO const* src;             // source stream: surviving old entity | key
-  unsigned short const* srct;  // source stream: SRC_SURVIVOR | product number
+  LO const* off;    // scanned representative counts (nold + 1)
+  LO const* st;     // status per old entity (dims >= 1)
   LO const* ol2nl;  // old low -> new low
   GO const* og;     // old globals
   GO const* lg;     // scanned counts on the linear partition (general globals only)
   bool ident;       // globals are the identity
   I8* pm;           // product marks (only where a product-only transfer follows)
+  LO const* cs;     // coarse samples of the slot search
   LO const* voff;   // first vertex -> keys
   LO const* vkeys;
   TagTable stab, itab;
@@ -332,10 +328,13 @@ static void run_gather(GatherArgs const& ga, Topo const& t2) {
   GO* ng = t2.ng[D];
   LO const* ov2nv = t2.o2n[0];
   parallel_for(a.nnew, OSHB_LAMBDA(LO ne) {
-    LO const sv = a.src[ne];
-    unsigned const st = a.srct[ne];
-    if (st == SRC_SURVIVOR) {
-      LO const e = sv;
+    // the old entity that represents this slot: last e with off[e] <= ne
+    LO lo = a.cs[ne >> CS_SHIFT];
+    LO hi = a.cs[(ne >> CS_SHIFT) + 1];
+    LO e = lo + upper_bound(a.off + lo + 1, hi - lo, ne);
+    LO local = ne - a.off[e];
+    LO s = (D >= 1) ? a.st[e] : -1;
+    if (s == -1 && local == 0) {
       // a surviving entity keeps its place: remapped row, codes, vertices, global, tags
       // (modify_conn / transfer_common2, src/Omega_h_modify.cpp:20-70, Omega_h_transfer.cpp:160-170)
       ng[ne] = a.ident ? GO(ne) : (a.og ? a.lg[a.og[e]] : a.lg[e]);
@@ -360,15 +359,16 @@ static void run_gather(GatherArgs const& ga, Topo const& t2) {
       return;
     }
     if (a.pm) a.pm[ne] = 1;
-    LO const key = sv;
-    LO const t = LO(st);
     if (D == VERT) {
-      // midpoint vertex of key `key`
+      // midpoint vertex of the (local-1)-th key whose first vertex is e
+      LO key = a.vkeys[a.voff[e] + local - 1];
       LO ke = t2.k2e[key];
       ng[ne] = t2.gbase[0][key];
       for (int k = 0; k < a.itab.n; ++k) copy_ent(a.itab.t[k].dst, ne, a.itab.t[k].src_up, ke, a.itab.t[k].bytes);
       return;
     }
+    LO key = s;
+    LO t = local;
     ng[ne] = a.ident ? GO(ne) : (t2.gbase[D][key] + t);
     LO fb = t2.ef_off[key];
     LO nf = t2.ef_off[key + 1] - fb;
@@ -441,8 +441,7 @@ struct Rebuild {
   LOs ev2v_old, fv2v, rv2v;
   Adj e2f, e2r, f2e, r2f, r2e;
   Topo tp;
-  LOs old2new[4], pbase[4], offsets[4], status[4], src[4];
-  DArr<unsigned short> srct[4];
+  LOs old2new[4], pbase[4], offsets[4], status[4], coarse[4];
   bool identity[4];
   GOs gbase[4], new_globals[4], lin_globals[4], ext_bases[4];
   LO nnew[4];
@@ -568,43 +567,22 @@ void Rebuild::number() {
     identity[ent_dim] = ident;
     GOs old_globals = mesh->globals(ent_dim);
     GO const* og = old_globals.data();
-    // the source stream of the gather (see SRC_SURVIVOR above): every old entity files itself, or
-    // the products of the key it represents, under its stretch of new slots
+    // coarse[i] = old entity representing new slot (i << CS_SHIFT) (the gather's per-thread search then only
+    // bisects the cache-resident stretch of offsets between two samples); every old entity files
+    // itself under the samples that fall into its stretch of new slots
     LO const nnew_d = nnew[ent_dim];
-    src[ent_dim] = LOs(nnew_d);
-    srct[ent_dim] = DArr<unsigned short>(nnew_d);
-    LO* sr = src[ent_dim].data();
-    unsigned short* srt = srct[ent_dim].data();
-    LO const* vk = ko.vert_keys.data();
-    int* err = device_error_cell();
-    auto file_sources = OSHB_LAMBDA(LO e, LO a0, LO a1) {
-      if (ent_dim == VERT) {
-        // a vertex survives, then come the midpoints of the keys whose first vertex it is
-        sr[a0] = e;
-        srt[a0] = (unsigned short)SRC_SURVIVOR;
-        for (LO i = a0 + 1; i < a1; ++i) {
-          sr[i] = vk[voff[e] + (i - a0 - 1)];
-          srt[i] = (unsigned short)(i - a0 - 1);
-        }
-        return;
-      }
-      LO sta = st[e];
-      if (sta == -1) {
-        sr[a0] = e;
-        srt[a0] = (unsigned short)SRC_SURVIVOR;
-      } else if (sta >= 0) {
-        if (a1 - a0 >= LO(SRC_SURVIVOR)) atomic_or_i32(err, 8);  // a key with >= 65535 products: not a mesh
-        for (LO i = a0; i < a1; ++i) {
-          sr[i] = sta;
-          srt[i] = (unsigned short)(i - a0);
-        }
-      }
-    };
+    LO const ncoarse = (nnew_d >> CS_SHIFT) + 2;
+    coarse[ent_dim] = LOs(ncoarse);
+    LO* cs = coarse[ent_dim].data();
     if (ident || ext_g) {
       parallel_for(nold, OSHB_LAMBDA(LO e) {
         LO a0 = off[e], a1 = off[e + 1];
         o2n[e] = (st && st[e] != -1) ? -1 : a0;
-        file_sources(e, a0, a1);
+        if (a1 > a0) {
+          for (LO i = (a0 + CS_MASK) >> CS_SHIFT; (int64_t(i) << CS_SHIFT) < a1; ++i) cs[i] = e;
+          if (a1 == nnew_d)
+            for (LO i = ((a1 - 1) >> CS_SHIFT) + 1; i < ncoarse; ++i) cs[i] = e;
+        }
       }, "old2new");
     } else {
       lin_globals[ent_dim] = GOs(int64_t(nold) + 1);
@@ -614,7 +592,11 @@ void Rebuild::number() {
         LO a0 = off[e], a1 = off[e + 1];
         o2n[e] = (st && st[e] != -1) ? -1 : a0;
         lc[og[e]] = a1 - a0;
-        file_sources(e, a0, a1);
+        if (a1 > a0) {
+          for (LO i = (a0 + CS_MASK) >> CS_SHIFT; (int64_t(i) << CS_SHIFT) < a1; ++i) cs[i] = e;
+          if (a1 == nnew_d)
+            for (LO i = ((a1 - 1) >> CS_SHIFT) + 1; i < ncoarse; ++i) cs[i] = e;
+        }
       }, "old2new+to_lin");
       scan_offsets(lin_counts.data(), nold, lin_globals[ent_dim].data());
     }
@@ -750,8 +732,8 @@ void Rebuild::finish() {
     ga.od = (d >= 1) ? old_down.ab2b.data() : nullptr;
     ga.oc = (d >= 2) ? old_down.codes.data() : nullptr;
     ga.ovo = (d == FACE) ? tp.fv2v : ((d == REGION) ? tp.rv2v : nullptr);
-    ga.src = src[d].data();
-    ga.srct = srct[d].data();
+    ga.off = offsets[d].data();
+    ga.st = (d >= 1) ? status[d].data() : nullptr;
     ga.ol2nl = (d >= 1) ? tp.o2n[d - 1] : nullptr;
     GOs ogs = mesh->globals(d);
     ga.og = ext ? nullptr : ogs.data();
@@ -762,13 +744,13 @@ void Rebuild::finish() {
     ga.vkeys = vkeys;
     ga.stab = same_tab[d];
     ga.itab = inh_tab[d];
+    LO const* cs = coarse[d].data();
+    ga.cs = cs;
     int const deg = (d >= 1) ? simplex_degree(d, d - 1) : 0;
     int const nv = d + 1;
     int64_t tag_bytes = 0;
     for (int k = 0; k < ga.stab.n; ++k) tag_bytes += ga.stab.t[k].bytes;
     // algorithmic bytes: every new array written once + the old arrays read once
-    // (same formula as round 1 -- 4+4 B per old entity stood for offsets + status, now the 6 B source
-    // stream per new entity is NOT added: the declared bytes only ever shrink relative to the traffic)
     algo_bytes(int64_t(nnew[d]) * (8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes) +
                int64_t(ga.nold) * (4 + 4 + 8 + deg * 5 + (d >= 2 ? nv * 4 : 0) + tag_bytes));
     if (d == VERT) run_gather<0>(ga, tp);
