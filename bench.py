@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table to stderr and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="N = 1: skip the `also` block (aniso n=64 loop, 100 M-tet adjacency microbench)")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the N-rank == serial self-check")
     ap.add_argument("--halo", type=int, default=4, help="N > 1: element layers each part keeps of its neighbours")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent boxes instead of one partitioned box")
     return ap.parse_args()
@@ -131,7 +133,10 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the unmodified reference on the host cores
 # ---------------------------------------------------------------------------------------------
-def run_reference(n, maxpasses, omp=True):
+def run_reference_loops(n, kind, reps, budget_s, omp=True):
+    """The UNMODIFIED reference (oracle/_ref, built by oracle/Makefile) running the WHOLE
+    `while (refine_by_size)` loop `reps` times on copies of one input mesh, all host cores; one record
+    per repetition. Stops early after budget_s seconds of wall time."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver_omp" if omp else "ref_driver")
     if not os.path.exists(exe):
         return None
@@ -139,60 +144,64 @@ def run_reference(n, maxpasses, omp=True):
     cores = os.cpu_count() or 1
     env["OMP_NUM_THREADS"] = str(cores)
     env["OMP_PROC_BIND"] = "false"
-    out = subprocess.run([exe, "time", "3", str(n), "0", str(maxpasses)], capture_output=True, text=True, env=env)
+    out = subprocess.run([exe, "timeloops", "3", str(n), str(kind), str(reps), str(budget_s)], capture_output=True,
+                         text=True, env=env)
     if out.returncode != 0:
         return None
-    for ln in out.stdout.splitlines():
-        if ln.startswith("{"):
-            return json.loads(ln)
-    return None
+    recs = [json.loads(ln) for ln in out.stdout.splitlines() if ln.startswith("{")]
+    return recs or None
 
 
-def reference_sample(n):
-    """bounded sample: the first two passes of the same loop on the same box (the remaining two
-    passes repeat the same work on 4x and 8x the entities)."""
-    r = run_reference(n, 2, omp=True)
-    if r is None:
+def reference_sample(n, workload="iso"):
+    """cpu_baseline of the N = 1 line: ONE complete loop of the same workload (same box, same metric,
+    all passes) by the unmodified reference on all host cores."""
+    recs = run_reference_loops(n, 2 if workload == "aniso" else 0, 1, 1e9)
+    if not recs:
         return None
+    r = recs[-1]
     new = r["nelems_after"] - r["nelems_before"]
     return {"value": new / r["seconds"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
-            "sample": "passes 0-1 of the %d^3 loop (%d -> %d tets) in %.2f s, OpenMP build of the unmodified "
-                      "reference (oracle/_ref), %d threads" % (n, r["nelems_before"], r["nelems_after"], r["seconds"],
-                                                               r["threads"]),
+            "sample": "one complete %d^3 loop (%d passes, %d -> %d tets) in %.2f s, OpenMP build of the unmodified "
+                      "reference (oracle/_ref), %d threads" % (n, r["passes"], r["nelems_before"], r["nelems_after"],
+                                                               r["seconds"], r["threads"]),
             "seconds": r["seconds"]}
 
 
 def main_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, the same config, metric and
+    unit; a step = the complete loop (all passes), W warm-up + K timed repetitions as asked, cut short
+    only if that would exceed REF_BUDGET_S of wall time (then `steps` says how many were timed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    vals = []
-    last = None
-    t0 = time.time()
-    for i in range(args.warmup + args.steps):
-        # keep the whole arm within a few minutes whatever K/W the driver passes
-        if i >= 1 and time.time() - t0 > 150:
-            break
-        s = reference_sample(args.n)
-        if s is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_omp missing or failed"}))
-            return 0
-        last = s
-        if i >= min(args.warmup, 1):
-            vals.append(s)
-    if not vals:
-        vals = [last]
-    secs = sum(v["seconds"] for v in vals) / len(vals)
-    value = sum(v["value"] for v in vals) / len(vals)
+    budget = float(os.environ.get("OSHB_REF_BUDGET_S", "330"))
+    kind = 2 if args.workload == "aniso" else 0
+    recs = run_reference_loops(args.n, kind, args.warmup + args.steps, budget)
+    if not recs:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_omp missing or failed"}))
+        return 0
+    warm = min(args.warmup, max(len(recs) - 1, 0))
+    timed = recs[warm:]
+    secs = sum(r["seconds"] for r in timed) / len(timed)
+    new = timed[0]["nelems_after"] - timed[0]["nelems_before"]
+    value = new * len(timed) / sum(r["seconds"] for r in timed)
+    cfg = workload_config(args.n, args.workload)
+    cfg["passes_per_step"] = timed[0]["passes"]
+    cfg["tets_per_step"] = "%d -> %d" % (timed[0]["nelems_before"], timed[0]["nelems_after"])
+    cfg["parallelism"] = "host CPU, OpenMP, %d threads" % timed[0]["threads"]
+    cfg["input_caches"] = "length + quality tags measured before the timed loop (ask_lengths/ask_qualities), as in our arm"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": secs * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.n),
-        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "steps": len(timed), "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": secs * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": timed[0]["threads"], "kind": "reference",
+                         "sample": "%d complete loops (%d passes each, %d -> %d tets), %.2f s per loop, OpenMP build of the "
+                                   "unmodified reference (oracle/_ref)" % (len(timed), timed[0]["passes"],
+                                                                          timed[0]["nelems_before"], timed[0]["nelems_after"], secs)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    line["cpu_baseline"]["value"] = value
     print(json.dumps(line))
     return 0
 
@@ -308,6 +317,106 @@ class Download:
                 m.get_array(d, name, out=ob)
                 nbytes += n * np.dtype(NP_OF[t]).itemsize
         return nbytes
+
+
+def also_aniso(lib, n=64, steps=3):
+    """BASELINE config[2]'s shape on one GPU (anisotropic tanh-layer 3x3 metric, field transfer), n^3 box:
+    device-timed loops after the headline region, so the anisotropic rate is in the driver's record too."""
+    from omega_h_b200 import AdaptOpts
+    base = build_input(n, lib, "aniso")
+    opts = AdaptOpts(base)
+    n0 = base.nelems()
+    for _ in range(2):
+        m = base.copy()
+        run_loop(m, opts)
+    lib.sync()
+    ms = 0.0
+    for _ in range(steps):
+        m = base.copy()
+        lib.timer_start()
+        passes = run_loop(m, opts)
+        ms += lib.timer_stop()
+    n1 = m.nelems()
+    return {"workload": workload_config(n, "aniso")["workload"], "value": (n1 - n0) * steps / (ms / 1e3), "unit": UNIT,
+            "ms_per_step": ms / steps, "steps": steps, "passes_per_step": passes, "tets_per_step": "%d -> %d" % (n0, n1),
+            "timing": "CUDA events on the library stream, input resident in HBM"}
+
+
+def also_adj(lib):
+    """BASELINE config[4]: adjacency-derivation microbench on a 100 M-tet box (tools/adj_bench.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import adj_bench
+    out = adj_bench.run(lib, 256, 256, 254)
+    return {"mesh": out["mesh"], "peak_gbs": out["peak_gbs"],
+            "bytes": "algorithmic (SURVEY.md 8d): compulsory reads + writes of each primitive",
+            "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
+                        for k, v in out["kernels"].items()}}
+
+
+def partition_parity_check(lib, device, halo, n=16):
+    """N-rank == serial, checked on the GPUs of this very run before anything is timed: an n^3-per-rank box
+    goes through the partitioned loop (NCCL exchanges and all), is assembled on rank 0 (DistMesh.gather) and
+    compared with the serial loop's mesh ARRAY BY ARRAY -- connectivity, codes, global numbers, every tag.
+    A mismatch aborts the benchmark."""
+    import numpy as np
+    import torch.distributed as dist
+    from omega_h_b200 import VERT, build_box, refine_by_size, AdaptOpts, simplex_degree
+    from omega_h_b200 import dist as D
+    world, rank = dist.get_world_size(), dist.get_rank()
+    shape = box_shape(world)
+    base = build_box(float(shape[0]), float(shape[1]), float(shape[2]), shape[0] * n, shape[1] * n, shape[2] * n, lib=lib)
+    h = 1.0 / n / 2.0
+    base.add_tag(VERT, "metric", 1, np.full(base.nverts(), 1.0 / (h * h)))
+    serial = None
+    spasses = 0
+    if rank == 0:
+        serial = base.copy()
+        sopts = AdaptOpts(serial)
+        while refine_by_size(serial, sopts):
+            spasses += 1
+    part = D.distribute(base, halo, device)
+    opts = AdaptOpts(part.mesh)
+    passes = 0
+    while part.refine_by_size(opts):
+        passes += 1
+    whole = part.gather(0)
+    res = {"ok": True, "ranks": world, "box": "%dx%dx%d cells" % (shape[0] * n, shape[1] * n, shape[2] * n),
+           "halo": halo, "passes": passes, "arrays_compared": 0}
+    if rank == 0:
+        bad = []
+        if passes != spasses:
+            bad.append("passes %d vs %d" % (passes, spasses))
+        dim = serial.dim()
+        for d in range(dim + 1):
+            if whole.nents(d) != serial.nents(d):
+                bad.append("nents(%d)" % d)
+                continue
+            for name, _, _ in serial.tags(d):
+                res["arrays_compared"] += 1
+                if not np.array_equal(serial.get_array(d, name), whole.get_array(d, name)):
+                    bad.append("tag %d:%s" % (d, name))
+            if d >= 1:
+                a, ac = serial.ask_down(d, d - 1)
+                b, bc = whole.ask_down(d, d - 1)
+                res["arrays_compared"] += 1
+                if not np.array_equal(a, b):
+                    bad.append("down %d" % d)
+                if d >= 2:
+                    res["arrays_compared"] += 1
+                    if not np.array_equal(ac, bc):
+                        bad.append("codes %d" % d)
+        res["tets"] = int(serial.nelems())
+        res["compared"] = "every tag (reals bit for bit), downward adjacency and alignment codes of every dimension"
+        if bad:
+            res["ok"] = False
+            res["mismatch"] = bad
+    flag = __import__("torch").tensor([1 if res["ok"] else 0], device=device)
+    dist.broadcast(flag, 0)
+    if int(flag.item()) != 1:
+        if rank == 0:
+            print(json.dumps({"parity_check": res}))
+        raise SystemExit("partitioned result differs from the serial loop: refusing to time it")
+    return res
 
 
 def summarize_profile(recs):
@@ -501,22 +610,40 @@ def main_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        s = reference_sample(args.n)
+        s = reference_sample(args.n, args.workload)
         if s:
             cpu = {k: s[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    also = None
+    if rank == 0 and world == 1 and not args.no_also and args.workload == "iso":
+        # after the headline regions: the other single-GPU configurations of BASELINE.json, so that they
+        # are in the driver's own record (only config[1] was driver-run)
+        del base
+        also = {}
+        try:
+            also["aniso_n64"] = also_aniso(lib, 64, 3)
+        except Exception as e:  # noqa: BLE001
+            also["aniso_n64"] = {"error": str(e)[:300]}
+        try:
+            also["adj_100M"] = also_adj(lib)
+        except Exception as e:  # noqa: BLE001
+            also["adj_100M"] = {"error": str(e)[:300]}
 
     if rank == 0:
         cfg = workload_config(args.n, args.workload)
         cfg["parallelism"] = "1 GPU" if world == 1 else "%d independent replicas (one box per GPU, no ghost exchange yet)" % world
         cfg["passes_per_step"] = npasses
         cfg["tets_per_step"] = "%d -> %d" % (nelems0, nelems1)
+        cfg["input_caches"] = ("the input mesh carries its derived R->E, R->V, F->V and the length + quality tags, measured "
+                               "before the timed region (the reference arm calls ask_lengths/ask_qualities first too); "
+                               "base.copy() shares them, so pass 0 pays no transit / measure_edges (~0.2 ms of the loop)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "wall_ms_per_step": wall_ms / args.steps, "syncs_per_step": None,
-            "peak_device_bytes": lib.peak_bytes(),
+            "peak_device_bytes": lib.peak_bytes(), "also": also,
         }
         print(json.dumps(line))
     if world > 1:
@@ -561,6 +688,10 @@ def main_b200_partitioned(args):
     D.share_stream(lib, device)   # torch, NCCL and the library on one stream: no host syncs between them
     n = args.n
     shape = box_shape(world)
+    parity = None
+    if not args.no_parity_check:
+        parity = partition_parity_check(lib, device, args.halo)
+        torch.cuda.empty_cache()
     base = build_box(float(shape[0]), float(shape[1]), float(shape[2]), shape[0] * n, shape[1] * n, shape[2] * n, lib=lib)
     h = 1.0 / n / 2.0
     base.add_tag(VERT, "metric", 1, np.full(base.nverts(), 1.0 / (h * h)))
@@ -690,7 +821,7 @@ def main_b200_partitioned(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
-            "peak_device_bytes": lib.peak_bytes(),
+            "peak_device_bytes": lib.peak_bytes(), "parity_check": parity,
         }
         print(json.dumps(line))
     if os.environ.get("OSHB_DIST_CPROFILE") and rank == 0:

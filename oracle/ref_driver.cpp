@@ -10,6 +10,8 @@
 // Modes:
 //   refine <dim> <n> <metric> <npasses|-1> <out_prefix> [minq] [askq]   per-pass dumps
 //   time   <dim> <n> <metric> [maxpasses]                              JSON timing line (CPU baseline)
+//   timeloops <dim> <n> <metric> <reps> <budget_s>                     the WHOLE loop, repeated on copies of one input
+//                                                                      mesh; one JSON line per repetition (bench.py --impl reference)
 //   box    <dim> <n> <out>                                             build_box dump only
 //   adjtime <n>                                                        invert_adj / reflect_down timing
 //   writeosh <dim> <n> <metric> <npasses> <path.osh> <dump>            binary::write + dump of the same mesh
@@ -271,6 +273,43 @@ static int mode_time(Library* lib, int argc, char** argv) {
   return 0;
 }
 
+
+// timeloops: the complete `while (refine_by_size)` loop, repeated `reps` times on shallow copies of the same
+// input mesh (the reference's Mesh copy shares its immutable arrays), stopping early when `budget_s` seconds
+// of wall time are used up. Prints one JSON line per repetition.
+static int mode_timeloops(Library* lib, int argc, char** argv) {
+  int dim = atoi(argv[2]);
+  int n = atoi(argv[3]);
+  int kind = atoi(argv[4]);
+  int reps = (argc > 5) ? atoi(argv[5]) : 1;
+  double budget = (argc > 6) ? atof(argv[6]) : 1e30;
+  auto base = make_box(lib, dim, n);
+  set_metric(&base, n, kind);
+  auto opts = AdaptOpts(&base);
+  opts.verbosity = SILENT;
+  base.ask_lengths();
+  base.ask_qualities();
+  int threads = 1;
+#ifdef OSHB_REF_OPENMP
+  threads = omp_get_max_threads();
+#endif
+  auto start = now();
+  for (int rep = 0; rep < reps; ++rep) {
+    Mesh mesh = base;
+    long long first = mesh.nelems();
+    int passes = 0;
+    auto t0 = now();
+    while (refine_by_size(&mesh, opts)) ++passes;
+    auto t1 = now();
+    printf("{\"impl\":\"reference\",\"threads\":%d,\"dim\":%d,\"n\":%d,\"metric\":%d,\"rep\":%d,\"passes\":%d,"
+           "\"nelems_before\":%lld,\"nelems_after\":%lld,\"seconds\":%.6f}\n",
+        threads, dim, n, kind, rep, passes, first, (long long)mesh.nelems(), t1 - t0);
+    fflush(stdout);
+    if (now() - start > budget) break;
+  }
+  return 0;
+}
+
 static int mode_box(Library* lib, int, char** argv) {
   int dim = atoi(argv[2]);
   int n = atoi(argv[3]);
@@ -341,6 +380,7 @@ int main(int argc, char** argv) {
   std::string mode = argv[1];
   if (mode == "refine") return mode_refine(&lib, argc, argv);
   if (mode == "time") return mode_time(&lib, argc, argv);
+  if (mode == "timeloops") return mode_timeloops(&lib, argc, argv);
   if (mode == "box") return mode_box(&lib, argc, argv);
   if (mode == "adjtime") return mode_adjtime(&lib, argc, argv);
   if (mode == "writeosh") return mode_writeosh(&lib, argc, argv);

@@ -19,6 +19,18 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     nx, ny, nz = (int(args[0]), int(args[1]), int(args[2])) if len(args) >= 3 else (256, 256, 254)
     lib = Lib(device=0).init()
+    out = run(lib, nx, ny, nz, profile="--profile" in sys.argv, log=sys.stderr)
+    if "--json" in sys.argv:
+        print(json.dumps(out))
+
+
+def run(lib, nx=256, ny=256, nz=254, profile=False, log=None):
+    """the microbench as a function (bench.py emits its result as `also.adj_100M`)"""
+    class _Null:
+        def write(self, *_):
+            pass
+    if log is None:
+        log = _Null()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -29,7 +41,7 @@ def main():
     m = build_box(1.0, 1.0, 1.0, nx, ny, nz, lib=lib)
     t_build = lib.timer_stop()
     nv, ne, nf, nr = (m.nents(d) for d in range(4))
-    print("build_box %dx%dx%d: V %d E %d F %d R %d in %.1f ms" % (nx, ny, nz, nv, ne, nf, nr, t_build), file=sys.stderr)
+    print("build_box %dx%dx%d: V %d E %d F %d R %d in %.1f ms" % (nx, ny, nz, nv, ne, nf, nr, t_build), file=log)
     c = lib.c
     out = {"mesh": {"nverts": nv, "nedges": ne, "nfaces": nf, "ntets": nr, "build_box_ms": t_build}, "peak_gbs": peak,
            "kernels": {}}
@@ -50,7 +62,7 @@ def main():
             lib.timer_start()
             fn()
             best = min(best, lib.timer_stop())
-        if "--profile" in sys.argv:
+        if profile:
             # per-kernel split of one more call (CUDA events around every launch)
             lib.profile_begin(None)
             fn()
@@ -58,13 +70,13 @@ def main():
             for name, ms in lib.profile_end():
                 k = name.split("\t")[0]
                 agg[k] = agg.get(k, 0.0) + ms
-            print("    " + "  ".join("%s %.2f" % kv for kv in sorted(agg.items(), key=lambda kv: -kv[1])), file=sys.stderr)
+            print("    " + "  ".join("%s %.2f" % kv for kv in sorted(agg.items(), key=lambda kv: -kv[1])), file=log)
         return best
 
     def report(name, ms, nbytes):
         gbs = nbytes / 1e9 / (ms / 1e3)
         out["kernels"][name] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": gbs, "frac_of_peak": gbs / peak}
-        print("%-34s %9.3f ms %9.1f GB/s  %5.1f%% of %.0f" % (name, ms, gbs, 100 * gbs / peak, peak), file=sys.stderr)
+        print("%-34s %9.3f ms %9.1f GB/s  %5.1f%% of %.0f" % (name, ms, gbs, 100 * gbs / peak, peak), file=log)
 
     # ---- invert_adj -------------------------------------------------------------------------
     for (hd, ld) in ((3, 0), (3, 2), (2, 1), (3, 1)):
@@ -99,9 +111,14 @@ def main():
     d_perm = lib.empty_device(nf, np.int32)
     ms = timeit(lambda: lib.check(c.oshb_sort_by_keys_i32(d_fv.ptr, C.c_int64(nf), C.c_int(3), d_perm.ptr)), reps=2)
     report("sort_by_keys i32 width 3 (n=%d)" % nf, ms, nf * (3 * 4 + 4))
-    ms = timeit(lambda: lib.check(c.oshb_sort_by_keys_i32(d_rv.ptr, C.c_int64(nr * 4), C.c_int(1), d_perm.ptr if nr * 4 <= nf else lib.empty_device(nr * 4, np.int32).ptr)), reps=2) if False else None
-    if "--json" in sys.argv:
-        print(json.dumps(out))
+    # a radix sort moves (word, index) pairs once per 8-bit digit: also report the rate per pass
+    nbits = max(1, int(nv - 1).bit_length())
+    npass = 3 * ((nbits + 7) // 8)
+    k = out["kernels"]["sort_by_keys i32 width 3 (n=%d)" % nf]
+    k["passes"] = npass
+    k["per_pass_gbs_16B_per_key"] = 16.0 * nf / 1e9 / (ms / npass / 1e3)
+    k["per_pass_frac_of_peak"] = k["per_pass_gbs_16B_per_key"] / peak
+    return out
 
 
 if __name__ == "__main__":
