@@ -67,6 +67,24 @@ int oshb_minmax_f64(const double* d_in, int64_t n, double* h_min, double* h_max)
 int oshb_sort_by_keys_i32(const int32_t* d_keys, int64_t n, int width, int32_t* d_perm);
 int oshb_sort_by_keys_i64(const int64_t* d_keys, int64_t n, int width, int32_t* d_perm);
 
+/* ---- array maps on device pointers (src/Omega_h_map.cpp) ---------------------------------------- *
+ * `width` values of `elem_bytes` (1, 4 or 8) bytes per entry; a2b holds na int32 indices.            */
+/* unmap: a_out[a] = b_data[a2b[a]]  (a gather).  src/Omega_h_map.cpp:74-87 */
+int oshb_unmap(const int32_t* d_a2b, int64_t na, const void* d_b_data, int width, int elem_bytes, void* d_a_out);
+/* map_into: b_data[a2b[a]] = a_data[a]  (a scatter; entries of b_data outside the image are left alone).
+ * src/Omega_h_map.cpp:25-37 */
+int oshb_map_into(const void* d_a_data, const int32_t* d_a2b, int64_t na, void* d_b_data, int width, int elem_bytes);
+/* expand_into: b_data[b] = a_data[a] for b in [a2b[a], a2b[a+1]); d_a2b are na+1 offsets, the last is nb.
+ * src/Omega_h_map.cpp:104-128 */
+int oshb_expand_into(const void* d_a_data, const int32_t* d_a2b_offsets, int64_t na, int64_t nb, void* d_b_data,
+    int width, int elem_bytes);
+/* mark_image: marks[b] = 1 iff b = a2b[a] for some a.  src/Omega_h_map.cpp:183-190 */
+int oshb_mark_image(const int32_t* d_a2b, int64_t na, int64_t nb, int8_t* d_marks);
+/* invert_injective_map: b2a[a2b[a]] = a, -1 elsewhere.  src/Omega_h_map.cpp:199-205 */
+int oshb_invert_injective_map(const int32_t* d_a2b, int64_t na, int64_t nb, int32_t* d_b2a);
+/* compound_maps: a2c[a] = b2c[a2b[a]].  src/Omega_h_map.cpp:157-165 */
+int oshb_compound_maps(const int32_t* d_a2b, int64_t na, const int32_t* d_b2c, int32_t* d_a2c);
+
 /* ---- adjacency derivation on device pointers --------------------------------------------- */
 /* invert_adj: upward adjacency (offsets nlow+1, entries nhigh*deg, codes nhigh*deg) from a
  * downward one; rows sorted by high index. d_down_codes may be NULL (target = vertices).
@@ -158,6 +176,31 @@ typedef struct oshb_adapt_opts {
   int32_t verbosity;
 } oshb_adapt_opts;
 int oshb_adapt_opts_init(int dim, oshb_adapt_opts* opts);
+
+/* TransferOpts::type_map (src/Omega_h_adapt.hpp:30-31, src/Omega_h_transfer.cpp:14-140): how a user tag is carried
+ * through a refine pass. The rule travels with the mesh (and its refined successors). Built-in names
+ * (coordinates, warp, metric, target_metric, class_id, class_dim, length, quality, global) need no rule; tags
+ * with no rule are not transferred, exactly as in the reference. Supported: INHERIT (same tag on every dimension),
+ * LINEAR_INTERP and METRIC (vertex reals), DENSITY and POINTWISE (element reals: children inherit the parent's
+ * value, src/Omega_h_transfer.cpp:309-335). CONSERVE and MOMENTUM_VELOCITY fail loudly at the next pass. */
+enum { OSHB_XFER_INHERIT = 0, OSHB_XFER_LINEAR_INTERP = 1, OSHB_XFER_METRIC = 2, OSHB_XFER_DENSITY = 3,
+  OSHB_XFER_CONSERVE = 4, OSHB_XFER_MOMENTUM_VELOCITY = 5, OSHB_XFER_POINTWISE = 6 };
+int oshb_mesh_set_transfer(oshb_mesh* m, const char* tag_name, int transfer_type);
+/* UserTransfer::refine (src/Omega_h_adapt.hpp:15-20, called at src/Omega_h_transfer.cpp:422-426): a process-wide
+ * callback run once per dimension at the end of every refine pass with the old mesh, the new mesh (add tags to it
+ * with oshb_mesh_add_tag) and the reference's maps as DEVICE arrays. NULL unregisters. */
+typedef struct oshb_user_transfer_maps {
+  int32_t prod_dim, nkeys, nprods, nsame;
+  const int32_t* d_keys2edges;         /* nkeys */
+  const int32_t* d_keys2midverts;      /* nkeys */
+  const int32_t* d_keys2prods;         /* nkeys + 1 */
+  const int32_t* d_prods2new_ents;     /* nprods */
+  const int32_t* d_same_ents2old_ents; /* nsame */
+  const int32_t* d_same_ents2new_ents; /* nsame */
+} oshb_user_transfer_maps;
+typedef void (*oshb_user_transfer_fn)(void* user, oshb_mesh* old_mesh, oshb_mesh* new_mesh,
+    const oshb_user_transfer_maps* maps);
+int oshb_set_user_transfer(oshb_user_transfer_fn fn, void* user);
 
 /* per-stage intermediates of one pass (used by parity tests; mirrors the locals of
  * refine_ghosted, src/Omega_h_refine.cpp:17-41) */

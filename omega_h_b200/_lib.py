@@ -49,13 +49,15 @@ SYMBOLS = [
     "oshb_peak_bytes", "oshb_dev_alloc", "oshb_dev_free", "oshb_h2d", "oshb_d2h",
     "oshb_offset_scan_i8", "oshb_offset_scan_i32", "oshb_offset_scan_i32_i64", "oshb_collect_marked",
     "oshb_max_i8", "oshb_minmax_f64", "oshb_sort_by_keys_i32", "oshb_sort_by_keys_i64",
+    "oshb_unmap", "oshb_map_into", "oshb_expand_into", "oshb_mark_image", "oshb_invert_injective_map",
+    "oshb_compound_maps",
     "oshb_invert_adj", "oshb_transit", "oshb_reflect_down", "oshb_find_unique",
     "oshb_measure_edges_metric", "oshb_measure_qualities", "oshb_libm_eval",
     "oshb_mesh_create", "oshb_mesh_destroy", "oshb_mesh_clone", "oshb_mesh_dim", "oshb_mesh_nents",
     "oshb_mesh_set_verts", "oshb_mesh_set_ents", "oshb_mesh_add_tag", "oshb_mesh_remove_tag", "oshb_mesh_ntags",
     "oshb_mesh_tag_info", "oshb_mesh_get_tag", "oshb_mesh_gather_tag", "oshb_mesh_ask_down", "oshb_mesh_ask_up", "oshb_mesh_ask_star",
     "oshb_mesh_ask_lengths", "oshb_mesh_ask_qualities", "oshb_build_box",
-    "oshb_adapt_opts_init", "oshb_refine_qualities", "oshb_mident_metrics", "oshb_find_indset",
+    "oshb_adapt_opts_init", "oshb_mesh_set_transfer", "oshb_set_user_transfer", "oshb_refine_qualities", "oshb_mident_metrics", "oshb_find_indset",
     "oshb_rep_vertex2md_order", "oshb_refine_by_size", "oshb_last_pass_stats",
     "oshb_pass_create", "oshb_pass_destroy", "oshb_pass_begin", "oshb_pass_restate", "oshb_pass_indset_round",
     "oshb_pass_select_keys", "oshb_pass_number", "oshb_pass_finish", "oshb_pass_size", "oshb_pass_get",

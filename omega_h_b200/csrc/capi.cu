@@ -242,6 +242,91 @@ int oshb_find_unique(const int32_t* d_hv2v, int64_t nhigh, int high_dim, int low
   OSHB_CATCH
 }
 
+// ---- transfer rules ---------------------------------------------------------------------------
+int oshb_mesh_set_transfer(oshb_mesh* m, const char* tag_name, int transfer_type) {
+  OSHB_TRY
+  OSHB_CHECK(m && tag_name && transfer_type >= XFER_INHERIT && transfer_type <= XFER_POINTWISE);
+  m->m.xfer_rules_[tag_name] = transfer_type;
+  OSHB_CATCH
+}
+namespace {
+oshb_user_transfer_fn g_user_fn = nullptr;
+void* g_user_ptr = nullptr;
+void user_transfer_trampoline(void*, Mesh* old_mesh, Mesh* new_mesh, UserTransferMaps const* mp) {
+  oshb_mesh old_h{*old_mesh};  // shallow: shares the arrays
+  oshb_mesh new_h{*new_mesh};
+  oshb_user_transfer_maps c;
+  c.prod_dim = mp->prod_dim;
+  c.nkeys = mp->nkeys;
+  c.nprods = mp->nprods;
+  c.nsame = mp->nsame;
+  c.d_keys2edges = mp->keys2edges;
+  c.d_keys2midverts = mp->keys2midverts;
+  c.d_keys2prods = mp->keys2prods;
+  c.d_prods2new_ents = mp->prods2new_ents;
+  c.d_same_ents2old_ents = mp->same_ents2old_ents;
+  c.d_same_ents2new_ents = mp->same_ents2new_ents;
+  g_user_fn(g_user_ptr, &old_h, &new_h, &c);
+  *new_mesh = new_h.m;  // picks up the tags the callback added
+}
+}  // namespace
+int oshb_set_user_transfer(oshb_user_transfer_fn fn, void* user) {
+  OSHB_TRY
+  g_user_fn = fn;
+  g_user_ptr = user;
+  user_transfer_hook().fn = fn ? user_transfer_trampoline : nullptr;
+  user_transfer_hook().user = nullptr;
+  OSHB_CATCH
+}
+
+// ---- maps -----------------------------------------------------------------------------------
+int oshb_unmap(const int32_t* d_a2b, int64_t na, const void* d_b_data, int width, int elem_bytes, void* d_a_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  OSHB_CHECK(na >= 0 && width >= 1);
+  unmap_bytes(d_a2b, na, d_b_data, width, elem_bytes, d_a_out);
+  sync_unless_shared();
+  OSHB_CATCH
+}
+int oshb_map_into(const void* d_a_data, const int32_t* d_a2b, int64_t na, void* d_b_data, int width, int elem_bytes) {
+  OSHB_TRY
+  init_ctx(-1);
+  OSHB_CHECK(na >= 0 && width >= 1);
+  map_into_bytes(d_a_data, d_a2b, na, d_b_data, width, elem_bytes);
+  sync_unless_shared();
+  OSHB_CATCH
+}
+int oshb_expand_into(const void* d_a_data, const int32_t* d_a2b_offsets, int64_t na, int64_t nb, void* d_b_data,
+    int width, int elem_bytes) {
+  OSHB_TRY
+  init_ctx(-1);
+  OSHB_CHECK(na >= 0 && nb >= 0 && width >= 1);
+  expand_into_bytes(d_a_data, d_a2b_offsets, na, nb, d_b_data, width, elem_bytes);
+  sync_unless_shared();
+  OSHB_CATCH
+}
+int oshb_mark_image(const int32_t* d_a2b, int64_t na, int64_t nb, int8_t* d_marks) {
+  OSHB_TRY
+  init_ctx(-1);
+  mark_image(d_a2b, na, nb, d_marks);
+  sync_unless_shared();
+  OSHB_CATCH
+}
+int oshb_invert_injective_map(const int32_t* d_a2b, int64_t na, int64_t nb, int32_t* d_b2a) {
+  OSHB_TRY
+  init_ctx(-1);
+  invert_injective_map(d_a2b, na, nb, d_b2a);
+  sync_unless_shared();
+  OSHB_CATCH
+}
+int oshb_compound_maps(const int32_t* d_a2b, int64_t na, const int32_t* d_b2c, int32_t* d_a2c) {
+  OSHB_TRY
+  init_ctx(-1);
+  compound_maps(d_a2b, na, d_b2c, d_a2c);
+  sync_unless_shared();
+  OSHB_CATCH
+}
+
 // ---- geometry ------------------------------------------------------------------------------
 int oshb_measure_edges_metric(int dim, int metric_ncomps, const int32_t* d_ev2v, const double* d_coords,
     const double* d_metrics, const int32_t* d_a2e, int32_t n, double* d_out) {

@@ -34,6 +34,9 @@ Mesh::Mesh() {
 
 void Mesh::set_ents(int ent_dim, Adj const& down) {
   OSHB_CHECK(ent_dim >= 1 && ent_dim <= 3);
+  // the reference asserts !has_ents(ent_dim) (src/Omega_h_mesh.cpp:88); re-setting entities here
+  // would leave derived adjacencies, the star and tags of this dimension stale
+  OSHB_CHECK(!has_adj_[ent_dim][ent_dim - 1]);
   int deg = simplex_degree(ent_dim, ent_dim - 1);
   nents_[ent_dim] = LO(down.ab2b.size() / deg);
   add_adj(ent_dim, ent_dim - 1, down);
@@ -196,7 +199,13 @@ bool Mesh::globals_are_identity(int d) {
 Mesh Mesh::copy_meta() const {
   Mesh m;
   m.dim_ = dim_;
+  m.xfer_rules_ = xfer_rules_;
   return m;
+}
+
+UserTransferHook& user_transfer_hook() {
+  static UserTransferHook h;
+  return h;
 }
 
 }  // namespace oshb

@@ -53,6 +53,30 @@ struct Tag {
   static int elem_bytes(int type) { return type == TAG_I8 ? 1 : (type == TAG_I32 ? 4 : 8); }
 };
 
+// Omega_h_Transfer (src/Omega_h_defines.hpp:29-37)
+enum XferType { XFER_INHERIT = 0, XFER_LINEAR_INTERP = 1, XFER_METRIC = 2, XFER_DENSITY = 3, XFER_CONSERVE = 4,
+  XFER_MOMENTUM_VELOCITY = 5, XFER_POINTWISE = 6 };
+
+// UserTransfer::refine (src/Omega_h_adapt.hpp:15-20): called once per dimension after the new mesh is
+// assembled, with the maps the reference hands to its virtual
+struct UserTransferMaps {
+  int prod_dim;
+  LO nkeys, nprods, nsame;
+  LO const* keys2edges;          // nkeys
+  LO const* keys2midverts;       // nkeys: new vertex at the midpoint of each key
+  LO const* keys2prods;          // nkeys + 1 offsets into prods2new_ents
+  LO const* prods2new_ents;      // nprods
+  LO const* same_ents2old_ents;  // nsame
+  LO const* same_ents2new_ents;  // nsame
+};
+class Mesh;
+typedef void (*UserTransferFn)(void* user, Mesh* old_mesh, Mesh* new_mesh, UserTransferMaps const* maps);
+struct UserTransferHook {
+  UserTransferFn fn = nullptr;
+  void* user = nullptr;
+};
+UserTransferHook& user_transfer_hook();
+
 struct AdaptOpts {
   // defaults of AdaptOpts(dim), src/Omega_h_adapt.cpp:52-85
   Real min_length_desired;
@@ -79,6 +103,13 @@ class Mesh {
   // identity and the refine pass skips that scan; verified on the device, never assumed.
   int globals_state_[4] = {0, 0, 0, 0};
   bool globals_are_identity(int d);
+  // TransferOpts::type_map (src/Omega_h_adapt.hpp:30-31): tag name -> Omega_h_Transfer; travels with
+  // the mesh through copy_meta, like the reference's opts travel with every adapt call
+  std::map<std::string, int> xfer_rules_;
+  int xfer_rule(std::string const& name) const {
+    auto it = xfer_rules_.find(name);
+    return it == xfer_rules_.end() ? -1 : it->second;
+  }
 
   Mesh();
   int dim() const { return dim_; }
@@ -140,6 +171,13 @@ LOs offset_scan(LOs a);
 LO last_of(LOs a);
 
 // ---- geometry / metric kernels (geom.cu) ------------------------------------------------
+// standalone maps on device pointers (maps.cu; src/Omega_h_map.cpp)
+void unmap_bytes(LO const* a2b, int64_t na, void const* b_data, int width, int elem_bytes, void* a_out);
+void map_into_bytes(void const* a_data, LO const* a2b, int64_t na, void* b_data, int width, int elem_bytes);
+void expand_into_bytes(void const* a_data, LO const* a2b, int64_t na, int64_t nb, void* b_data, int width, int elem_bytes);
+void mark_image(LO const* a2b, int64_t na, int64_t nb, I8* marks);
+void invert_injective_map(LO const* a2b, int64_t na, int64_t nb, LO* b2a);
+void compound_maps(LO const* a2b, int64_t na, LO const* b2c, LO* a2c);
 void libm_eval(int fn, Real const* x, int64_t n, Real* out);  // glibm.hpp functions elementwise (parity check entry)
 Reals measure_edges_metric(Mesh* mesh, LOs a2e, Reals metrics);     // src/Omega_h_shape.cpp:7-37 (a2e may be absent = all)
 Reals measure_edges_metric_raw(int dim, LOs ev2v, Reals coords, Reals metrics, int metric_ncomps, LOs a2e, LO n);

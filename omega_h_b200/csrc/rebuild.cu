@@ -236,8 +236,8 @@ static bool should_inherit(Mesh* mesh, Tag const& tag, int d) {
   // "own:*": partition bookkeeping of a distributed caller (omega_h_b200/dist.py), inherited like
   // the classification
   (void)d;
-  if (!(tag.name == "class_id" || tag.name == "class_dim" || tag.name == "momentum_velocity_fixed" ||
-          tag.name.compare(0, 4, "own:") == 0))
+  if (!(mesh->xfer_rule(tag.name) == XFER_INHERIT || tag.name == "class_id" || tag.name == "class_dim" ||
+          tag.name == "momentum_velocity_fixed" || tag.name.compare(0, 4, "own:") == 0))
     return false;
   for (int i = 0; i <= mesh->dim(); ++i) {
     Tag const* t = mesh->find_tag(i, tag.name);
@@ -686,15 +686,28 @@ void Rebuild::finish() {
       }
     }
     for (auto const& tag : mesh->tags_[d]) {
+      // the rules of src/Omega_h_transfer.cpp:20-140: built-in names, plus TransferOpts::type_map
+      // (Mesh::xfer_rules_) for user fields
       int kind = -1;
+      int const rule = mesh->xfer_rule(tag.name);
+      if (rule == XFER_CONSERVE || rule == XFER_MOMENTUM_VELOCITY)
+        fail(__FILE__, __LINE__, "transfer of '" + tag.name + "': OMEGA_H_CONSERVE / OMEGA_H_MOMENTUM_VELOCITY need the "
+            "reference's conservation machinery (src/Omega_h_conserve.cpp), which is outside this path");
       bool inherit = should_inherit(mesh, tag, d);
       if (inherit) kind = 0;
-      else if (d == VERT && tag.type == TAG_F64 && (tag.name == "coordinates" || tag.name == "warp")) kind = 1;
-      else if (d == VERT && tag.type == TAG_F64 && (tag.name == "metric" || tag.name == "target_metric") &&
+      else if (d == VERT && tag.type == TAG_F64 &&
+               (tag.name == "coordinates" || tag.name == "warp" || rule == XFER_LINEAR_INTERP)) kind = 1;
+      else if (d == VERT && tag.type == TAG_F64 &&
+               (tag.name == "metric" || tag.name == "target_metric" || rule == XFER_METRIC) &&
                (tag.ncomps == 1 || tag.ncomps == (dim * (dim + 1)) / 2)) kind = 2;
       else if (d == EDGE && tag.type == TAG_F64 && tag.name == "length" && tag.ncomps == 1) kind = 3;
       else if (d == dim && tag.type == TAG_F64 && tag.name == "quality" && tag.ncomps == 1) kind = 4;
-      if (kind < 0) continue;  // "global" is rebuilt; tags without a transfer rule are dropped
+      else if (d == dim && tag.type == TAG_F64 && (rule == XFER_DENSITY || rule == XFER_POINTWISE)) {
+        // transfer_density_refine / transfer_pointwise_refine: the children inherit the parent element's value
+        kind = 0;
+        inherit = true;
+      }
+      if (kind < 0) continue;  // "global" is rebuilt; tags without a transfer rule are dropped, as in the reference
       Tag nt = alloc_like(tag, nnew[d]);
       new_tags[d].push_back(nt);
       TagCopy tc;
@@ -854,6 +867,50 @@ void Rebuild::finish() {
     LOs list = collect_marked(prod_marks[dim]);
     Reals prod = measure_qualities(&new_mesh, list, new_mesh.get_reals(VERT, "metric"));
     scatter_by<Real>(prod.data(), new_tags[dim][s.new_index].f64.data(), list.data(), LO(list.size()), 1);
+  }
+  // ---- UserTransfer::refine (src/Omega_h_transfer.cpp:422-426), once per dimension ---------------------
+  if (user_transfer_hook().fn) {
+    for (int d = 0; d <= dim; ++d) {
+      LO const nold = mesh->nents(d);
+      LO const* o2n = tp.o2n[d];
+      // same entities: the surviving old entities in order, and where they went
+      Bytes same_marks(nold);
+      I8* sm = same_marks.data();
+      parallel_for(nold, OSHB_LAMBDA(LO e) { sm[e] = (o2n[e] >= 0) ? 1 : 0; }, "user_transfer(same marks)");
+      LOs same2old = collect_marked(same_marks);
+      LO const nsame = LO(same2old.size());
+      LOs same2new(nsame);
+      LO const* s2o = same2old.data();
+      LO* s2n = same2new.data();
+      parallel_for(nsame, OSHB_LAMBDA(LO i) { s2n[i] = o2n[s2o[i]]; }, "user_transfer(same2new)");
+      // products: contiguous per key from its base
+      Topo const t1 = tp;
+      LOs counts(nkeys);
+      LO* kc = counts.data();
+      parallel_for(nkeys, OSHB_LAMBDA(LO key) { kc[key] = key_nprods(t1, d, key); }, "user_transfer(counts)");
+      LOs k2p = offset_scan(counts);
+      LO const nprods = (nkeys > 0) ? last_of(k2p) : 0;
+      LOs p2n(nprods);
+      LO* pn = p2n.data();
+      LO const* kp = k2p.data();
+      LO const* pb = tp.pbase[d];
+      parallel_for(nkeys, OSHB_LAMBDA(LO key) {
+        for (LO i = kp[key]; i < kp[key + 1]; ++i) pn[i] = pb[key] + (i - kp[key]);
+      }, "user_transfer(prods2new)");
+      UserTransferMaps maps;
+      maps.prod_dim = d;
+      maps.nkeys = nkeys;
+      maps.nprods = nprods;
+      maps.nsame = nsame;
+      maps.keys2edges = k2e;
+      maps.keys2midverts = tp.pbase[0];
+      maps.keys2prods = kp;
+      maps.prods2new_ents = pn;
+      maps.same_ents2old_ents = s2o;
+      maps.same_ents2new_ents = s2n;
+      sync_stream();
+      user_transfer_hook().fn(user_transfer_hook().user, mesh, &new_mesh, &maps);
+    }
   }
   *mesh = new_mesh;
 }

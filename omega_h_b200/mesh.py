@@ -20,6 +20,11 @@ from ._lib import AdaptOptsC, F64, I8, I32, I64, NP_OF, TYPE_OF, OshbError, Pass
 VERT, EDGE, FACE, REGION = 0, 1, 2, 3
 
 
+# Omega_h_Transfer (src/Omega_h_defines.hpp:29-37)
+OMEGA_H_INHERIT, OMEGA_H_LINEAR_INTERP, OMEGA_H_METRIC, OMEGA_H_DENSITY, OMEGA_H_CONSERVE, OMEGA_H_MOMENTUM_VELOCITY, \
+    OMEGA_H_POINTWISE = range(7)
+
+
 def simplex_degree(from_dim, to_dim):
     if from_dim == to_dim:
         return 1
@@ -127,6 +132,11 @@ class Mesh:
                                                     C.c_int(ncomps), _ptr(a), C.c_int(1), C.c_int(int(internal))))
 
     set_tag = add_tag
+
+    def set_transfer(self, name, transfer_type):
+        """TransferOpts::type_map[name] = transfer_type (src/Omega_h_adapt.hpp:30): how a user tag is carried
+        through refine passes; see OMEGA_H_INHERIT ... OMEGA_H_POINTWISE below."""
+        self.lib.check(self.lib.c.oshb_mesh_set_transfer(self.h, name.encode(), C.c_int(int(transfer_type))))
 
     def remove_tag(self, ent_dim, name):
         self.lib.check(self.lib.c.oshb_mesh_remove_tag(self.h, C.c_int(ent_dim), name.encode()))

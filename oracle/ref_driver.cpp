@@ -8,7 +8,9 @@
 // output mesh into a flat record file ("OSHD1") that tests/ read with numpy.
 //
 // Modes:
-//   refine <dim> <n> <metric> <npasses|-1> <out_prefix> [minq] [askq]   per-pass dumps
+//   refine <dim> <n> <metric> <npasses|-1> <out_prefix> [minq] [askq] [userfields]   per-pass dumps; userfields=1 adds
+//          four user tags carried by TransferOpts::type_map: "temperature" (LINEAR_INTERP), "aux_metric" (METRIC),
+//          "mat_id" on every dimension (INHERIT), "rho" on elements (DENSITY)
 //   time   <dim> <n> <metric> [maxpasses]                              JSON timing line (CPU baseline)
 //   timeloops <dim> <n> <metric> <reps> <budget_s>                     the WHOLE loop, repeated on copies of one input
 //                                                                      mesh; one JSON line per repetition (bench.py --impl reference)
@@ -196,6 +198,38 @@ static int mode_refine(Library* lib, int argc, char** argv) {
   opts.verbosity = SILENT;
   if (argc > 7 && atof(argv[7]) > 0) opts.min_quality_allowed = atof(argv[7]);
   bool askq = (argc > 8) ? atoi(argv[8]) != 0 : true;
+  bool userfields = (argc > 9) ? atoi(argv[9]) != 0 : false;
+  if (userfields) {
+    // user fields carried through the pass by TransferOpts::type_map (src/Omega_h_adapt.hpp:30)
+    auto coords = mesh.coords();
+    auto nv = mesh.nverts();
+    Write<Real> temp(nv), auxm(nv);
+    auto f = OMEGA_H_LAMBDA(LO v) {
+      Real sum = 0;
+      for (Int j = 0; j < dim; ++j) sum += (j + 1) * coords[v * dim + j];
+      temp[v] = sum;
+      auxm[v] = metric_eigenvalue_from_length(0.05 + 0.1 * coords[v * dim]);
+    };
+    parallel_for(nv, f);
+    mesh.add_tag(VERT, "temperature", 1, Reals(temp));
+    mesh.add_tag(VERT, "aux_metric", 1, Reals(auxm));
+    for (Int d = 0; d <= dim; ++d) {
+      auto cid = mesh.get_array<ClassId>(d, "class_id");
+      auto cdim = mesh.get_array<I8>(d, "class_dim");
+      Write<LO> mat(mesh.nents(d));
+      auto g = OMEGA_H_LAMBDA(LO e) { mat[e] = cid[e] * 7 + cdim[e]; };
+      parallel_for(mesh.nents(d), g);
+      mesh.add_tag(d, "mat_id", 1, LOs(mat));
+    }
+    Write<Real> rho(mesh.nelems());
+    auto h = OMEGA_H_LAMBDA(LO e) { rho[e] = 1.0 + (e % 17) * 0.25; };
+    parallel_for(mesh.nelems(), h);
+    mesh.add_tag(dim, "rho", 1, Reals(rho));
+    opts.xfer_opts.type_map["temperature"] = OMEGA_H_LINEAR_INTERP;
+    opts.xfer_opts.type_map["aux_metric"] = OMEGA_H_METRIC;
+    opts.xfer_opts.type_map["mat_id"] = OMEGA_H_INHERIT;
+    opts.xfer_opts.type_map["rho"] = OMEGA_H_DENSITY;
+  }
   for (int pass = 0; npasses < 0 || pass < npasses; ++pass) {
     if (kind == 3 && pass > 0) {
       set_metric(&mesh, n, kind);
@@ -207,6 +241,7 @@ static int mode_refine(Library* lib, int argc, char** argv) {
     d.scalarf("opts:min_quality_allowed", opts.min_quality_allowed);
     d.scalar("metric_kind", kind);
     d.scalar("box_n", n);
+    for (auto const& kv : opts.xfer_opts.type_map) d.scalar("xfer:" + kv.first, int(kv.second));
     dump_mesh(d, "in:", &mesh);
     /* intermediates, recomputed with the reference's own functions on a shallow copy
        (arrays are immutable and shared; src/Omega_h_refine.cpp:17-41) */

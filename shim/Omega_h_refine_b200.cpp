@@ -132,8 +132,15 @@ bool refine_by_size(Mesh* mesh, AdaptOpts const& opts) {
   OMEGA_H_CHECK(mesh->comm()->size() == 1);  // partitioned meshes go through the oshb_pass_* stages
   OMEGA_H_CHECK(mesh->family() == OMEGA_H_SIMPLEX);
   mesh->ask_lengths();  // the reference's contract: "length" is cached on the mesh after this call
+  // UserTransfer virtuals take Omega_h::Mesh objects; this host-resident variant cannot hand them device
+  // meshes. (The C ABI has the hook: oshb_set_user_transfer with the same maps as device arrays.)
+  OMEGA_H_CHECK(!opts.xfer_opts.user_xfer);
   Handle h;
   upload(mesh, h);
+  // TransferOpts::type_map (src/Omega_h_adapt.hpp:30): the Omega_h_Transfer values are the ABI's
+  for (auto const& kv : opts.xfer_opts.type_map) {
+    check(oshb_mesh_set_transfer(h.m, kv.first.c_str(), int(kv.second)), kv.first.c_str());
+  }
   oshb_adapt_opts o;
   check(oshb_adapt_opts_init(mesh->dim(), &o), "adapt_opts_init");
   o.min_length_desired = opts.min_length_desired;

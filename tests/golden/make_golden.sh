@@ -16,6 +16,9 @@ $R refine 3  3 0 2 $T/d3n3m0 > /dev/null      # non-power-of-two grid (inexact c
 $R refine 3  4 2 2 $T/d3n4m2 > /dev/null      # 3-D anisotropic, distinct eigenvalues
 $R refine 3  4 1 1 $T/d3n4m1 > /dev/null      # 3-D anisotropic, repeated eigenvalues
 $R refine 3  4 3 3 $T/d3n4m3 0.47 > /dev/null # corner_test.cpp metric + min_quality_allowed=0.47
+# user fields through TransferOpts::type_map: temperature LINEAR_INTERP, aux_metric METRIC, mat_id INHERIT, rho DENSITY
+$R refine 3  3 0 2 $T/d3n3m0x 0 1 1 > /dev/null
+$R refine 2  6 1 2 $T/d2n6m1x 0 1 1 > /dev/null
 for f in $T/*.oshd; do gzip -9 -n -c $f > $(basename $f).gz; done
 rm -rf $T
 ls -la *.gz | awk '{s+=$5} END {print NR, "fixtures,", s, "bytes"}'

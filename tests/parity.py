@@ -32,6 +32,9 @@ def mesh_from_fixture(fx, lib, prefix="in:", Mesh=None):
                 name = k[len(tp):]
                 nc = int(fx[k + ":ncomps"][0])
                 m.add_tag(d, name, nc, fx[k], internal=True)
+    for k in fx:
+        if k.startswith("xfer:"):   # TransferOpts::type_map entries of the reference run
+            m.set_transfer(k[5:], int(fx[k][0]))
     return m
 
 
