@@ -118,49 +118,132 @@ Adj invert_adj(Adj const& down, int nlows_per_high, LO nlows) {
 }
 
 // ---------------------------------------------------------------------------------------
-// transit: two-level downward adjacency through the upward template and the alignment
-// algebra (src/Omega_h_adj.cpp:443-510). One thread per high entity.
+// transit: the two-level downward adjacency high -> low through the stored high -> mid and
+// mid -> low rows (what src/Omega_h_adj.cpp:443-510 computes; R->E from R->F o F->E with codes,
+// F->V from F->E o E->V, R->V from R->E o E->V).
+//
+// Mid-centric formulation, one thread per high entity, everything sized at compile time:
+//   1. the high's mid row and its alignment codes are read once (16-byte / 4-byte vector loads for
+//      tet -> faces);
+//   2. for every mid the code is turned ONCE into a "position word": 2 bits per canonical slot w
+//      giving where the mid stores its w-th low as seen from the high (the inverse alignment applied
+//      to w). A face shared by three template slots (tet edges 0..2 all come from face 0) is decoded
+//      once, not three times;
+//   3. every template slot then is one field extract + one gathered load; for low = edges the output
+//      code is the parity of three flips (high->mid flip, stored mid->low direction, template flip).
+// Algorithmic bytes: 5*N*n_mid in + 5*N*n_low out (+ the gathered mid rows, shared by neighbours).
 // ---------------------------------------------------------------------------------------
-Adj transit(Adj const& h2m, Adj const& m2l, int high_dim, int low_dim) {
-  OSHB_CHECK(low_dim == 0 || low_dim == 1);
-  int const mid_dim = low_dim + 1;
-  OSHB_CHECK(high_dim > mid_dim);
-  int const nmids_per_high = simplex_degree(high_dim, mid_dim);
-  int const nlows_per_mid = simplex_degree(mid_dim, low_dim);
-  int const nlows_per_high = simplex_degree(high_dim, low_dim);
-  int64_t const nhighs = h2m.ab2b.size() / nmids_per_high;
-  LOs hl2l(nhighs * nlows_per_high);
-  Bytes codes;
-  if (low_dim == 1) codes = Bytes(nhighs * nlows_per_high);
-  LO const* hm2m = h2m.ab2b.data();
-  I8 const* m2hm_codes = h2m.codes.data();
-  LO const* ml2l = m2l.ab2b.data();
-  I8 const* ml_codes = m2l.codes.exists() ? m2l.codes.data() : nullptr;
-  LO* out = hl2l.data();
-  I8* cout = codes.exists() ? codes.data() : nullptr;
-  OSHB_CHECK(m2hm_codes != nullptr);
+template <int HD, int LD>
+struct TransitShape {
+  static constexpr int MD = LD + 1;
+  static constexpr int NM = (HD == 3) ? (MD == 2 ? 4 : 6) : 3;  // mids per high
+  static constexpr int NLM = MD + 1;                            // lows per mid (simplex)
+  static constexpr int NL = (HD == 3) ? (LD == 1 ? 6 : 4) : 3;  // lows per high
+  // first upward use of low slot s inside the high: (mid slot, slot of the low inside that mid, flipped)
+  // tet edges {f0:2, f0:1, f0:0, f1:2, f2:2, f3:2} all flipped; tet verts {e0:0, e1:0, e2:0, e5:1};
+  // tri verts {e0:0, e1:0, e2:0}   (src/Omega_h_simplex.hpp:142-229, first entry of each list)
+  static OSHB_HD int mid_slot(int s) {
+    if (HD == 3 && LD == 1) return s < 3 ? 0 : s - 2;
+    if (HD == 3 && LD == 0) return s < 3 ? s : 5;
+    return s;
+  }
+  static OSHB_HD int low_slot(int s) {
+    if (HD == 3 && LD == 1) return s < 3 ? 2 - s : 2;
+    if (HD == 3 && LD == 0) return s < 3 ? 0 : 1;
+    return 0;
+  }
+  static constexpr bool template_flip = (HD == 3 && LD == 1);
+};
+
+// where a mid of NLM lows stores canonical slot w, for the code the HIGH holds of that mid:
+// 2 bits per w. Inverse alignment: a flip is its own inverse, a pure rotation r inverts to n - r.
+template <int NLM, int LD>
+OSHB_HD unsigned position_word(I8 code) {
+  int const rot = code_rotation(code);
+  bool const flip = code_is_flipped(code);
+  int const back = flip ? rot : mod_small(NLM - rot, NLM);
+  unsigned word = 0;
+#pragma unroll
+  for (int w = 0; w < NLM; ++w) {
+    int r = mod_small(w + back, NLM);
+    int p = flip ? (LD == 0 ? mod_small(NLM - r, NLM) : NLM - 1 - r) : r;
+    word |= unsigned(p) << (2 * w);
+  }
+  return word;
+}
+
+template <int HD, int LD>
+static void transit_rows(LO const* hm2m, I8 const* hm_codes, LO const* ml2l, I8 const* ml_codes, int64_t nhighs,
+    LO* out, I8* cout) {
+  typedef TransitShape<HD, LD> S;
+  algo_bytes(nhighs * 5 * (S::NM + S::NL));
   parallel_for(nhighs, OSHB_LAMBDA(LO h) {
-    int64_t const hl_begin = int64_t(h) * nlows_per_high;
-    int64_t const hm_begin = int64_t(h) * nmids_per_high;
-    for (int hl = 0; hl < nlows_per_high; ++hl) {
-      TemplateUp ut = simplex_up_template0(high_dim, low_dim, hl);
-      LO m = hm2m[hm_begin + ut.up];
-      I8 m2hm_code = m2hm_codes[hm_begin + ut.up];
-      I8 hm2m_code = invert_alignment(nlows_per_mid, m2hm_code);
-      int ml = align_index(nlows_per_mid, low_dim, ut.which_down, hm2m_code);
-      int64_t ml_begin = int64_t(m) * nlows_per_mid;
-      out[hl_begin + hl] = ml2l[ml_begin + ml];
-      if (low_dim == 1) {
-        bool region_face_flipped = code_is_flipped(hm2m_code);
-        bool face_edge_flipped = (code_rotation(ml_codes[ml_begin + ml]) == 1);
-        bool flipped = region_face_flipped ^ face_edge_flipped ^ ut.is_flipped;
-        cout[hl_begin + hl] = make_code(false, int(flipped), 0);
+    LO mid[S::NM];
+    I8 mcode[S::NM];
+#ifndef OSHB_EMU
+    if (S::NM == 4) {
+      int4 q = reinterpret_cast<int4 const*>(hm2m)[h];
+      mid[0] = q.x;
+      mid[1] = q.y;
+      mid[2] = q.z;
+      mid[3] = q.w;
+      unsigned c4 = reinterpret_cast<unsigned const*>(hm_codes)[h];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mcode[j & (S::NM - 1)] = I8((c4 >> (8 * j)) & 0xffu);
+    } else
+#endif
+    {
+#pragma unroll
+      for (int j = 0; j < S::NM; ++j) {
+        mid[j] = hm2m[int64_t(h) * S::NM + j];
+        mcode[j] = hm_codes[int64_t(h) * S::NM + j];
       }
     }
+    unsigned pos[S::NM];
+#pragma unroll
+    for (int j = 0; j < S::NM; ++j) pos[j] = position_word<S::NLM, LD>(mcode[j]);
+    LO low[S::NL];
+    I8 lcode[S::NL];
+#pragma unroll
+    for (int s = 0; s < S::NL; ++s) {
+      int const j = S::mid_slot(s);
+      int const p = int((pos[j] >> (2 * S::low_slot(s))) & 3u);
+      int64_t const at = int64_t(mid[j]) * S::NLM + p;
+      low[s] = ml2l[at];
+      if (LD == 1) {
+        // the edge runs backwards in the high iff an odd number of: high->face flip, the face stores
+        // the edge reversed (rotation 1 of a 2-vertex entity), the template's own flip
+        bool rev = code_is_flipped(mcode[j]) ^ (code_rotation(ml_codes[at]) == 1) ^ S::template_flip;
+        lcode[s] = make_code(false, int(rev), 0);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S::NL; ++s) {
+      out[int64_t(h) * S::NL + s] = low[s];
+      if (LD == 1) cout[int64_t(h) * S::NL + s] = lcode[s];
+    }
   }, "transit");
+}
+
+Adj transit(Adj const& h2m, Adj const& m2l, int high_dim, int low_dim) {
+  OSHB_CHECK(low_dim == 0 || low_dim == 1);
+  OSHB_CHECK(high_dim > low_dim + 1 && high_dim <= 3);
+  OSHB_CHECK(h2m.codes.exists());
+  int const nmids_per_high = simplex_degree(high_dim, low_dim + 1);
+  int const nlows_per_high = simplex_degree(high_dim, low_dim);
+  int64_t const nhighs = h2m.ab2b.size() / nmids_per_high;
   Adj a;
-  a.ab2b = hl2l;
-  a.codes = codes;
+  a.ab2b = LOs(nhighs * nlows_per_high);
+  if (low_dim == 1) {
+    OSHB_CHECK(high_dim == 3 && m2l.codes.exists());
+    a.codes = Bytes(nhighs * nlows_per_high);
+    transit_rows<3, 1>(h2m.ab2b.data(), h2m.codes.data(), m2l.ab2b.data(), m2l.codes.data(), nhighs, a.ab2b.data(),
+        a.codes.data());
+  } else if (high_dim == 3) {
+    transit_rows<3, 0>(h2m.ab2b.data(), h2m.codes.data(), m2l.ab2b.data(), nullptr, nhighs, a.ab2b.data(), nullptr);
+  } else {
+    transit_rows<2, 0>(h2m.ab2b.data(), h2m.codes.data(), m2l.ab2b.data(), nullptr, nhighs, a.ab2b.data(), nullptr);
+  }
   return a;
 }
 

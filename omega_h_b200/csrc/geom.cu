@@ -171,83 +171,6 @@ Reals get_mident_metrics(Mesh* mesh, int ent_dim, LOs a2e, Reals v2m) {
   fail(__FILE__, __LINE__, "get_mident_metrics: unsupported metric ncomps");
 }
 
-// ---------------------------------------------------------------------------------------
-// refine_qualities (src/Omega_h_refine_qualities.cpp:34-86): for each candidate edge the
-// minimum quality over the 2*deg children its split would create.
-// ---------------------------------------------------------------------------------------
-template <int dim, int mdim>
-static Reals refine_qualities_tmpl(LO const* cands, LO ncands, LO const* ev2v, LO const* cv2v, LO const* e2ec,
-    LO const* ec2c, I8 const* ec_codes, Real const* coords, Real const* vert_metrics, Real const* midpt_metrics) {
-  Reals out(ncands);
-  Real* o = out.data();
-  parallel_for(ncands, OSHB_LAMBDA(LO cand) {
-    LO e = cands[cand];
-    Vec<dim> ep0 = get_vec<dim>(coords, ev2v[int64_t(e) * 2 + 0]);
-    Vec<dim> ep1 = get_vec<dim>(coords, ev2v[int64_t(e) * 2 + 1]);
-    Vec<dim> midp = (ep0 + ep1) / 2.;
-    Mat<mdim> midm = Symm<mdim>::get(midpt_metrics, cand);
-    Real minqual = 1.0;
-    for (LO ec = e2ec[e]; ec < e2ec[e + 1]; ++ec) {
-      LO c = ec2c[ec];
-      I8 code = ec_codes[ec];
-      int cce = code_which_down(code);
-      int rot = code_rotation(code);
-      LO ccv2v[dim + 1];
-      for (int k = 0; k <= dim; ++k) ccv2v[k] = cv2v[int64_t(c) * (dim + 1) + k];
-      for (int eev = 0; eev < 2; ++eev) {
-        int cev = eev ^ rot;
-        int ccv = simplex_down_template(dim, EDGE, cce, cev);
-        int ccs = simplex_opposite_template(dim, VERT, ccv);
-        LO csv2v[dim];
-        Vec<dim> ncp[dim + 1];
-        for (int csv = 0; csv < dim; ++csv) {
-          int ccv2 = simplex_down_template(dim, dim - 1, ccs, csv);
-          LO v2 = ccv2v[ccv2];
-          csv2v[csv] = v2;
-          ncp[csv] = get_vec<dim>(coords, v2);
-        }
-        ncp[dim] = midp;
-        if (dim == 3) {  // flip_new_elem (src/Omega_h_refine_topology.hpp:35-58)
-          LO tv = csv2v[1];
-          csv2v[1] = csv2v[2];
-          csv2v[2] = tv;
-          Vec<dim> tp = ncp[1];
-          ncp[1] = ncp[2];
-          ncp[2] = tp;
-        }
-        Mat<mdim> ms[dim + 1];
-        for (int csv = 0; csv < dim; ++csv) ms[csv] = Symm<mdim>::get(vert_metrics, csv2v[csv]);
-        ms[dim] = midm;
-        Mat<mdim> m = maxdet_metric<mdim, dim + 1>(ms);
-        Real cqual = metric_element_quality<dim, mdim>(ncp, m);
-        minqual = (cqual < minqual) ? cqual : minqual;  // min2(minqual, cqual)
-      }
-    }
-    o[cand] = minqual;
-  }, "refine_qualities");
-  return out;
-}
-
-Reals refine_qualities(Mesh* mesh, LOs cands2edges) {
-  int dim = mesh->dim();
-  LO ncands = LO(cands2edges.size());
-  if (ncands == 0) return Reals(0);
-  Reals vert_metrics = mesh->get_reals(VERT, "metric");
-  int ncomps = mesh->metric_ncomps();
-  Reals midpt = get_mident_metrics(mesh, EDGE, cands2edges, vert_metrics);
-  LOs ev2v = mesh->ask_verts_of(EDGE);
-  LOs cv2v = mesh->ask_verts_of(dim);
-  Adj e2c = mesh->ask_up(EDGE, dim);
-  Reals coords = mesh->coords();
-#define OSHB_RQ(D, M)                                                                                         \
-  return refine_qualities_tmpl<D, M>(cands2edges.data(), ncands, ev2v.data(), cv2v.data(), e2c.a2ab.data(), \
-      e2c.ab2b.data(), e2c.codes.data(), coords.data(), vert_metrics.data(), midpt.data())
-  if (dim == 3 && ncomps == 6) OSHB_RQ(3, 3);
-  if (dim == 2 && ncomps == 3) OSHB_RQ(2, 2);
-  if (dim == 3 && ncomps == 1) OSHB_RQ(3, 1);
-  if (dim == 2 && ncomps == 1) OSHB_RQ(2, 1);
-#undef OSHB_RQ
-  fail(__FILE__, __LINE__, "refine_qualities: unsupported (dim, metric ncomps)");
-}
+// refine_qualities lives in select.cu: the per-edge entry point reads back the element-centric evaluation.
 
 }  // namespace oshb

@@ -113,8 +113,40 @@ static Reals edge_midpoint_metrics(LO const* ev2v, Real const* v2m, I8 const* ca
 }
 
 // ---------------------------------------------------------------------------------------
-// cavity qualities, element-centric (refine_qualities, src/Omega_h_refine_qualities.cpp:34-86)
+// cavity qualities, element-centric (what refine_qualities, src/Omega_h_refine_qualities.cpp:34-86,
+// computes per candidate edge by walking its upward row).
+//
+// Splitting edge (a, b) of an element at its midpoint M gives two children: the element with a
+// replaced by M and the element with b replaced by M. The reference lists a child's vertices as
+// "the side opposite the replaced vertex, in side-template order, tets flipped, then M"
+// (refine_topology: flip_new_elem) -- floating-point results depend on that order, so it is
+// reproduced as a packed table: child_slot<dim>(gone, k) = parent-local index of child vertex k.
+//   tets: gone 0 -> (1,3,2)  1 -> (2,3,0)  2 -> (0,3,1)  3 -> (0,1,2);  tris: 0 -> (1,2)  1 -> (2,0)  2 -> (0,1)
 // ---------------------------------------------------------------------------------------
+template <int dim>
+OSHB_HD int child_slot(int gone, int k) {
+  if (dim == 3) return int((0x91c3adu >> (2 * (3 * gone + k))) & 3u);  // 2-bit fields, (gone, k) row-major
+  return mod_small(gone + 1 + k, 3);
+}
+
+// quality, in the max-determinant metric of its vertices, of the child of an element (parent vertices pv)
+// whose local vertex `gone` moves to the split point (position midp, metric midm)
+template <int dim, int mdim>
+OSHB_HD Real split_child_quality(LO const* pv, int gone, Vec<dim> midp, Mat<mdim> midm, Real const* coords,
+    Real const* vert_metrics) {
+  Vec<dim> x[dim + 1];
+  Mat<mdim> ms[dim + 1];
+#pragma unroll
+  for (int k = 0; k < dim; ++k) {
+    LO v = pv[child_slot<dim>(gone, k)];
+    x[k] = get_vec<dim>(coords, v);
+    ms[k] = Symm<mdim>::get(vert_metrics, v);
+  }
+  x[dim] = midp;
+  ms[dim] = midm;
+  return metric_element_quality<dim, mdim>(x, maxdet_metric<mdim, dim + 1>(ms));
+}
+
 template <int dim, int mdim>
 static void cavity_qualities_tmpl(LO nelems, LO const* ce2e, I8 const* ce_codes, LO const* cv2v, LO const* ev2v,
     I8 const* cand, Real const* coords, Real const* vert_metrics, Real const* edge_mid, unsigned long long* qord) {
@@ -131,48 +163,88 @@ static void cavity_qualities_tmpl(LO nelems, LO const* ce2e, I8 const* ce_codes,
   LO const* act = active.data();
   algo_bytes(int64_t(nactive) * (4 + 4 + 1 + (dim + 1) * 4 + 8));
   parallel_for(nactive, OSHB_LAMBDA(LO a) {
-    LO i = act[a];
-    LO e = ce2e[i];
-    LO c = i / nce;
-    int cce = i - c * nce;
-    int rot = code_rotation(ce_codes[i]);
-    Vec<dim> ep0 = get_vec<dim>(coords, ev2v[int64_t(e) * 2 + 0]);
-    Vec<dim> ep1 = get_vec<dim>(coords, ev2v[int64_t(e) * 2 + 1]);
-    Vec<dim> midp = (ep0 + ep1) / 2.;
-    Mat<mdim> midm = Symm<mdim>::get(edge_mid, e);
-    LO ccv2v[dim + 1];
-    for (int k = 0; k <= dim; ++k) ccv2v[k] = cv2v[int64_t(c) * (dim + 1) + k];
-    Real minqual = 1.0;
-    for (int eev = 0; eev < 2; ++eev) {
-      int cev = eev ^ rot;
-      int ccv = simplex_down_template(dim, EDGE, cce, cev);
-      int ccs = simplex_opposite_template(dim, VERT, ccv);
-      LO csv2v[dim];
-      Vec<dim> ncp[dim + 1];
-      for (int csv = 0; csv < dim; ++csv) {
-        LO v2 = ccv2v[simplex_down_template(dim, dim - 1, ccs, csv)];
-        csv2v[csv] = v2;
-        ncp[csv] = get_vec<dim>(coords, v2);
-      }
-      ncp[dim] = midp;
-      if (dim == 3) {  // flip_new_elem (src/Omega_h_refine_topology.hpp:35-58)
-        LO tv = csv2v[1];
-        csv2v[1] = csv2v[2];
-        csv2v[2] = tv;
-        Vec<dim> tpp = ncp[1];
-        ncp[1] = ncp[2];
-        ncp[2] = tpp;
-      }
-      Mat<mdim> ms[dim + 1];
-      for (int csv = 0; csv < dim; ++csv) ms[csv] = Symm<mdim>::get(vert_metrics, csv2v[csv]);
-      ms[dim] = midm;
-      Mat<mdim> m = maxdet_metric<mdim, dim + 1>(ms);
-      Real cqual = metric_element_quality<dim, mdim>(ncp, m);
-      minqual = (cqual < minqual) ? cqual : minqual;
-    }
-    unsigned long long mine = ord_of_f64(minqual);
+    LO const i = act[a];
+    LO const e = ce2e[i];
+    LO const c = i / nce;
+    int const local_edge = i - c * nce;
+    LO pv[dim + 1];
+#pragma unroll
+    for (int k = 0; k <= dim; ++k) pv[k] = cv2v[int64_t(c) * (dim + 1) + k];
+    Vec<dim> const midp = (get_vec<dim>(coords, ev2v[int64_t(e) * 2 + 0]) + get_vec<dim>(coords, ev2v[int64_t(e) * 2 + 1])) / 2.;
+    Mat<mdim> const midm = Symm<mdim>::get(edge_mid, e);
+    // children in the order (first endpoint of the EDGE replaced, second replaced): the element sees the
+    // edge reversed when its code has rotation 1
+    int const rot = code_rotation(ce_codes[i]);
+    Real q0 = split_child_quality<dim, mdim>(pv, simplex_down_template(dim, EDGE, local_edge, rot), midp, midm, coords, vert_metrics);
+    Real q1 = split_child_quality<dim, mdim>(pv, simplex_down_template(dim, EDGE, local_edge, 1 ^ rot), midp, midm, coords, vert_metrics);
+    Real worst = 1.0;
+    worst = (q0 < worst) ? q0 : worst;
+    worst = (q1 < worst) ? q1 : worst;
+    unsigned long long mine = ord_of_f64(worst);
     if (mine < qord[e]) atomic_min_u64(&qord[e], mine);  // a stale read only costs an extra atomic
   }, "cavity_qualities");
+}
+
+// per-edge worst child quality of the marked edges as order-preserving integers (image of 1.0 elsewhere),
+// + the midpoint metrics of the marked edges
+static DArr<GO> cavity_qord_of_marked(Mesh* mesh, I8 const* cand, Reals* edge_mid_out) {
+  int const dim = mesh->dim();
+  LO const nedges = mesh->nedges();
+  LO const nelems = mesh->nelems();
+  Adj c2e = mesh->ask_down(dim, EDGE);
+  LOs cv2v = mesh->ask_verts_of(dim);
+  LOs ev2v = mesh->ask_verts_of(EDGE);
+  Reals coords = mesh->coords();
+  Reals vert_metrics = mesh->get_reals(VERT, "metric");
+  int const ncomps = mesh->metric_ncomps();
+  DArr<GO> qord_a(nedges);
+  unsigned long long* qord = reinterpret_cast<unsigned long long*>(qord_a.data());
+  {
+    unsigned long long const one = ord_of_f64(1.0);
+    parallel_for(nedges, OSHB_LAMBDA(LO e) { qord[e] = one; }, "qualities(init)");
+  }
+  Reals edge_mid;
+#define OSHB_CQ(D, M)                                                                                       \
+  {                                                                                                         \
+    edge_mid = edge_midpoint_metrics<M>(ev2v.data(), vert_metrics.data(), cand, nedges, mesh->nverts());    \
+    cavity_qualities_tmpl<D, M>(nelems, c2e.ab2b.data(), c2e.codes.data(), cv2v.data(), ev2v.data(), cand,  \
+        coords.data(), vert_metrics.data(), edge_mid.data(), qord);                                         \
+  }
+  if (dim == 3 && ncomps == 6) OSHB_CQ(3, 3)
+  else if (dim == 2 && ncomps == 3) OSHB_CQ(2, 2)
+  else if (dim == 3 && ncomps == 1) OSHB_CQ(3, 1)
+  else if (dim == 2 && ncomps == 1) OSHB_CQ(2, 1)
+  else fail(__FILE__, __LINE__, "refine_by_size: unsupported (dim, metric ncomps)");
+#undef OSHB_CQ
+  if (edge_mid_out) *edge_mid_out = edge_mid;
+  return qord_a;
+}
+
+Reals cavity_qualities_of_marked(Mesh* mesh, Bytes edge_marks, Reals* edge_mid_out) {
+  DArr<GO> qord_a = cavity_qord_of_marked(mesh, edge_marks.data(), edge_mid_out);
+  unsigned long long const* qord = reinterpret_cast<unsigned long long const*>(qord_a.data());
+  LO const nedges = mesh->nedges();
+  Reals out(nedges);
+  Real* o = out.data();
+  parallel_for(nedges, OSHB_LAMBDA(LO e) { o[e] = f64_of_ord(qord[e]); }, "qualities(decode)");
+  return out;
+}
+
+// refine_qualities(mesh, cands2edges) of the reference's interface (src/Omega_h_refine_qualities.cpp:88-107):
+// the element-centric evaluation above, read back at the listed edges
+Reals refine_qualities(Mesh* mesh, LOs cands2edges) {
+  LO const ncands = LO(cands2edges.size());
+  if (ncands == 0) return Reals(0);
+  Bytes marks = filled<I8>(mesh->nedges(), 0);
+  I8* mk = marks.data();
+  LO const* c2e = cands2edges.data();
+  parallel_for(ncands, OSHB_LAMBDA(LO i) { mk[c2e[i]] = 1; }, "refine_qualities(mark)");
+  Reals per_edge = cavity_qualities_of_marked(mesh, marks, nullptr);
+  Reals out(ncands);
+  Real* o = out.data();
+  Real const* pe = per_edge.data();
+  parallel_for(ncands, OSHB_LAMBDA(LO i) { o[i] = pe[c2e[i]]; }, "refine_qualities(unmap)");
+  return out;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -325,27 +397,8 @@ int Pass::begin(int keep_going) {
   c2e = mesh->ask_down(dim, EDGE);
   cv2v = mesh->ask_verts_of(dim);
   ev2v = mesh->ask_verts_of(EDGE);
-  Reals coords = mesh->coords();
-  Reals vert_metrics = mesh->get_reals(VERT, "metric");
-  int const ncomps = mesh->metric_ncomps();
-  DArr<GO> qord_a(nedges);
+  DArr<GO> qord_a = cavity_qord_of_marked(mesh, cand, &sel.edge_mid_metrics);
   unsigned long long* qord = reinterpret_cast<unsigned long long*>(qord_a.data());
-  {
-    unsigned long long const one = ord_of_f64(1.0);
-    parallel_for(nedges, OSHB_LAMBDA(LO e) { qord[e] = one; }, "qualities(init)");
-  }
-#define OSHB_CQ(D, M)                                                                                       \
-  {                                                                                                         \
-    sel.edge_mid_metrics = edge_midpoint_metrics<M>(ev2v.data(), vert_metrics.data(), cand, nedges, mesh->nverts()); \
-    cavity_qualities_tmpl<D, M>(nelems, c2e.ab2b.data(), c2e.codes.data(), cv2v.data(), ev2v.data(), cand,  \
-        coords.data(), vert_metrics.data(), sel.edge_mid_metrics.data(), qord);                             \
-  }
-  if (dim == 3 && ncomps == 6) OSHB_CQ(3, 3)
-  else if (dim == 2 && ncomps == 3) OSHB_CQ(2, 2)
-  else if (dim == 3 && ncomps == 1) OSHB_CQ(3, 1)
-  else if (dim == 2 && ncomps == 1) OSHB_CQ(2, 1)
-  else fail(__FILE__, __LINE__, "refine_by_size: unsupported (dim, metric ncomps)");
-#undef OSHB_CQ
   // ---- each_geq_to + get_max + the two map_onto of refine_ghosted (:23-28) in one sweep
   state_a = Bytes(nedges);
   edge_quals = Reals(nedges);
