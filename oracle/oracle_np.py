@@ -217,6 +217,7 @@ class Mesh:
         self.down = {}
         self.tags = [dict() for _ in range(4)]
         self.cache = {}
+        self.xfer = {}   # TransferOpts::type_map: tag name -> Omega_h_Transfer (src/Omega_h_adapt.hpp:30)
 
     def set_ents(self, d, ab2b, codes=None):
         self.down[d] = (np.asarray(ab2b, dtype=I32), None if codes is None else np.asarray(codes, dtype=I8))
@@ -494,6 +495,7 @@ def refine_element_based(mesh, keys2edges, global_order):
     dim = mesh.dim
     nkeys = keys2edges.size
     new = Mesh(dim)
+    new.xfer = dict(mesh.xfer)
     ev2v = mesh.verts_of(1).reshape(-1, 2)
     keys2midverts = ov2nv = old_lows2new_lows = None
     for ent_dim in range(dim + 1):
@@ -583,7 +585,10 @@ def transfer_refine(old, new, d, keys2edges, keys2midverts, keys2prods, prods2ne
     nkeys = keys2edges.size
     for name, (nc, arr) in old.tags[d].items():
         arr = arr.reshape(-1, nc)
-        inherit = name in ("class_id", "class_dim") and all(name in old.tags[i] for i in range(dim + 1))
+        rule = old.xfer.get(name, -1)   # 0 INHERIT 1 LINEAR_INTERP 2 METRIC 3 DENSITY 6 POINTWISE (src/Omega_h_defines.hpp:29-37)
+        inherit = (name in ("class_id", "class_dim") or rule == 0) and all(name in old.tags[i] for i in range(dim + 1))
+        if d == dim and rule in (3, 6) and arr.dtype == F64:
+            inherit = True   # transfer_density_refine / transfer_pointwise_refine: children take the parent's value
         out = None
         if inherit:
             out = np.empty((nnew, nc), dtype=arr.dtype)
@@ -610,14 +615,14 @@ def transfer_refine(old, new, d, keys2edges, keys2midverts, keys2prods, prods2ne
                     local = np.arange(idx.size) - off[owner]
                     prod[keys2prods[owner + 1] - ndoms + local] = up[d2[idx]]
             out[prods2new] = prod
-        elif d == 0 and name in ("coordinates", "warp"):
+        elif d == 0 and (name in ("coordinates", "warp") or rule == 1):
             out = np.empty((nnew, nc), dtype=F64)
             ev = old.verts_of(1).reshape(-1, 2)[keys2edges]
             comp = np.zeros((nkeys, nc))
             comp = comp + arr[ev[:, 0]]
             comp = comp + arr[ev[:, 1]]
             out[keys2midverts] = comp / 2
-        elif d == 0 and name in ("metric", "target_metric"):
+        elif d == 0 and (name in ("metric", "target_metric") or rule == 2):
             out = np.empty((nnew, nc), dtype=F64)
             out[keys2midverts] = get_mident_metrics(old, keys2edges, name).reshape(-1, nc)
         elif d == 1 and name == "length":
@@ -643,4 +648,7 @@ def mesh_from_fixture(fx, prefix="in:"):
         for k in fx:
             if k.startswith(tp) and not k.endswith(":ncomps"):
                 m.add_tag(d, k[len(tp):], int(fx[k + ":ncomps"][0]), fx[k])
+    for k in fx:
+        if k.startswith("xfer:"):
+            m.xfer[k[5:]] = int(fx[k][0])
     return m
