@@ -867,7 +867,7 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return main_reference(args)
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.replicas:
+    if (int(os.environ.get("WORLD_SIZE", "1")) > 1 or os.environ.get("OSHB_FORCE_PARTITIONED")) and not args.replicas:
         return main_b200_partitioned(args)
     return main_b200(args)
 

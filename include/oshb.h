@@ -253,6 +253,8 @@ int oshb_pass_destroy(oshb_pass* p);
  * then (a neighbouring rank may have work); 2: candidate marks only (then call again with 1).
  * *status: 0 no candidate, 1 candidates but none good enough, 2 there is work */
 int oshb_pass_begin(oshb_pass* p, int keep_going, int* status);
+/* any_good / pending may be NULL: the stage is only enqueued, nothing is read back (a partitioned caller decides
+ * from the states of all ranks anyway and saves a stream drain per call) */
 int oshb_pass_restate(oshb_pass* p, int* any_good);
 int oshb_pass_indset_round(oshb_pass* p, int* pending);
 int oshb_pass_select_keys(oshb_pass* p, int32_t* nkeys);

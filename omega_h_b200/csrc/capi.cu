@@ -645,12 +645,14 @@ int oshb_pass_begin(oshb_pass* p, int keep_going, int* status) {
 }
 int oshb_pass_restate(oshb_pass* p, int* any_good) {
   OSHB_TRY
-  *any_good = pass_restate(reinterpret_cast<Pass*>(p));
+  int r = pass_restate(reinterpret_cast<Pass*>(p), any_good != nullptr);  // NULL: no read-back
+  if (any_good) *any_good = r;
   OSHB_CATCH
 }
 int oshb_pass_indset_round(oshb_pass* p, int* pending) {
   OSHB_TRY
-  *pending = pass_indset_round(reinterpret_cast<Pass*>(p));
+  int r = pass_indset_round(reinterpret_cast<Pass*>(p), pending != nullptr);  // NULL: no read-back
+  if (pending) *pending = r;
   OSHB_CATCH
 }
 int oshb_pass_select_keys(oshb_pass* p, int32_t* nkeys) {

@@ -228,8 +228,8 @@ struct Pass;
 Pass* pass_create(Mesh* mesh, AdaptOpts const& opts);
 void pass_destroy(Pass* p);
 int pass_begin(Pass* p, int keep_going);
-int pass_restate(Pass* p);
-int pass_indset_round(Pass* p);
+int pass_restate(Pass* p, bool read = true);
+int pass_indset_round(Pass* p, bool read = true);
 void pass_select_keys(Pass* p);
 void pass_number(Pass* p, bool external_globals);
 void pass_finish(Pass* p);

@@ -353,8 +353,8 @@ struct Pass {
     if (rb) rebuild_discard(rb);
   }
   int begin(int keep_going);
-  int restate();
-  int indset_round();
+  int restate(bool read = true);
+  int indset_round(bool read = true);
   void select_keys();
   void number(bool ext);
   void finish();
@@ -429,7 +429,7 @@ int Pass::begin(int keep_going) {
 }
 
 // recompute the set states after the caller replaced qualities of edges it does not own
-int Pass::restate() {
+int Pass::restate(bool read) {
   I8 const* cand = edge_is_cand.data();
   I8* state = state_a.data();
   Real const* eq = edge_quals.data();
@@ -441,12 +441,13 @@ int Pass::restate() {
     state[e] = good ? UNKNOWN : NOT_IN;
     return good;
   }, flags3 + 1, 1, "cands_are_good(restate)");
-  return read_scalar(flags3 + 1) != 0;
+  // a distributed caller decides from the states of all ranks and skips this read-back
+  return read ? (read_scalar(flags3 + 1) != 0) : -1;
 }
 
 // ---- independent set (find_indset, :29): one element-centric Jacobi round; returns whether
 // any edge of this mesh is still undecided
-int Pass::indset_round() {
+int Pass::indset_round(bool read) {
   GOs globals = mesh->globals(EDGE);
   GO const* g = globals.data();
   LO const* ce2e = c2e.ab2b.data();
@@ -501,9 +502,16 @@ int Pass::indset_round() {
     state[e] = IN;
     return false;
   }, more, 1, "indset(edges)");
-  int pending = read_scalar(more);
-  if (pending) dev_memset(fl, 0, size_t(nedges) * sizeof(LO));
-  flags_clean = (pending != 0);
+  int pending = -1;
+  if (read) {
+    pending = read_scalar(more);
+    if (pending) dev_memset(fl, 0, size_t(nedges) * sizeof(LO));
+    flags_clean = (pending != 0);
+  } else {
+    // no read-back (a distributed caller decides from the states of all ranks): clear unconditionally
+    dev_memset(fl, 0, size_t(nedges) * sizeof(LO));
+    flags_clean = true;
+  }
   ++rounds;
   OSHB_CHECK(rounds < 10000);
   g_stats.indset_rounds = rounds;
@@ -804,8 +812,8 @@ Pass* pass_create(Mesh* mesh, AdaptOpts const& opts) {
 }
 void pass_destroy(Pass* p) { delete p; }
 int pass_begin(Pass* p, int keep_going) { return p->begin(keep_going); }
-int pass_restate(Pass* p) { return p->restate(); }
-int pass_indset_round(Pass* p) { return p->indset_round(); }
+int pass_restate(Pass* p, bool read) { return p->restate(read); }
+int pass_indset_round(Pass* p, bool read) { return p->indset_round(read); }
 void pass_select_keys(Pass* p) { p->select_keys(); }
 void pass_number(Pass* p, bool ext) { p->number(ext); }
 void pass_finish(Pass* p) { p->finish(); }
