@@ -355,6 +355,12 @@ struct Pass {
   int begin(int keep_going);
   int restate(bool read = true);
   int indset_round(bool read = true);
+  void ensure_rows() {
+    if (c2e.ab2b.exists()) return;
+    c2e = mesh->ask_down(dim, EDGE);
+    cv2v = mesh->ask_verts_of(dim);
+    ev2v = mesh->ask_verts_of(EDGE);
+  }
   void select_keys();
   void number(bool ext);
   void finish();
@@ -393,6 +399,15 @@ int Pass::begin(int keep_going) {
   bool const any_cand = read_scalar(flags3) != 0;
   if (!any_cand && !keep_going) return 0;
   if (keep_going == 2) return any_cand ? 2 : 0;
+  if (!any_cand) {
+    // keep_going == 1 on a part without a candidate of its own (a neighbouring rank may have work): the
+    // arrays of the later stages exist, nothing is evaluated -- no R->E, no cavity sweep on the whole part
+    state_a = filled<I8>(nedges, I8(NOT_IN));
+    edge_quals = filled<Real>(nedges, 0.0);
+    flags = filled<LO>(nedges, 0);
+    flags_clean = true;
+    return 0;  // (the element rows are derived by ensure_rows() if a later stage runs at all)
+  }
   // ---- cavity qualities of the candidates (refine_qualities, :22)
   c2e = mesh->ask_down(dim, EDGE);
   cv2v = mesh->ask_verts_of(dim);
@@ -448,6 +463,7 @@ int Pass::restate(bool read) {
 // ---- independent set (find_indset, :29): one element-centric Jacobi round; returns whether
 // any edge of this mesh is still undecided
 int Pass::indset_round(bool read) {
+  ensure_rows();
   GOs globals = mesh->globals(EDGE);
   GO const* g = globals.data();
   LO const* ce2e = c2e.ab2b.data();
@@ -520,6 +536,7 @@ int Pass::indset_round(bool read) {
 
 // ---- keys: state is now NOT_IN(0)/IN(1) = the key marks (:30-33); then their cavities
 void Pass::select_keys() {
+  ensure_rows();
   I8 const* state = state_a.data();
   LOs key_scan = offset_scan(state_a);
   LO const nkeys = last_of(key_scan);

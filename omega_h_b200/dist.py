@@ -361,8 +361,9 @@ class DistMesh:
         owner = (edge_own >> 8).to(torch.int64)
         band_mask = (edge_depth < 0) & (owner == me)
         shell_mask = edge_depth == trust + 1
-        to_owner = torch.zeros(P, dtype=torch.int64, device=dev)
-        to_owner.scatter_add_(0, owner.clamp(0, P - 1), shell_mask.to(torch.int64))
+        # requests per owner: a P+1-bin histogram (bin P = "not in the shell"); torch's bincount privatises the
+        # bins per block -- a scatter_add_ of 15 M ones onto <= 8 addresses serialises in L2 (measured: +19 ms/loop)
+        to_owner = torch.bincount(torch.where(shell_mask, owner.clamp(0, P - 1), P), minlength=P + 1)[:P]
         head = torch.cat([to_owner, torch.stack([band_mask.sum(), shell_mask.sum()])])
         table = torch.empty(P * (P + 2), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(table, head, group=self.group)
@@ -398,7 +399,8 @@ class DistMesh:
         try:
             # candidates + cavity qualities + set states in one go, then ONE reduction over the ranks of the
             # two questions "is any own edge too long?" / "is any own candidate good enough?" (one collective
-            # and one read-back per pass; the last call of a loop finds no candidate and evaluates nothing)
+            # and one read-back per pass). A rank without a candidate of its own skips the evaluation inside
+            # begin (the last call of a loop costs one each_gt sweep).
             with _Section(dm, "begin(lib)"):
                 ps.begin(1)
             with _Section(dm, "edge tags"):
