@@ -298,6 +298,23 @@ def _tick(name, t0, dev):
     return t1
 
 
+def _alltoallv(send, send_counts, group=None):
+    """send is grouped by destination rank; returns (received values grouped by source rank, counts)."""
+    dev = send.device
+    t = _tick("", 0.0, dev)
+    sc = torch.as_tensor(list(send_counts), dtype=torch.int64, device=dev)
+    rc = torch.empty_like(sc)
+    t = _tick("a2a: h2d counts", t, dev)
+    dist.all_to_all_single(rc, sc, group=group)
+    t = _tick("a2a: counts exchange", t, dev)
+    rc_l = [int(x) for x in rc.tolist()]
+    recv = torch.empty(sum(rc_l), dtype=send.dtype, device=dev)
+    t = _tick("a2a: tolist+empty", t, dev)
+    dist.all_to_all_single(recv, send.contiguous(), rc_l, [int(x) for x in send_counts], group=group)
+    t = _tick("a2a: data", t, dev)
+    return recv, rc_l
+
+
 def _any_rank(flags, group=None):
     """does any rank have a set entry in `flags` (a device tensor)? One collective, one read-back."""
     t = flags.any().to(torch.int32).reshape(1)
@@ -352,42 +369,31 @@ class DistMesh:
         return int(self.owned_mask(self.mesh.dim()).sum().item())
 
     # ---- plans ------------------------------------------------------------------------------------
-    def _shell_plan(self, edge_own, edge_depth, trust):
-        """Who sends which per-edge values to whom in this pass: the shell edges (depth == trust + 1) ask
-        their owners; an owner answers from its band (own edges near the partition boundary, sorted by global
-        number). ONE host read-back: the sizes of both lists and the P x P matrix of request counts travel in
-        a single all_gather + tolist; the lists themselves are cut with nonzero_static (no sync)."""
-        dm, dev, P, me = self.dm, self.device, self.size, self.rank
-        owner = (edge_own >> 8).to(torch.int64)
-        band_mask = (edge_depth < 0) & (owner == me)
-        shell_mask = edge_depth == trust + 1
-        # requests per owner: a P+1-bin histogram (bin P = "not in the shell"); torch's bincount privatises the
-        # bins per block -- a scatter_add_ of 15 M ones onto <= 8 addresses serialises in L2 (measured: +19 ms/loop)
-        to_owner = torch.bincount(torch.where(shell_mask, owner.clamp(0, P - 1), P), minlength=P + 1)[:P]
-        head = torch.cat([to_owner, torch.stack([band_mask.sum(), shell_mask.sum()])])
-        table = torch.empty(P * (P + 2), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(table, head, group=self.group)
-        table = table.view(P, P + 2).tolist()                      # the one read-back of the plan
-        nband, nshell = int(table[me][P]), int(table[me][P + 1])
-        counts = [int(x) for x in table[me][:P]]                    # what I ask of every rank
-        asked_counts = [int(table[r][me]) for r in range(P)]        # what every rank asks of me
-        band = torch.nonzero_static(band_mask, size=nband).flatten()
-        shell = torch.nonzero_static(shell_mask, size=nshell).flatten()
-        have_gid = dm.tag_gather(EDGE, "global", band.to(torch.int32), torch.int64)
-        if CHECK and have_gid.numel() > 1:
-            assert bool((have_gid[1:] > have_gid[:-1]).all().item()), "local edge order lost the global order"
-        want_owner = owner[shell]
+    def _fetch_plan(self, want_idx, want_owner, want_gid, have_idx, have_gid, runs=None):
+        """want_*: local entities whose value lives on another rank (want_owner);
+        have_*: this rank's counted entities sorted by global number (the lookup table), or
+        runs = (first key of every run of counted entities, its local position, all local keys)."""
+        P = self.size
         order = torch.argsort(want_owner, stable=True)
-        want_idx = shell[order]
-        want_gid = dm.tag_gather(EDGE, "global", want_idx.to(torch.int32), torch.int64)
-        asked = torch.empty(sum(asked_counts), dtype=torch.int64, device=dev)
-        dist.all_to_all_single(asked, want_gid, asked_counts, counts, group=self.group)
-        pos = torch.searchsorted(have_gid, asked).clamp(max=max(nband - 1, 0))
+        want_idx, want_owner, want_gid = want_idx[order], want_owner[order], want_gid[order]
+        counts = torch.bincount(want_owner, minlength=P).tolist()
+        asked, asked_counts = _alltoallv(want_gid, counts, self.group)
+        if runs is not None:
+            run_key, run_pos, key = runs
+            if asked.numel() and run_key.numel():
+                r = (torch.searchsorted(run_key, asked, right=True) - 1).clamp(min=0)
+                pos = (run_pos[r] + (asked - run_key[r])).clamp(0, key.numel() - 1)
+            else:
+                pos = torch.zeros_like(asked)
+            found = key[pos] if asked.numel() else asked
+        else:
+            pos = torch.searchsorted(have_gid, asked).clamp(max=max(have_gid.numel() - 1, 0))
+            found = have_gid[pos] if have_gid.numel() else asked - 1
+            if have_idx is not None:
+                pos = have_idx[pos]
         if CHECK and asked.numel():
-            found = have_gid[pos] if nband else asked - 1
             assert bool((found == asked).all().item()), "a neighbour asked for an entity this rank does not answer for"
-        send_idx = band[pos] if nband else pos
-        return FetchPlan(send_idx, asked_counts, want_idx, counts, self.group)
+        return FetchPlan(pos, asked_counts, want_idx, counts, self.group)
 
     # ---- the pass -------------------------------------------------------------------------------
     def refine_by_size(self, opts=None):
@@ -397,21 +403,15 @@ class DistMesh:
         trust = self.halo - self.passes - 1   # deepest layer whose entities see their whole star
         ps = _Pass(dm, opts)
         try:
-            # candidates + cavity qualities + set states in one go, then ONE reduction over the ranks of the
-            # two questions "is any own edge too long?" / "is any own candidate good enough?" (one collective
-            # and one read-back per pass). A rank without a candidate of its own skips the evaluation inside
-            # begin (the last call of a loop costs one each_gt sweep).
-            with _Section(dm, "begin(lib)"):
-                ps.begin(1)
+            # the cheap question first: is any edge of any rank still too long? (the last call of a
+            # loop ends here, before any cavity is evaluated)
+            with _Section(dm, "candidates(lib)"):
+                ps.begin(2)
             with _Section(dm, "edge tags"):
-                edge_own = dm.tag(EDGE, "own:part")
-                edge_depth = _depth_of(edge_own)
+                edge_depth = _depth_of(dm.tag(EDGE, "own:part"))
                 mine = edge_depth <= 0
                 cand = ps.get(PASS_CANDIDATES)
-                state = ps.get(PASS_STATES)
-                both = torch.stack([((cand != 0) & mine).any(), ((state == UNKNOWN) & mine).any()]).to(torch.int32)
-                dist.all_reduce(both, op=dist.ReduceOp.MAX, group=self.group)
-                any_cand, any_good = (bool(x) for x in both.tolist())
+                any_cand = _any_rank((cand != 0) & mine, self.group)
             if not any_cand:
                 return False
             if trust < 0:
@@ -420,10 +420,25 @@ class DistMesh:
                 with _Section(dm, "reghost"):
                     self.reghost()
                 return self.refine_by_size(opts)
+            with _Section(dm, "begin(lib)"):
+                ps.begin(1)
+                # the qualities of this rank's own edges (depth <= 0) are final before any exchange
+                state = ps.get(PASS_STATES)
+                any_good = _any_rank((state == UNKNOWN) & mine, self.group)
             if not any_good:
                 return False
             with _Section(dm, "shell plan"):
-                plan = self._shell_plan(edge_own, edge_depth, trust)
+                # lookup table of the edges this rank answers for: counted here and inside the band
+                band = torch.nonzero(edge_depth < 0).flatten().to(torch.int32)
+                band = band[(dm.tag_gather(EDGE, "own:part", band, torch.int32) >> 8) == self.rank]
+                have_idx = band.to(torch.int64)
+                have_gid = dm.tag_gather(EDGE, "global", band, torch.int64)
+                if CHECK and have_gid.numel() > 1:
+                    assert bool((have_gid[1:] > have_gid[:-1]).all().item()), "local edge order lost the global order"
+                shell = torch.nonzero(edge_depth == trust + 1).flatten()
+                shell32 = shell.to(torch.int32)
+                plan = self._fetch_plan(shell, (dm.tag_gather(EDGE, "own:part", shell32, torch.int32) >> 8).to(torch.int64),
+                                        dm.tag_gather(EDGE, "global", shell32, torch.int64), have_idx, have_gid)
             with _Section(dm, "qualities exchange"):
                 plan.pull_pass_array(ps, PASS_QUALITIES)
                 ps.restate()
