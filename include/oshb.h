@@ -164,6 +164,12 @@ int oshb_mesh_ask_qualities(oshb_mesh* m);
  * classification, identity globals). */
 int oshb_build_box(double x, double y, double z, int32_t nx, int32_t ny, int32_t nz, oshb_mesh** out);
 
+/* Mesh::balance() (src/Omega_h_mesh.cpp:536-568): recursive inertial bisection of the elements into nparts
+ * (a power of two) parts, unit element weights, tolerance 2 elements; out[e] = part of element e -- the same
+ * assignment as the reference's inertia::recursively_bisect (src/Omega_h_inertia.cpp:162-193, reductions by
+ * repro_sum) when the mesh starts on one rank. h_axes_out (may be NULL) receives the nparts-1 cutting axes. */
+int oshb_mesh_rib_partition(oshb_mesh* m, int nparts, int32_t* out, int host, double* h_axes_out);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* AdaptOpts, src/Omega_h_adapt.hpp:50-82; defaults from oshb_adapt_opts_init(dim),
  * src/Omega_h_adapt.cpp:52-85 */

@@ -242,6 +242,15 @@ int oshb_find_unique(const int32_t* d_hv2v, int64_t nhigh, int high_dim, int low
   OSHB_CATCH
 }
 
+int oshb_mesh_rib_partition(oshb_mesh* m, int nparts, int32_t* out, int host, double* h_axes_out) {
+  OSHB_TRY
+  init_ctx(-1);
+  LOs parts = rib_partition(&m->m, nparts, h_axes_out);
+  export_array(parts, out, host);
+  sync_unless_shared();
+  OSHB_CATCH
+}
+
 // ---- transfer rules ---------------------------------------------------------------------------
 int oshb_mesh_set_transfer(oshb_mesh* m, const char* tag_name, int transfer_type) {
   OSHB_TRY

@@ -171,6 +171,8 @@ LOs offset_scan(LOs a);
 LO last_of(LOs a);
 
 // ---- geometry / metric kernels (geom.cu) ------------------------------------------------
+// recursive inertial bisection (rib.cu): element -> part, the assignment Mesh::balance() makes
+LOs rib_partition(Mesh* mesh, int nparts, Real* axes_out);
 // standalone maps on device pointers (maps.cu; src/Omega_h_map.cpp)
 void unmap_bytes(LO const* a2b, int64_t na, void const* b_data, int width, int elem_bytes, void* a_out);
 void map_into_bytes(void const* a_data, LO const* a2b, int64_t na, void* b_data, int width, int elem_bytes);

@@ -87,6 +87,17 @@ OSHB_HD Vec<3> cross(Vec<3> a, Vec<3> b) {
   r[2] = a[0] * b[1] - a[1] * b[0];
   return r;
 }
+// [a]x, the matrix with [a]x b = a x b (src/Omega_h_matrix.hpp:323-325; columns (0,a2,-a1) (-a2,0,a0) (a1,-a0,0))
+OSHB_HD Mat<3> cross_matrix(Vec<3> a);
+// sign convention of an axis: flipped when its negative components outweigh the others as a bit pattern
+// (src/Omega_h_vector.hpp:205-217)
+OSHB_HD Vec<3> positivize(Vec<3> v) {
+  unsigned bits = 0;
+  for (int i = 0; i < 3; ++i) bits |= (unsigned(v[i] >= 0.0) << i);
+  unsigned neg_bits = (~bits) & 7u;
+  if (neg_bits > bits) return v * -1.0;
+  return v;
+}
 OSHB_HD Vec<2> perp(Vec<2> v) {
   Vec<2> r;
   r[0] = -v[1];
@@ -112,6 +123,23 @@ OSHB_HD Mat<N> operator*(Mat<N> a, Real s) {
   Mat<N> c;
   for (int j = 0; j < N; ++j) c[j] = a[j] * s;
   return c;
+}
+template <int N>
+OSHB_HD Mat<N> operator*(Real s, Mat<N> a) {
+  return a * s;
+}
+OSHB_HD Mat<3> cross_matrix(Vec<3> a) {
+  Mat<3> o;
+  o[0][0] = 0;
+  o[0][1] = a[2];
+  o[0][2] = -a[1];
+  o[1][0] = -a[2];
+  o[1][1] = 0;
+  o[1][2] = a[0];
+  o[2][0] = a[1];
+  o[2][1] = -a[0];
+  o[2][2] = 0;
+  return o;
 }
 template <int N>
 OSHB_HD Mat<N> operator/(Mat<N> a, Real s) {

@@ -782,18 +782,28 @@ def _build_part(lib, device, group, dim, n, down, cv2v, tags, gids, owner, halo,
     return out
 
 
-def distribute(base, halo, device, group=None):
-    """Cut a mesh that every rank holds in full (e.g. each built the same box) into parts:
-    contiguous ranges of the element order + `halo` layers of vertex-adjacent elements. Local
-    entities are the kept ones in increasing global number."""
+def distribute(base, halo, device, group=None, parting="hilbert"):
+    """Cut a mesh that every rank holds in full (e.g. each built the same box) into parts + `halo` layers of
+    vertex-adjacent elements. Local entities are the kept ones in increasing global number.
+      parting = "hilbert": contiguous ranges of the (Hilbert) element order;
+      parting = "rib":     recursive inertial bisection, the assignment the reference's Mesh::balance() makes
+                           (src/Omega_h_mesh.cpp:536-568; library: oshb_mesh_rib_partition) -- world size 2^k."""
     P = dist.get_world_size(group)
+    assert 1 <= halo <= 125, "depths are kept in a signed byte (DEEP = 127, band down to -(halo + 1))"
     src = DevMesh(base, device)
     dev = src.device
     dim = base.dim()
     n = [base.nents(d) for d in range(dim + 1)]
     down = {d: src.down(d, d - 1) for d in range(1, dim + 1)}
     cv2v = src.down(dim, VERT)[0].to(torch.int64).view(n[dim], dim + 1)
-    owner = (torch.arange(n[dim], device=dev, dtype=torch.int64) * P) // n[dim]
+    if parting == "rib":
+        parts32 = torch.empty(n[dim], dtype=torch.int32, device=dev)
+        src._pre()
+        base.lib.check(base.lib.c.oshb_mesh_rib_partition(base.h, C.c_int(P), C.c_void_p(parts32.data_ptr()), C.c_int(0), None))
+        src._post()
+        owner = parts32.to(torch.int64)
+    else:
+        owner = (torch.arange(n[dim], device=dev, dtype=torch.int64) * P) // n[dim]
     tags = {}
     for d in range(dim + 1):
         tags[d] = [(name, nc, src.tag(d, name)) for name, _, nc in base.tags(d)

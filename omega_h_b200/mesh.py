@@ -133,6 +133,14 @@ class Mesh:
 
     set_tag = add_tag
 
+    def rib_partition(self, nparts):
+        """element -> part by recursive inertial bisection (Mesh::balance, src/Omega_h_mesh.cpp:536-568);
+        returns (parts int32[nelems], axes float64[nparts-1, 3])"""
+        out = np.empty(self.nelems(), dtype=np.int32)
+        axes = np.zeros((max(nparts - 1, 1), 3))
+        self.lib.check(self.lib.c.oshb_mesh_rib_partition(self.h, C.c_int(nparts), _ptr(out), C.c_int(1), _ptr(axes)))
+        return out, axes[:nparts - 1]
+
     def set_transfer(self, name, transfer_type):
         """TransferOpts::type_map[name] = transfer_type (src/Omega_h_adapt.hpp:30): how a user tag is carried
         through refine passes; see OMEGA_H_INHERIT ... OMEGA_H_POINTWISE below."""

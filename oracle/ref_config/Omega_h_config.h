@@ -7,6 +7,9 @@
 #ifdef OSHB_REF_OPENMP
 #define OMEGA_H_USE_OPENMP
 #endif
+#ifdef OSHB_REF_CUDA
+#define OMEGA_H_USE_CUDA /* the reference's own (non-Kokkos) CUDA backend: src/Omega_h_for.hpp:16-58 */
+#endif
 #define OMEGA_H_VERSION_MAJOR 9
 #define OMEGA_H_VERSION_MINOR 34
 #define OMEGA_H_VERSION_PATCH 13

@@ -15,6 +15,8 @@
 //   timeloops <dim> <n> <metric> <reps> <budget_s>                     the WHOLE loop, repeated on copies of one input
 //                                                                      mesh; one JSON line per repetition (bench.py --impl reference)
 //   box    <dim> <n> <out>                                             build_box dump only
+//   rib    <dim> <nx> <ny> <nz> <nparts> <out>                         element -> part by the reference's inertia::mark_bisection,
+//                                                                      applied recursively as recursively_bisect does
 //   adjtime <n>                                                        invert_adj / reflect_down timing
 //   writeosh <dim> <n> <metric> <npasses> <path.osh> <dump>            binary::write + dump of the same mesh
 //   readosh <path.osh> <dump>                                          binary::read + dump
@@ -26,6 +28,7 @@
 #include <Omega_h_file.hpp>
 #include <Omega_h_for.hpp>
 #include <Omega_h_indset.hpp>
+#include <Omega_h_inertia.hpp>
 #include <Omega_h_map.hpp>
 #include <Omega_h_mesh.hpp>
 #include <Omega_h_metric.hpp>
@@ -345,6 +348,47 @@ static int mode_timeloops(Library* lib, int argc, char** argv) {
   return 0;
 }
 
+// rib: Mesh::balance()'s element -> rank assignment without MPI. recursively_bisect (src/Omega_h_inertia.cpp:162-193)
+// marks a group's elements with inertia::mark_bisection, sends unmarked / marked elements to the lower / upper half
+// of the group's ranks (bi_partition, src/Omega_h_bipart.cpp:9-33) and recurses on each half; the marks depend on
+// the group's elements only through order-independent reductions (repro_sum), so calling the reference's own
+// mark_bisection on each group with a one-rank communicator gives the assignment of the MPI run.
+static void rib_recurse(CommPtr comm, Reals ecoords, LOs elems, int first, int size, Write<LO> parts,
+    std::vector<Vector<3>>* axes) {
+  if (size == 1 || elems.size() == 0) {
+    auto f = OMEGA_H_LAMBDA(LO i) { parts[elems[i]] = first; };
+    parallel_for(elems.size(), f);
+    return;
+  }
+  auto coords = unmap(elems, ecoords, 3);
+  Reals masses(elems.size(), 1.0);
+  Vector<3> axis;
+  auto marks = inertia::mark_bisection(comm, coords, masses, 2.0, axis);
+  axes->push_back(axis);
+  auto upper = collect_marked(marks);
+  auto lower = collect_marked(invert_marks(marks));
+  rib_recurse(comm, ecoords, unmap(lower, elems, 1), first, size / 2, parts, axes);
+  rib_recurse(comm, ecoords, unmap(upper, elems, 1), first + size / 2, size / 2, parts, axes);
+}
+
+static int mode_rib(Library* lib, int, char** argv) {
+  int dim = atoi(argv[2]);
+  int nx = atoi(argv[3]), ny = atoi(argv[4]), nz = atoi(argv[5]);
+  int nparts = atoi(argv[6]);
+  auto mesh = build_box(lib->world(), OMEGA_H_SIMPLEX, double(nx), double(ny), dim == 3 ? double(nz) : 0.0, nx, ny,
+      dim == 3 ? nz : 0);
+  auto ecoords = average_field(&mesh, dim, LOs(mesh.nelems(), 0, 1), dim, mesh.coords());
+  if (dim < 3) ecoords = resize_vectors(ecoords, dim, 3);
+  Write<LO> parts(mesh.nelems(), -1);
+  std::vector<Vector<3>> axes;
+  rib_recurse(lib->world(), ecoords, LOs(mesh.nelems(), 0, 1), 0, nparts, parts, &axes);
+  Dump d(argv[7]);
+  dump_mesh(d, "in:", &mesh);
+  d.put("rib:parts", LOs(parts));
+  d.scalar("rib:nparts", nparts);
+  return 0;
+}
+
 static int mode_box(Library* lib, int, char** argv) {
   int dim = atoi(argv[2]);
   int n = atoi(argv[3]);
@@ -417,6 +461,7 @@ int main(int argc, char** argv) {
   if (mode == "time") return mode_time(&lib, argc, argv);
   if (mode == "timeloops") return mode_timeloops(&lib, argc, argv);
   if (mode == "box") return mode_box(&lib, argc, argv);
+  if (mode == "rib") return mode_rib(&lib, argc, argv);
   if (mode == "adjtime") return mode_adjtime(&lib, argc, argv);
   if (mode == "writeosh") return mode_writeosh(&lib, argc, argv);
   if (mode == "readosh") return mode_readosh(&lib, argc, argv);

@@ -31,6 +31,7 @@ def add_metric(m, n, aniso):
 
 def main():
     lib_path, device, n, halo, aniso, dim = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+    parting = sys.argv[7] if len(sys.argv) > 7 else "hilbert"
     backend = "nccl" if device == "cuda" else "gloo"
     dist.init_process_group(backend)
     rank, P = dist.get_rank(), dist.get_world_size()
@@ -46,7 +47,7 @@ def main():
     npass = 0
     while M.refine_by_size(serial):
         npass += 1
-    part = D.distribute(base, halo, device)
+    part = D.distribute(base, halo, device, parting=parting)
     dpass = 0
     while part.refine_by_size():
         dpass += 1

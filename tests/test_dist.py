@@ -10,10 +10,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 WORKER = os.path.join(HERE, "dist_worker.py")
 
 
-def run_worker(nranks, lib_path, device, n, halo, aniso, dim, port, timeout=900):
+def run_worker(nranks, lib_path, device, n, halo, aniso, dim, port, timeout=900, parting="hilbert"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
            "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, lib_path, device, str(n), str(halo),
-           str(aniso), str(dim)]
+           str(aniso), str(dim), parting]
     env = dict(os.environ)
     env["OMP_NUM_THREADS"] = "1"
     env["OSHB_DIST_CHECK"] = "1"
@@ -45,6 +45,17 @@ def test_reghosting_gloo(emu_lib, nranks, n, halo, aniso, dim):
     remaining passes again equal the serial ones"""
     out = run_worker(nranks, emu_lib.path, "cpu", n, halo, aniso, dim, 29560 + nranks + n + halo)
     assert int(out.split("reghosts=")[1].split()[0]) >= 1
+
+
+@pytest.mark.parametrize("nranks,n,halo,aniso,dim", [
+    (2, 8, 4, 0, 3),    # RIB halves of the cube
+    (4, 6, 2, 1, 3),    # four RIB parts, anisotropic, with re-ghosting
+    (2, 12, 4, 0, 2),   # triangles
+])
+def test_partitioned_loop_on_rib_parts_gloo(emu_lib, nranks, n, halo, aniso, dim):
+    """parts cut by recursive inertial bisection (Mesh::balance, BASELINE config[3]) instead of ranges of the
+    element order: the partitioned loop still equals the serial one array by array"""
+    run_worker(nranks, emu_lib.path, "cpu", n, halo, aniso, dim, 29590 + nranks + n, parting="rib")
 
 
 @pytest.mark.gpu
