@@ -39,7 +39,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"],
+                    help="reference = the unmodified reference on the host cores (OpenMP); reference-cuda = the reference's "
+                         "own CUDA backend (OMEGA_H_USE_CUDA, built by `make -C oracle refcuda`) on this GPU")
     ap.add_argument("--n", "--box-n", dest="n", type=int, default=64,
                     help="box cells per axis and GPU (config[1] = 64); under torchrun spell it --box-n")
     ap.add_argument("--workload", default="iso", choices=["iso", "aniso"],
@@ -51,6 +53,9 @@ def parse_args():
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the N-rank == serial self-check")
     ap.add_argument("--halo", type=int, default=4, help="N > 1: element layers each part keeps of its neighbours")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent boxes instead of one partitioned box")
+    ap.add_argument("--parting", default="rib", choices=["rib", "hilbert"],
+                    help="N > 1: parts by recursive inertial bisection (Mesh::balance, the reference's partitioner) or by "
+                         "contiguous ranges of the Hilbert element order")
     return ap.parse_args()
 
 
@@ -133,6 +138,36 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the unmodified reference on the host cores
 # ---------------------------------------------------------------------------------------------
+def run_reference_cuda_loops(n, kind, reps, budget_s, device=0):
+    """The reference's OWN CUDA backend (generic kernels + Thrust/CUB, src/Omega_h_for.hpp:16-58) compiled for sm_100
+    from the unmodified sources (oracle/Makefile `refcuda`), running the same complete loop on this GPU."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver_cuda")
+    if not os.path.exists(exe):
+        return None
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = str(device)
+    out = subprocess.run([exe, "timeloops", "3", str(n), str(kind), str(reps), str(budget_s)], capture_output=True,
+                         text=True, env=env)
+    if out.returncode != 0:
+        return None
+    recs = [json.loads(ln) for ln in out.stdout.splitlines() if ln.startswith("{")]
+    return recs or None
+
+
+def gpu_baseline_sample(n, workload="iso", device=0):
+    """gpu_baseline of the N = 1 line: 1 warm-up + 2 timed complete loops by the reference's own CUDA backend"""
+    recs = run_reference_cuda_loops(n, 2 if workload == "aniso" else 0, 3, 120, device)
+    if not recs:
+        return None
+    timed = recs[1:] if len(recs) > 1 else recs
+    new = timed[0]["nelems_after"] - timed[0]["nelems_before"]
+    secs = sum(r["seconds"] for r in timed) / len(timed)
+    return {"value": new / secs, "unit": UNIT, "kind": "reference-cuda", "ms_per_step": secs * 1e3,
+            "sample": "%d complete %d^3 loops (%d passes, %d -> %d tets) after one warm-up, the reference's own CUDA backend "
+                      "(OMEGA_H_USE_CUDA, unmodified sources, nvcc sm_100, oracle/_ref/ref_driver_cuda) on this GPU" % (
+                          len(timed), n, timed[0]["passes"], timed[0]["nelems_before"], timed[0]["nelems_after"])}
+
+
 def run_reference_loops(n, kind, reps, budget_s, omp=True):
     """The UNMODIFIED reference (oracle/_ref, built by oracle/Makefile) running the WHOLE
     `while (refine_by_size)` loop `reps` times on copies of one input mesh, all host cores; one record
@@ -176,9 +211,14 @@ def main_reference(args):
         return 0
     budget = float(os.environ.get("OSHB_REF_BUDGET_S", "330"))
     kind = 2 if args.workload == "aniso" else 0
-    recs = run_reference_loops(args.n, kind, args.warmup + args.steps, budget)
+    cuda = args.impl == "reference-cuda"
+    if cuda:
+        recs = run_reference_cuda_loops(args.n, kind, args.warmup + args.steps, budget, int(os.environ.get("LOCAL_RANK", "0")))
+    else:
+        recs = run_reference_loops(args.n, kind, args.warmup + args.steps, budget)
     if not recs:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_omp missing or failed"}))
+        print(json.dumps({"impl": args.impl, "unavailable": "oracle/_ref/%s missing or failed" %
+                          ("ref_driver_cuda (make -C oracle refcuda)" if cuda else "ref_driver_omp")}))
         return 0
     warm = min(args.warmup, max(len(recs) - 1, 0))
     timed = recs[warm:]
@@ -188,17 +228,19 @@ def main_reference(args):
     cfg = workload_config(args.n, args.workload)
     cfg["passes_per_step"] = timed[0]["passes"]
     cfg["tets_per_step"] = "%d -> %d" % (timed[0]["nelems_before"], timed[0]["nelems_after"])
-    cfg["parallelism"] = "host CPU, OpenMP, %d threads" % timed[0]["threads"]
+    cfg["parallelism"] = ("1 GPU, the reference's own CUDA backend (OMEGA_H_USE_CUDA)" if cuda else
+                          "host CPU, OpenMP, %d threads" % timed[0]["threads"])
     cfg["input_caches"] = "length + quality tags measured before the timed loop (ask_lengths/ask_qualities), as in our arm"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": args.impl, "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(timed), "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": secs * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": timed[0]["threads"], "kind": "reference",
-                         "sample": "%d complete loops (%d passes each, %d -> %d tets), %.2f s per loop, OpenMP build of the "
+                         "sample": "%d complete loops (%d passes each, %d -> %d tets), %.2f s per loop, %s build of the "
                                    "unmodified reference (oracle/_ref)" % (len(timed), timed[0]["passes"],
-                                                                          timed[0]["nelems_before"], timed[0]["nelems_after"], secs)},
+                                                                          timed[0]["nelems_before"], timed[0]["nelems_after"], secs,
+                                                                          "CUDA (sm_100)" if cuda else "OpenMP")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -374,7 +416,7 @@ def partition_parity_check(lib, device, halo, n=16):
         sopts = AdaptOpts(serial)
         while refine_by_size(serial, sopts):
             spasses += 1
-    part = D.distribute(base, halo, device)
+    part = D.distribute(base, halo, device, parting="rib" if (world & (world - 1)) == 0 else "hilbert")
     opts = AdaptOpts(part.mesh)
     passes = 0
     while part.refine_by_size(opts):
@@ -614,6 +656,9 @@ def main_b200(args):
         if s:
             cpu = {k: s[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gpu_base = gpu_baseline_sample(args.n, args.workload, local_rank)
     also = None
     if rank == 0 and world == 1 and not args.no_also and args.workload == "iso":
         # after the headline regions: the other single-GPU configurations of BASELINE.json, so that they
@@ -643,7 +688,7 @@ def main_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "wall_ms_per_step": wall_ms / args.steps, "syncs_per_step": None,
-            "peak_device_bytes": lib.peak_bytes(), "also": also,
+            "peak_device_bytes": lib.peak_bytes(), "gpu_baseline": gpu_base, "also": also,
         }
         print(json.dumps(line))
     if world > 1:
@@ -698,7 +743,7 @@ def main_b200_partitioned(args):
     base.ask_lengths()
     base.ask_qualities()
     halo = args.halo
-    part0 = D.distribute(base, halo, device)
+    part0 = D.distribute(base, halo, device, parting=args.parting)
     nglobal0 = base.nelems()
     # derive what the first pass asks for once, as the N = 1 arm's input has it cached
     part0.mesh.ask_down(part0.mesh.dim(), 1)
@@ -810,8 +855,9 @@ def main_b200_partitioned(args):
         cfg["workload"] = ("3D tet box build_box %dx%dx%d cells (x6 tets) = %d ranks x %d^3, uniform isotropic metric "
                            "h=1/(2n), while(refine_by_size) loop on the partitioned mesh" %
                            (shape[0] * n, shape[1] * n, shape[2] * n, world, n))
-        cfg["parallelism"] = ("%d parts (contiguous ranges of the Hilbert element order), halo %d layers, per-pass "
-                              "shell exchange + global-number scan over NCCL" % (world, halo))
+        cfg["parallelism"] = ("%d parts (%s), halo %d layers, per-pass shell exchange + global-number scan over NCCL" % (
+            world, "recursive inertial bisection = Mesh::balance" if args.parting == "rib" else
+            "contiguous ranges of the Hilbert element order", halo))
         cfg["passes_per_step"] = npasses
         cfg["tets_per_step"] = "%d -> %d" % (nglobal0, nglobal1)
         cfg["local_tets_rank0"] = local1
@@ -865,7 +911,7 @@ def main_b200_partitioned(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-cuda"):
         return main_reference(args)
     if (int(os.environ.get("WORLD_SIZE", "1")) > 1 or os.environ.get("OSHB_FORCE_PARTITIONED")) and not args.replicas:
         return main_b200_partitioned(args)
