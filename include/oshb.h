@@ -170,6 +170,14 @@ int oshb_build_box(double x, double y, double z, int32_t nx, int32_t ny, int32_t
  * repro_sum) when the mesh starts on one rank. h_axes_out (may be NULL) receives the nparts-1 cutting axes. */
 int oshb_mesh_rib_partition(oshb_mesh* m, int nparts, int32_t* out, int host, double* h_axes_out);
 
+/* compare_meshes (src/Omega_h_compare.cpp:179-277; what oshdiff and check_regression run): entity by entity in
+ * global-number order, connectivity exactly and every tag of `a` against `b`. compare_type: 0 NONE (tags only have
+ * to exist), 1 RELATIVE |b-a|/max(|a|,|b|) <= tolerance unless both <= floor (oshdiff's default: 1e-6, floor 0),
+ * 2 ABSOLUTE. full != 0 compares every dimension, else vertices and elements only.
+ * *result: 0 OMEGA_H_SAME, 1 OMEGA_H_MORE (b has tags a has not), 2 OMEGA_H_DIFF. */
+int oshb_mesh_compare(oshb_mesh* a, oshb_mesh* b, int compare_type, double tolerance, double floor, int verbose, int full,
+    int* result);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* AdaptOpts, src/Omega_h_adapt.hpp:50-82; defaults from oshb_adapt_opts_init(dim),
  * src/Omega_h_adapt.cpp:52-85 */

@@ -56,7 +56,7 @@ SYMBOLS = [
     "oshb_mesh_create", "oshb_mesh_destroy", "oshb_mesh_clone", "oshb_mesh_dim", "oshb_mesh_nents",
     "oshb_mesh_set_verts", "oshb_mesh_set_ents", "oshb_mesh_add_tag", "oshb_mesh_remove_tag", "oshb_mesh_ntags",
     "oshb_mesh_tag_info", "oshb_mesh_get_tag", "oshb_mesh_gather_tag", "oshb_mesh_ask_down", "oshb_mesh_ask_up", "oshb_mesh_ask_star",
-    "oshb_mesh_ask_lengths", "oshb_mesh_ask_qualities", "oshb_build_box", "oshb_mesh_rib_partition",
+    "oshb_mesh_ask_lengths", "oshb_mesh_ask_qualities", "oshb_build_box", "oshb_mesh_rib_partition", "oshb_mesh_compare",
     "oshb_adapt_opts_init", "oshb_mesh_set_transfer", "oshb_set_user_transfer", "oshb_refine_qualities", "oshb_mident_metrics", "oshb_find_indset",
     "oshb_rep_vertex2md_order", "oshb_refine_by_size", "oshb_last_pass_stats",
     "oshb_pass_create", "oshb_pass_destroy", "oshb_pass_begin", "oshb_pass_restate", "oshb_pass_indset_round",

@@ -251,6 +251,15 @@ int oshb_mesh_rib_partition(oshb_mesh* m, int nparts, int32_t* out, int host, do
   OSHB_CATCH
 }
 
+int oshb_mesh_compare(oshb_mesh* a, oshb_mesh* b, int compare_type, double tolerance, double floor, int verbose, int full,
+    int* result) {
+  OSHB_TRY
+  init_ctx(-1);
+  OSHB_CHECK(a && b && result && compare_type >= 0 && compare_type <= 2);
+  *result = compare_meshes(&a->m, &b->m, compare_type, tolerance, floor, verbose != 0, full != 0);
+  OSHB_CATCH
+}
+
 // ---- transfer rules ---------------------------------------------------------------------------
 int oshb_mesh_set_transfer(oshb_mesh* m, const char* tag_name, int transfer_type) {
   OSHB_TRY

@@ -171,6 +171,8 @@ LOs offset_scan(LOs a);
 LO last_of(LOs a);
 
 // ---- geometry / metric kernels (geom.cu) ------------------------------------------------
+// compare_meshes (compare.cu; src/Omega_h_compare.cpp:179-277): 0 same, 1 the second has more tags, 2 different
+int compare_meshes(Mesh* a, Mesh* b, int type, Real tol, Real floor, bool verbose, bool full);
 // recursive inertial bisection (rib.cu): element -> part, the assignment Mesh::balance() makes
 LOs rib_partition(Mesh* mesh, int nparts, Real* axes_out);
 // standalone maps on device pointers (maps.cu; src/Omega_h_map.cpp)

@@ -275,6 +275,18 @@ def refine_by_size(mesh, opts=None):
     return bool(did.value)
 
 
+OMEGA_H_SAME, OMEGA_H_MORE, OMEGA_H_DIFF = 0, 1, 2
+
+
+def compare_meshes(a, b, tolerance=1e-6, floor=0.0, compare_type="relative", verbose=False, full=True):
+    """Omega_h::compare_meshes (src/Omega_h_compare.cpp:179-277) on the device: OMEGA_H_SAME / OMEGA_H_MORE / OMEGA_H_DIFF"""
+    t = {"none": 0, "relative": 1, "absolute": 2}[compare_type]
+    res = C.c_int()
+    a.lib.check(a.lib.c.oshb_mesh_compare(a.h, b.h, C.c_int(t), C.c_double(tolerance), C.c_double(floor), C.c_int(int(verbose)),
+                                          C.c_int(int(full)), C.byref(res)))
+    return res.value
+
+
 def last_pass_stats(lib=None):
     lib = lib or _lib.default_lib()
     s = PassStatsC()

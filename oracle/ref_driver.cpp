@@ -20,11 +20,13 @@
 //   adjtime <n>                                                        invert_adj / reflect_down timing
 //   writeosh <dim> <n> <metric> <npasses> <path.osh> <dump>            binary::write + dump of the same mesh
 //   readosh <path.osh> <dump>                                          binary::read + dump
+//   diff <a.osh> <b.osh> <tolerance> <floor>                           compare_meshes (what oshdiff runs); prints the result code
 // metric: 0 iso h=1/(2n) | 1 tanh layer hx=hy | 2 tanh layer hy=0.7hx | 3 corner_test graded iso
 #include <Omega_h_adapt.hpp>
 #include <Omega_h_adj.hpp>
 #include <Omega_h_array_ops.hpp>
 #include <Omega_h_build.hpp>
+#include <Omega_h_compare.hpp>
 #include <Omega_h_file.hpp>
 #include <Omega_h_for.hpp>
 #include <Omega_h_indset.hpp>
@@ -389,6 +391,17 @@ static int mode_rib(Library* lib, int, char** argv) {
   return 0;
 }
 
+// diff: the reference's compare_meshes (src/Omega_h_compare.cpp:179-277) on two .osh files, as src/oshdiff.cpp:78-87 calls it
+static int mode_diff(Library* lib, int, char** argv) {
+  Mesh a(lib), b(lib);
+  binary::read(argv[2], lib->world(), &a);
+  binary::read(argv[3], lib->world(), &b);
+  auto opts = MeshCompareOpts::init(&a, VarCompareOpts{VarCompareOpts::RELATIVE, atof(argv[4]), atof(argv[5])});
+  auto res = compare_meshes(&a, &b, opts, true, true);
+  printf("RESULT %d\n", int(res));
+  return 0;
+}
+
 static int mode_box(Library* lib, int, char** argv) {
   int dim = atoi(argv[2]);
   int n = atoi(argv[3]);
@@ -461,6 +474,7 @@ int main(int argc, char** argv) {
   if (mode == "time") return mode_time(&lib, argc, argv);
   if (mode == "timeloops") return mode_timeloops(&lib, argc, argv);
   if (mode == "box") return mode_box(&lib, argc, argv);
+  if (mode == "diff") return mode_diff(&lib, argc, argv);
   if (mode == "rib") return mode_rib(&lib, argc, argv);
   if (mode == "adjtime") return mode_adjtime(&lib, argc, argv);
   if (mode == "writeosh") return mode_writeosh(&lib, argc, argv);
