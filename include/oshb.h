@@ -235,6 +235,40 @@ typedef struct oshb_pass_stats {
 } oshb_pass_stats;
 int oshb_last_pass_stats(oshb_pass_stats* out);
 
+/* ---- the partitioned pass: C++ host, exchanges over NCCL ------------------------------------------------------
+ * One process per GPU, one mesh part per process (a part = own elements + `halo` layers of vertex-adjacent foreign
+ * elements, "own:part" tag on every dimension, see DESIGN.md section 6 / omega_h_b200/dist.py for how parts are cut
+ * and re-ghosted). oshb_dist_refine_by_size is refine_by_size (src/Omega_h_refine.cpp:92-100) on such a part: the
+ * library runs the pass's stages and does between them what the reference does over MPI -- sync_array of cavity
+ * qualities and of the independent-set states (src/Omega_h_refine.cpp:25, src/Omega_h_indset_inline.hpp:38), the
+ * global-number scan of modify_globals (src/Omega_h_modify.cpp:406-444) -- through a communicator:
+ *   oshb_comm_create_nccl       NCCL over NVLink (grouped ncclSend/ncclRecv + all-gather/all-reduce on the library's
+ *                               stream). The 128-byte id comes from oshb_comm_nccl_unique_id on one rank and reaches the
+ *                               others by any means (MPI_Bcast, torch.distributed, a file).
+ *   oshb_comm_create_callbacks  the caller's collectives (an MPI host: MPI_Allreduce / MPI_Allgather / MPI_Alltoallv;
+ *                               the tests: gloo). Buffers are DEVICE pointers; sync_first != 0 drains the library's
+ *                               stream before every callback.
+ * *result: 0 no edge of any rank is left to split (the loop ends), 1 refined (*passes_inout and nglobal_inout[4] =
+ * global entity counts per dimension are updated), 2 the halo is used up (*passes_inout == halo): re-ghost first. */
+typedef struct oshb_comm oshb_comm;
+typedef struct oshb_comm_callbacks {
+  void* user;
+  int (*allreduce_max_i32)(void* user, int32_t* d_buf, int n);
+  int (*allgather_i64)(void* user, const int64_t* d_send, int n, int64_t* d_recv);
+  /* counts in elements of elem_bytes bytes, one entry per rank, data grouped by rank */
+  int (*alltoallv)(void* user, const void* d_send, const int64_t* send_counts, void* d_recv, const int64_t* recv_counts,
+      int elem_bytes);
+} oshb_comm_callbacks;
+int oshb_comm_nccl_unique_id(void* h_out128);
+int oshb_comm_create_nccl(int rank, int size, const void* h_unique_id128, oshb_comm** out);
+int oshb_comm_create_callbacks(int rank, int size, const oshb_comm_callbacks* cb, int sync_first, oshb_comm** out);
+int oshb_comm_destroy(oshb_comm* c);
+typedef struct oshb_dist_stats {
+  int32_t rounds, nkeys_local, shell_edges;
+} oshb_dist_stats;
+int oshb_dist_refine_by_size(oshb_mesh* part, oshb_comm* comm, const oshb_adapt_opts* opts, int halo, int* passes_inout,
+    int64_t* nglobal_inout, int* result, oshb_dist_stats* stats_or_null);
+
 /* ---- one refine pass, stage by stage -------------------------------------------------------------
  * The same pass as oshb_refine_by_size, cut at the points where the reference synchronises
  * across MPI ranks, so that a caller owning a partitioned mesh can do that synchronisation:

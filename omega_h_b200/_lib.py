@@ -59,6 +59,8 @@ SYMBOLS = [
     "oshb_mesh_ask_lengths", "oshb_mesh_ask_qualities", "oshb_build_box", "oshb_mesh_rib_partition", "oshb_mesh_compare",
     "oshb_adapt_opts_init", "oshb_mesh_set_transfer", "oshb_set_user_transfer", "oshb_refine_qualities", "oshb_mident_metrics", "oshb_find_indset",
     "oshb_rep_vertex2md_order", "oshb_refine_by_size", "oshb_last_pass_stats",
+    "oshb_comm_nccl_unique_id", "oshb_comm_create_nccl", "oshb_comm_create_callbacks", "oshb_comm_destroy",
+    "oshb_dist_refine_by_size",
     "oshb_pass_create", "oshb_pass_destroy", "oshb_pass_begin", "oshb_pass_restate", "oshb_pass_indset_round",
     "oshb_pass_select_keys", "oshb_pass_number", "oshb_pass_finish", "oshb_pass_size", "oshb_pass_get",
     "oshb_pass_set", "oshb_pass_gather", "oshb_pass_scatter", "oshb_pass_runs_begin", "oshb_pass_runs_get",

@@ -14,6 +14,8 @@ struct oshb_mesh {
   Mesh m;
 };
 
+
+
 #define OSHB_TRY try {
 #define OSHB_CATCH                                  \
   }                                                 \
@@ -257,6 +259,60 @@ int oshb_mesh_compare(oshb_mesh* a, oshb_mesh* b, int compare_type, double toler
   init_ctx(-1);
   OSHB_CHECK(a && b && result && compare_type >= 0 && compare_type <= 2);
   *result = compare_meshes(&a->m, &b->m, compare_type, tolerance, floor, verbose != 0, full != 0);
+  OSHB_CATCH
+}
+
+// ---- partitioned pass ---------------------------------------------------------------------------
+int oshb_comm_nccl_unique_id(void* h_out128) {
+  OSHB_TRY
+  init_ctx(-1);
+  comm_nccl_unique_id(h_out128);
+  OSHB_CATCH
+}
+int oshb_comm_create_nccl(int rank, int size, const void* h_unique_id128, oshb_comm** out) {
+  OSHB_TRY
+  *out = reinterpret_cast<oshb_comm*>(comm_create_nccl(rank, size, h_unique_id128));
+  OSHB_CATCH
+}
+int oshb_comm_create_callbacks(int rank, int size, const oshb_comm_callbacks* cb, int sync_first, oshb_comm** out) {
+  OSHB_TRY
+  init_ctx(-1);
+  OSHB_CHECK(cb && cb->allreduce_max_i32 && cb->allgather_i64 && cb->alltoallv);
+  CommCallbacks c;
+  c.user = cb->user;
+  c.allreduce_max_i32 = cb->allreduce_max_i32;
+  c.allgather_i64 = cb->allgather_i64;
+  c.alltoallv = cb->alltoallv;
+  *out = reinterpret_cast<oshb_comm*>(comm_create_callbacks(rank, size, c, sync_first != 0));
+  OSHB_CATCH
+}
+int oshb_comm_destroy(oshb_comm* c) {
+  OSHB_TRY
+  comm_destroy(reinterpret_cast<Comm*>(c));
+  OSHB_CATCH
+}
+int oshb_dist_refine_by_size(oshb_mesh* part, oshb_comm* comm, const oshb_adapt_opts* opts, int halo, int* passes_inout,
+    int64_t* nglobal_inout, int* result, oshb_dist_stats* stats_or_null) {
+  OSHB_TRY
+  OSHB_CHECK(part && comm && opts && passes_inout && nglobal_inout && result);
+  OSHB_CHECK(halo >= 1 && halo <= 125);  // depths live in a signed byte of "own:part"
+  AdaptOpts o(part->m.dim());
+  o.min_length_desired = opts->min_length_desired;
+  o.max_length_desired = opts->max_length_desired;
+  o.max_length_allowed = opts->max_length_allowed;
+  o.min_quality_allowed = opts->min_quality_allowed;
+  o.min_quality_desired = opts->min_quality_desired;
+  o.verbosity = opts->verbosity;
+  DistPassStats st;
+  GO ng[4];
+  for (int d = 0; d < 4; ++d) ng[d] = nglobal_inout[d];
+  *result = dist_refine_by_size(&part->m, reinterpret_cast<Comm*>(comm), o, halo, passes_inout, ng, &st);
+  for (int d = 0; d < 4; ++d) nglobal_inout[d] = ng[d];
+  if (stats_or_null) {
+    stats_or_null->rounds = st.rounds;
+    stats_or_null->nkeys_local = st.nkeys_local;
+    stats_or_null->shell_edges = st.shell_edges;
+  }
   OSHB_CATCH
 }
 

@@ -1,0 +1,545 @@
+// The partitioned refine pass, host side in C++: what the reference does under MPI between the stages of
+// refine_by_size (sync_array of the cavity qualities src/Omega_h_refine.cpp:25, one sync_array per
+// find_indset round src/Omega_h_indset_inline.hpp:38, modify_globals' scan over the linear partition
+// src/Omega_h_modify.cpp:406-444, Dist::exch src/Omega_h_dist.cpp:108-123) for a part with a deep halo
+// (DESIGN.md section 6), with the exchanges carried by NCCL over NVLink.
+//
+// One call = one pass of one rank:
+//   begin (candidates, cavity qualities, set states)      -> ONE 2-flag max-reduction over the ranks
+//   shell plan: the edges one layer beyond what this pass trusts ask their owners; owners answer from their
+//               band (own edges near the partition boundary, in global-number order); request counts of all
+//               ranks travel in one all-gather (the only read-back of the plan)
+//   qualities of the shell from the owners, restate; per independent-set round: states of the shell from
+//   the owners + one 1-flag reduction
+//   keys, local numbering, global numbering: runs of consecutive counted numbers -> linear partition of the
+//   number axis -> bases back (two all-to-alls), numbers of entities counted elsewhere from their owners (two
+//   all-to-alls), all sizes in one all-gather
+//   finish (the new part)
+// Collectives go through a small transport interface: NCCL (grouped ncclSend/ncclRecv for the all-to-alls; the
+// library binds the NCCL already loaded in the process, or libnccl.so.2, at run time -- no link dependency), or
+// caller-supplied callbacks (tests run the same C++ over gloo on the host emulation; an MPI host would plug in
+// MPI_Alltoallv). Every list this file builds is boundary-sized; the volume work stays in the pass's own kernels.
+#include "mesh.hpp"
+
+#include <algorithm>
+
+#ifndef OSHB_EMU
+#include <dlfcn.h>
+#endif
+
+namespace oshb {
+
+// ---------------------------------------------------------------------------------------------------
+// transport
+// ---------------------------------------------------------------------------------------------------
+struct Comm {
+  int rank = 0, size = 1;
+  virtual ~Comm() {}
+  virtual void allreduce_max_i32(int* d_buf, int n) = 0;                  // in place, device buffer
+  virtual void allgather_i64(GO const* d_send, int n, GO* d_recv) = 0;     // n values per rank
+  // send / recv are grouped by rank; counts in ELEMENTS of elem_bytes bytes, host arrays of `size` entries
+  virtual void alltoallv(void const* d_send, int64_t const* send_counts, void* d_recv, int64_t const* recv_counts,
+      int elem_bytes) = 0;
+};
+
+struct CallbackComm : public Comm {
+  CommCallbacks cb;
+  bool sync_first;  // the callbacks work outside the library's stream: drain it before every call
+  void pre() {
+    if (sync_first) sync_stream();
+  }
+  void allreduce_max_i32(int* d_buf, int n) override {
+    pre();
+    if (cb.allreduce_max_i32(cb.user, d_buf, n) != 0) fail(__FILE__, __LINE__, "comm callback allreduce failed");
+  }
+  void allgather_i64(GO const* d_send, int n, GO* d_recv) override {
+    pre();
+    if (cb.allgather_i64(cb.user, reinterpret_cast<int64_t const*>(d_send), n, reinterpret_cast<int64_t*>(d_recv)) != 0)
+      fail(__FILE__, __LINE__, "comm callback allgather failed");
+  }
+  void alltoallv(void const* d_send, int64_t const* sc, void* d_recv, int64_t const* rc, int eb) override {
+    pre();
+    if (cb.alltoallv(cb.user, d_send, sc, d_recv, rc, eb) != 0) fail(__FILE__, __LINE__, "comm callback alltoallv failed");
+  }
+};
+
+#ifndef OSHB_EMU
+// the few NCCL declarations used (ABI-stable across NCCL 2.x); bound at run time
+extern "C" {
+typedef struct ncclComm* oshb_ncclComm_t;
+typedef struct {
+  char internal[128];
+} oshb_ncclUniqueId;
+}
+struct NcclApi {
+  int (*GetUniqueId)(oshb_ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(oshb_ncclComm_t*, int, oshb_ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(oshb_ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, oshb_ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, oshb_ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, oshb_ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, oshb_ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl() {
+  static NcclApi api;
+  if (api.ok) return api;
+  // prefer the copy already in the process (torch's), else the system library
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) fail(__FILE__, __LINE__, std::string("NCCL not found (libnccl.so.2): ") + dlerror());
+#define OSHB_NCCL_SYM(field, name)                                                  \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name));                \
+  if (!api.field) fail(__FILE__, __LINE__, std::string("NCCL symbol missing: ") + name);
+  OSHB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  OSHB_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  OSHB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  OSHB_NCCL_SYM(AllReduce, "ncclAllReduce")
+  OSHB_NCCL_SYM(AllGather, "ncclAllGather")
+  OSHB_NCCL_SYM(Send, "ncclSend")
+  OSHB_NCCL_SYM(Recv, "ncclRecv")
+  OSHB_NCCL_SYM(GroupStart, "ncclGroupStart")
+  OSHB_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  OSHB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef OSHB_NCCL_SYM
+  api.ok = true;
+  return api;
+}
+#define OSHB_NCCL(call)                                                                                 \
+  do {                                                                                                  \
+    int r_ = (call);                                                                                    \
+    if (r_ != 0) fail(__FILE__, __LINE__, std::string(#call) + ": " + nccl().GetErrorString(r_));        \
+  } while (0)
+
+struct NcclComm : public Comm {
+  oshb_ncclComm_t comm = nullptr;
+  enum { kInt8 = 0, kInt32 = 2, kInt64 = 4, kMax = 2 };
+  ~NcclComm() override {
+    if (comm) nccl().CommDestroy(comm);
+  }
+  void allreduce_max_i32(int* d_buf, int n) override {
+    OSHB_NCCL(nccl().AllReduce(d_buf, d_buf, size_t(n), kInt32, kMax, comm, ctx().stream));
+  }
+  void allgather_i64(GO const* d_send, int n, GO* d_recv) override {
+    OSHB_NCCL(nccl().AllGather(d_send, d_recv, size_t(n), kInt64, comm, ctx().stream));
+  }
+  void alltoallv(void const* d_send, int64_t const* sc, void* d_recv, int64_t const* rc, int eb) override {
+    char const* s = static_cast<char const*>(d_send);
+    char* r = static_cast<char*>(d_recv);
+    OSHB_NCCL(nccl().GroupStart());
+    int64_t so = 0, ro = 0;
+    for (int p = 0; p < size; ++p) {
+      if (sc[p]) OSHB_NCCL(nccl().Send(s + so * eb, size_t(sc[p]) * eb, kInt8, p, comm, ctx().stream));
+      if (rc[p]) OSHB_NCCL(nccl().Recv(r + ro * eb, size_t(rc[p]) * eb, kInt8, p, comm, ctx().stream));
+      so += sc[p];
+      ro += rc[p];
+    }
+    OSHB_NCCL(nccl().GroupEnd());
+  }
+};
+#endif
+
+Comm* comm_create_callbacks(int rank, int size, CommCallbacks const& cb, bool sync_first) {
+  CallbackComm* c = new CallbackComm();
+  c->rank = rank;
+  c->size = size;
+  c->cb = cb;
+  c->sync_first = sync_first;
+  return c;
+}
+void comm_nccl_unique_id(void* out128) {
+#ifdef OSHB_EMU
+  (void)out128;
+  fail(__FILE__, __LINE__, "the host emulation has no NCCL transport");
+#else
+  oshb_ncclUniqueId id;
+  OSHB_NCCL(nccl().GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+#endif
+}
+Comm* comm_create_nccl(int rank, int size, void const* unique_id128) {
+#ifdef OSHB_EMU
+  (void)rank;
+  (void)size;
+  (void)unique_id128;
+  fail(__FILE__, __LINE__, "the host emulation has no NCCL transport");
+#else
+  init_ctx(-1);
+  NcclComm* c = new NcclComm();
+  c->rank = rank;
+  c->size = size;
+  oshb_ncclUniqueId id;
+  memcpy(&id, unique_id128, sizeof(id));
+  OSHB_NCCL(nccl().CommInitRank(&c->comm, size, id, rank));
+  return c;
+#endif
+}
+void comm_destroy(Comm* c) { delete c; }
+int comm_rank(Comm* c) { return c->rank; }
+int comm_size(Comm* c) { return c->size; }
+
+// ---------------------------------------------------------------------------------------------------
+// small device helpers (boundary-sized arrays)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+OSHB_HD int depth_of(LO own) { return int(I8(own & 0xff)); }
+
+// first index in [0, n] with a[idx] >= x (a ascending)
+template <class T>
+OSHB_HD LO lower_bound_dev(T const* a, LO n, T x) {
+  LO lo = 0, hi = n;
+  while (lo < hi) {
+    LO mid = lo + ((hi - lo) >> 1);
+    if (a[mid] < x) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+template <class T>
+DArr<T> gather_at(T const* src, LO const* idx, int64_t n) {
+  DArr<T> out(n);
+  T* o = out.data();
+  parallel_for(n, OSHB_LAMBDA(LO i) { o[i] = src[idx[i]]; }, "dist(gather)");
+  return out;
+}
+
+struct Plan {
+  LOs send_idx;  // my edges whose values the others asked for, grouped by asking rank
+  LOs recv_idx;  // my shell edges, grouped by owner
+  std::vector<int64_t> send_counts, recv_counts;
+  int64_t nsend = 0, nrecv = 0;
+};
+
+// owner -> requester transfer of one per-edge array of the pass, touching only the listed edges
+template <class T>
+void pull(Comm* comm, Plan const& plan, T* array) {
+  DArr<T> out = gather_at<T>(array, plan.send_idx.data(), plan.nsend);
+  DArr<T> in(plan.nrecv);
+  comm->alltoallv(out.data(), plan.send_counts.data(), in.data(), plan.recv_counts.data(), int(sizeof(T)));
+  T const* ip = in.data();
+  LO const* ri = plan.recv_idx.data();
+  parallel_for(plan.nrecv, OSHB_LAMBDA(LO i) { array[ri[i]] = ip[i]; }, "dist(scatter)");
+}
+
+// stable grouping of n items by a small key (a rank): permutation (sorted -> original) + per-key counts (device, P)
+LOs group_by_rank(LOs keys, int P, GOs* counts_out) {
+  int64_t const n = keys.size();
+  LOs perm(n);
+  if (n) sort_by_keys(keys.data(), n, 1, perm.data());
+  GOs counts(P);
+  GO* cp = counts.data();
+  LO const* kp = keys.data();
+  LO const* pp = perm.data();
+  LO const nn = LO(n);
+  // keys[perm[.]] is ascending: boundaries by bisection, one thread per rank
+  parallel_for(P, OSHB_LAMBDA(LO p) {
+    LO lo = 0, hi = nn;
+    while (lo < hi) {  // first position with key >= p
+      LO mid = lo + ((hi - lo) >> 1);
+      if (kp[pp[mid]] < p) lo = mid + 1;
+      else hi = mid;
+    }
+    LO a = lo;
+    lo = a;
+    hi = nn;
+    while (lo < hi) {  // first position with key > p
+      LO mid = lo + ((hi - lo) >> 1);
+      if (kp[pp[mid]] <= p) lo = mid + 1;
+      else hi = mid;
+    }
+    cp[p] = GO(lo - a);
+  }, "dist(rank counts)");
+  *counts_out = counts;
+  return perm;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// the pass
+// ---------------------------------------------------------------------------------------------------
+// returns 0: nothing left to refine anywhere (or no candidate is good enough): the loop ends
+//         1: refined; *passes and nglobal[] are updated
+//         2: the halo is used up (passes == halo): re-ghost, then call again
+int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo, int* passes, GO* nglobal,
+    DistPassStats* stats) {
+  int const P = comm->size, me = comm->rank;
+  int const dim = mesh->dim();
+  int const trust = halo - *passes - 1;  // deepest layer whose entities see their whole star
+  Pass* ps = pass_create(mesh, opts);
+  struct Guard {
+    Pass* p;
+    ~Guard() { pass_destroy(p); }
+  } guard{ps};
+  int* cells = reinterpret_cast<int*>(static_cast<char*>(ctx().dscratch) + 1408);  // 2 ints
+
+  // ---- candidates + cavity qualities + set states; is there work anywhere?
+  pass_begin(ps, 1);
+  LOs edge_own = mesh->get_los(EDGE, "own:part");
+  LO const* own = edge_own.data();
+  LO const nedges = mesh->nedges();
+  Bytes cand = pass_candidates(ps);
+  Bytes state_a = pass_states(ps);
+  Reals quals = pass_qualities(ps);
+  I8 const* cd = cand.data();
+  I8* state = state_a.data();
+  {
+    int z[2] = {0, 0};
+    h2d(cells, z, sizeof(z));
+    parallel_for(nedges, OSHB_LAMBDA(LO e) {
+      if (depth_of(own[e]) > 0) return;  // not mine
+      if (cd[e]) raise_flag(cells, 1);
+      if (state[e] == 2) raise_flag(cells + 1, 1);
+    }, "dist(flags)");
+    comm->allreduce_max_i32(cells, 2);
+    d2h(z, cells, sizeof(z));
+    if (!z[0]) return 0;
+    if (trust < 0) return 2;
+    if (!z[1]) return 0;
+  }
+
+  // ---- shell plan
+  Plan plan;
+  GOs edge_gid = mesh->globals(EDGE);
+  GO const* gid = edge_gid.data();
+  {
+    // band = own edges this rank answers for (depth < 0, counted here), shell = depth == trust + 1
+    Bytes band_m(nedges), shell_m(nedges);
+    I8* bm = band_m.data();
+    I8* sm = shell_m.data();
+    parallel_for(nedges, OSHB_LAMBDA(LO e) {
+      LO o = own[e];
+      int d = depth_of(o);
+      bm[e] = (d < 0 && (o >> 8) == me) ? 1 : 0;
+      sm[e] = (d == trust + 1) ? 1 : 0;
+    }, "dist(band+shell marks)");
+    LOs band = collect_marked(band_m);
+    LOs shell = collect_marked(shell_m);
+    LO const nband = LO(band.size()), nshell = LO(shell.size());
+    LO const* bp = band.data();
+    LO const* sp = shell.data();
+    // requests grouped by owner
+    LOs want_owner(nshell);
+    LO* wo = want_owner.data();
+    parallel_for(nshell, OSHB_LAMBDA(LO i) {
+      LO r = own[sp[i]] >> 8;
+      wo[i] = (r < 0) ? 0 : ((r >= P) ? P - 1 : r);
+    }, "dist(shell owners)");
+    GOs my_counts;
+    LOs order = group_by_rank(want_owner, P, &my_counts);
+    LO const* op = order.data();
+    plan.recv_idx = LOs(nshell);
+    GOs want_gid(nshell);
+    LO* ri = plan.recv_idx.data();
+    GO* wg = want_gid.data();
+    parallel_for(nshell, OSHB_LAMBDA(LO i) {
+      LO e = sp[op[i]];
+      ri[i] = e;
+      wg[i] = gid[e];
+    }, "dist(shell requests)");
+    // everybody's request counts in one all-gather, one read-back
+    GOs table(int64_t(P) * P);
+    comm->allgather_i64(my_counts.data(), P, table.data());
+    std::vector<GO> th = table.to_host();
+    plan.recv_counts.resize(P);
+    plan.send_counts.resize(P);
+    for (int r = 0; r < P; ++r) {
+      plan.recv_counts[r] = th[int64_t(me) * P + r];  // what I ask of r = what I will receive from r
+      plan.send_counts[r] = th[int64_t(r) * P + me];  // what r asks of me
+      plan.nrecv += plan.recv_counts[r];
+      plan.nsend += plan.send_counts[r];
+    }
+    OSHB_CHECK(plan.nrecv == nshell);
+    GOs asked(plan.nsend);
+    comm->alltoallv(want_gid.data(), plan.recv_counts.data(), asked.data(), plan.send_counts.data(), int(sizeof(GO)));
+    // the asked edges are in my band; the band is in global-number order
+    GOs have_gid = gather_at<GO>(gid, bp, nband);
+    plan.send_idx = LOs(plan.nsend);
+    LO* si = plan.send_idx.data();
+    GO const* hg = have_gid.data();
+    GO const* ak = asked.data();
+    int* err = device_error_cell();
+    parallel_for(plan.nsend, OSHB_LAMBDA(LO i) {
+      LO pos = lower_bound_dev<GO>(hg, nband, ak[i]);
+      if (pos >= nband || hg[pos] != ak[i]) {
+        raise_flag(err, 32);  // a neighbour asked for an edge this rank does not answer for
+        si[i] = 0;
+        return;
+      }
+      si[i] = bp[pos];
+    }, "dist(answers)");
+    if (stats) stats->shell_edges = nshell;
+  }
+
+  // ---- qualities of the shell from their owners, then the states follow from them
+  pull<Real>(comm, plan, quals.data());
+  pass_restate(ps, false);
+  // ---- independent set: one round, the shell's states from their owners, anybody undecided?
+  int rounds = 0;
+  while (true) {
+    pass_indset_round(ps, false);
+    pull<I8>(comm, plan, state);
+    ++rounds;
+    int z = 0;
+    h2d(cells, &z, sizeof(int));
+    parallel_for(nedges, OSHB_LAMBDA(LO e) {
+      if (depth_of(own[e]) <= 0 && state[e] == 2) raise_flag(cells, 1);
+    }, "dist(undecided)");
+    comm->allreduce_max_i32(cells, 1);
+    d2h(&z, cells, sizeof(int));
+    if (!z) break;
+    OSHB_CHECK(rounds < 10000);
+  }
+  device_error_check("partitioned pass: shell exchange");
+  // edges deeper than the shell never hear from their owner: keep them out of the set
+  parallel_for(nedges, OSHB_LAMBDA(LO e) {
+    state[e] = (depth_of(own[e]) <= trust + 1 && state[e] == 1) ? 1 : 0;
+  }, "dist(trusted keys)");
+  pass_select_keys(ps);
+  LO const nkeys = pass_nkeys(ps);
+  if (stats) {
+    stats->rounds = rounds;
+    stats->nkeys_local = nkeys;
+  }
+  if (nkeys) pass_number(ps, true);
+
+  // ---- global numbers (a rank where nothing splits still renumbers: every number shifts with the others' products)
+  GO nnext[4] = {0, 0, 0, 0};
+  {
+    GO koff[5] = {0, 0, 0, 0, 0};
+    for (int d = 1; d < 5; ++d) koff[d] = koff[d - 1] + nglobal[d - 1];
+    GO const N = koff[dim + 1];
+    GO chunk = (N + P - 1) / P;
+    if (chunk < 1) chunk = 1;
+    int64_t nruns = 0, nwant = 0;
+    GO newc[4] = {0, 0, 0, 0};
+    pass_runs_begin(ps, me, trust, koff, &nruns, &nwant, newc);
+    GOs run_key, run_sum, want_key;
+    LOs want_owner;
+    pass_runs_get(ps, &run_key, &run_sum);
+    pass_want_get(ps, &want_key, &want_owner);
+    LO const nr = LO(nruns), nw = LO(nwant);
+    // runs per partition rank of the key axis + their sums; wanted entities per owner; new totals -> one all-gather
+    GOs inc(int64_t(nr) + 1);
+    scan_offsets(run_sum.data(), nr, inc.data());
+    GOs want_counts;
+    LOs worder = group_by_rank(want_owner, P, &want_counts);
+    int const W = 3 * P + 4;
+    GOs mine(W);
+    {
+      GO* mp = mine.data();
+      GO const* rk = run_key.data();
+      GO const* ip = inc.data();
+      GO const* wc = want_counts.data();
+      GO const c0 = newc[0], c1 = newc[1], c2 = newc[2], c3 = newc[3];
+      parallel_for(P, OSHB_LAMBDA(LO p) {
+        LO b0 = lower_bound_dev<GO>(rk, nr, GO(p) * chunk);
+        LO b1 = lower_bound_dev<GO>(rk, nr, GO(p + 1) * chunk);
+        mp[p] = GO(b1 - b0);
+        mp[P + p] = ip[b1] - ip[b0];
+        mp[2 * P + p] = wc[p];
+        if (p == 0) {
+          mp[3 * P + 0] = c0;
+          mp[3 * P + 1] = c1;
+          mp[3 * P + 2] = c2;
+          mp[3 * P + 3] = c3;
+        }
+      }, "dist(numbering sizes)");
+    }
+    GOs table(int64_t(P) * W);
+    comm->allgather_i64(mine.data(), W, table.data());
+    std::vector<GO> th = table.to_host();
+    auto T = [&](int r, int k) { return th[int64_t(r) * W + k]; };
+    std::vector<int64_t> run_send(P), run_recv(P), want_send(P), want_recv(P);
+    GO sums_total = 0, below = 0, next_total = 0;
+    int64_t nrecv_runs = 0, nrecv_want = 0;
+    for (int q = 0; q < P; ++q) {
+      run_send[q] = T(me, q);
+      run_recv[q] = T(q, me);
+      want_send[q] = T(me, 2 * P + q);
+      want_recv[q] = T(q, 2 * P + me);
+      nrecv_runs += run_recv[q];
+      nrecv_want += want_recv[q];
+      GO to_q = 0;
+      for (int r = 0; r < P; ++r) to_q += T(r, P + q);
+      if (q < me) below += to_q;
+      sums_total += to_q;
+    }
+    for (int d = 0; d < 4; ++d) {
+      for (int r = 0; r < P; ++r) nnext[d] += T(r, 3 * P + d);
+      next_total += nnext[d];
+    }
+    if (sums_total != next_total) fail(__FILE__, __LINE__, "partitioned numbering: an old entity was counted twice or by no rank");
+    // runs -> linear partition of the key axis -> base of every run
+    DArr<GO> pairs(int64_t(nr) * 2);
+    {
+      GO* pp = pairs.data();
+      GO const* rk = run_key.data();
+      GO const* rs = run_sum.data();
+      parallel_for(nr, OSHB_LAMBDA(LO r) {
+        pp[2 * int64_t(r)] = rk[r];
+        pp[2 * int64_t(r) + 1] = rs[r];
+      }, "dist(run pairs)");
+    }
+    DArr<GO> both(nrecv_runs * 2);
+    comm->alltoallv(pairs.data(), run_send.data(), both.data(), run_recv.data(), 16);
+    GOs excl(nrecv_runs);
+    if (nrecv_runs) {
+      GOs rg(nrecv_runs), rs_sorted(nrecv_runs);
+      GO const* bp = both.data();
+      GO* rgp = rg.data();
+      LO const nn = LO(nrecv_runs);
+      parallel_for(nn, OSHB_LAMBDA(LO i) { rgp[i] = bp[2 * int64_t(i)]; }, "dist(run keys)");
+      LOs order(nrecv_runs);
+      sort_by_keys(rg.data(), nrecv_runs, 1, order.data());
+      LO const* op = order.data();
+      GO* rss = rs_sorted.data();
+      parallel_for(nn, OSHB_LAMBDA(LO i) { rss[i] = bp[2 * int64_t(op[i]) + 1]; }, "dist(run sums sorted)");
+      GOs scan(nrecv_runs + 1);
+      scan_offsets(rs_sorted.data(), nrecv_runs, scan.data());
+      GO const* sc = scan.data();
+      GO* ex = excl.data();
+      GO const bel = below;
+      parallel_for(nn, OSHB_LAMBDA(LO i) { ex[op[i]] = sc[i] + bel; }, "dist(run bases)");
+    }
+    GOs run_base(nr);
+    comm->alltoallv(excl.data(), run_recv.data(), run_base.data(), run_send.data(), int(sizeof(GO)));
+    GO new_off[4] = {0, 0, 0, 0};
+    for (int d = 1; d < 4; ++d) new_off[d] = new_off[d - 1] + nnext[d - 1];
+    pass_runs_set_bases(ps, run_base, new_off);
+    // entities another rank counts: ask the owner
+    GOs want_sorted(nw);
+    {
+      GO* ws = want_sorted.data();
+      GO const* wk = want_key.data();
+      LO const* wo = worder.data();
+      parallel_for(nw, OSHB_LAMBDA(LO i) { ws[i] = wk[wo[i]]; }, "dist(want keys)");
+    }
+    GOs asked(nrecv_want);
+    comm->alltoallv(want_sorted.data(), want_send.data(), asked.data(), want_recv.data(), int(sizeof(GO)));
+    GOs answers = pass_runs_lookup(ps, asked);
+    GOs got(nw);
+    comm->alltoallv(answers.data(), want_recv.data(), got.data(), want_send.data(), int(sizeof(GO)));
+    GOs values(nw);
+    {
+      GO* vp = values.data();
+      GO const* gp = got.data();
+      LO const* wo = worder.data();
+      parallel_for(nw, OSHB_LAMBDA(LO i) { vp[wo[i]] = gp[i]; }, "dist(want values)");
+    }
+    pass_want_set(ps, values);
+    pass_runs_commit(ps);
+  }
+  if (nkeys) pass_finish(ps);
+  for (int d = 0; d < 4; ++d) nglobal[d] = nnext[d];
+  *passes += 1;
+  return 1;
+}
+
+}  // namespace oshb

@@ -258,6 +258,27 @@ LO pass_nwant(Pass* p);
 LOs rep_vertex_order_from_keys(LOs ev2v, LO nverts, LO nedges, LOs keys2edges, LOs* keys_order_out,
     LOs* vert2keys_off_out, LOs* vert_keys_out);  // refine.cu
 
+// ---- partitioned pass, C++ host + NCCL (dist.cu) ------------------------------------------------------
+struct Comm;
+struct CommCallbacks {
+  void* user;
+  int (*allreduce_max_i32)(void* user, int32_t* buf, int n);
+  int (*allgather_i64)(void* user, const int64_t* send, int n, int64_t* recv);
+  int (*alltoallv)(void* user, const void* send, const int64_t* send_counts, void* recv, const int64_t* recv_counts,
+      int elem_bytes);
+};
+Comm* comm_create_callbacks(int rank, int size, CommCallbacks const& cb, bool sync_first);
+struct DistPassStats {
+  LO rounds = 0, nkeys_local = 0, shell_edges = 0;
+};
+Comm* comm_create_nccl(int rank, int size, void const* unique_id128);
+void comm_nccl_unique_id(void* out128);
+void comm_destroy(Comm* c);
+int comm_rank(Comm* c);
+int comm_size(Comm* c);
+int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo, int* passes, GO* nglobal,
+    DistPassStats* stats);
+
 struct PassStats {
   LO ncands = 0, nkeys = 0, indset_rounds = 0;
   LO nents_before[4] = {0, 0, 0, 0};

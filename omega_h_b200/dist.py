@@ -43,6 +43,7 @@ _TYPE_OF_T = {v: k for k, v in _TT.items()}
 _PASS_DTYPE = {PASS_CANDIDATES: torch.int8, PASS_STATES: torch.int8, PASS_QUALITIES: torch.float64,
                PASS_OFFSETS: torch.int32, PASS_OLD2NEW: torch.int32, PASS_KEYS2EDGES: torch.int32}
 DEEP = 127
+USE_PY_PASS = __import__("os").environ.get("OSHB_DIST_PY", "0") == "1"
 CHECK = bool(int(__import__("os").environ.get("OSHB_DIST_CHECK", "0")))  # consistency asserts (tests turn them on)
 
 # optional wall-clock breakdown of the partitioned pass (OSHB_DIST_TIMING=1): every section is
@@ -322,6 +323,88 @@ def _any_rank(flags, group=None):
     return bool(t.item())
 
 
+# ---- the library's communicator (include/oshb.h, oshb_comm_*) ---------------------------------------------
+_COMMS = {}
+_CB_KEEP = []
+
+
+class _DistStatsC(C.Structure):
+    _fields_ = [("rounds", C.c_int32), ("nkeys_local", C.c_int32), ("shell_edges", C.c_int32)]
+
+
+class _CommCallbacksC(C.Structure):
+    _fields_ = [("user", C.c_void_p),
+                ("allreduce_max_i32", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)),
+                ("allgather_i64", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)),
+                ("alltoallv", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p,
+                                          C.POINTER(C.c_int64), C.c_int))]
+
+
+def _host_tensor(ptr, n, dtype):
+    """a torch view of n values at a HOST address (the emulation build's "device" memory)"""
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=dtype)
+    np_dt = {torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8}[dtype]
+    buf = (C.c_char * (n * np.dtype(np_dt).itemsize)).from_address(ptr)
+    return torch.from_numpy(np.frombuffer(buf, dtype=np_dt, count=n))
+
+
+def library_comm(lib, device, group=None):
+    """The communicator the library's C++ partitioned pass exchanges through: NCCL over NVLink when the ranks are
+    GPUs (the 128-byte NCCL id of rank 0 is broadcast with torch.distributed, every rank then calls
+    oshb_comm_create_nccl: the library talks to NCCL itself, on its own stream); on the host emulation (CPU
+    tests) the collectives are torch.distributed/gloo calls handed to the library as callbacks."""
+    key = (id(lib), id(group))
+    if key in _COMMS:
+        return _COMMS[key]
+    device = torch.device(device)
+    rank, size = dist.get_rank(group), dist.get_world_size(group)
+    h = C.c_void_p()
+    if device.type == "cuda" and not lib.is_emulation:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            lib.check(lib.c.oshb_comm_nccl_unique_id(buf))
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.to(device)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(uid, src, group=group)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        lib.check(lib.c.oshb_comm_create_nccl(C.c_int(rank), C.c_int(size), raw, C.byref(h)))
+    else:
+        def allreduce(user, buf, n):
+            t = _host_tensor(buf, n, torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            return 0
+
+        def allgather(user, send, n, recv):
+            s = _host_tensor(send, n, torch.int64)
+            r = _host_tensor(recv, n * size, torch.int64)
+            parts = [torch.empty(n, dtype=torch.int64) for _ in range(size)]
+            dist.all_gather(parts, s.clone(), group=group)
+            r.copy_(torch.cat(parts))
+            return 0
+
+        def alltoallv(user, send, sc, recv, rc, eb):
+            scl = [int(sc[i]) * eb for i in range(size)]
+            rcl = [int(rc[i]) * eb for i in range(size)]
+            s = _host_tensor(send, sum(scl), torch.uint8).clone()
+            r = torch.empty(sum(rcl), dtype=torch.uint8)
+            dist.all_to_all_single(r, s, rcl, scl, group=group)
+            if r.numel():
+                _host_tensor(recv, r.numel(), torch.uint8).copy_(r)
+            return 0
+        cb = _CommCallbacksC()
+        cb.user = None
+        cb.allreduce_max_i32 = _CommCallbacksC._fields_[1][1](allreduce)
+        cb.allgather_i64 = _CommCallbacksC._fields_[2][1](allgather)
+        cb.alltoallv = _CommCallbacksC._fields_[3][1](alltoallv)
+        _CB_KEEP.append(cb)
+        lib.check(lib.c.oshb_comm_create_callbacks(C.c_int(rank), C.c_int(size), C.byref(cb), C.c_int(1), C.byref(h)))
+    _COMMS[key] = h
+    return h
+
+
 class FetchPlan:
     """Owner -> requester transfers of per-entity values (one value per requested entity)."""
 
@@ -397,6 +480,37 @@ class DistMesh:
 
     # ---- the pass -------------------------------------------------------------------------------
     def refine_by_size(self, opts=None):
+        """One pass of the partitioned loop. The pass itself -- stages, shell plan, exchanges, global numbering --
+        is the library's C++ (csrc/dist.cu, oshb_dist_refine_by_size) over NCCL; this method only re-ghosts when
+        the halo is used up. OSHB_DIST_PY=1 runs the earlier torch-level orchestration of the same stages instead
+        (kept as a second implementation the tests compare against)."""
+        if USE_PY_PASS:
+            return self._refine_by_size_py(opts)
+        mesh = self.mesh
+        opts = opts or AdaptOpts(mesh.dim(), mesh.lib)
+        comm = library_comm(mesh.lib, self.device, self.group)
+        while True:
+            passes = C.c_int(self.passes)
+            ng = (C.c_int64 * 4)(*[int(x) for x in (list(self.nglobal) + [0, 0, 0, 0])[:4]])
+            res = C.c_int()
+            st = _DistStatsC()
+            o = opts._c()
+            self.dm._pre()
+            mesh.lib.check(mesh.lib.c.oshb_dist_refine_by_size(mesh.h, comm, C.byref(o), C.c_int(self.halo), C.byref(passes),
+                                                               ng, C.byref(res), C.byref(st)))
+            if res.value == 2:
+                with _Section(self.dm, "reghost"):
+                    self.reghost()
+                mesh = self.mesh
+                continue
+            if res.value == 0:
+                return False
+            self.passes = passes.value
+            self.nglobal = [int(x) for x in ng][:len(self.nglobal)]
+            self.last = {"rounds": st.rounds, "nkeys_local": st.nkeys_local, "shell_edges": st.shell_edges}
+            return True
+
+    def _refine_by_size_py(self, opts=None):
         mesh, dm, dev = self.mesh, self.dm, self.device
         dim = mesh.dim()
         opts = opts or AdaptOpts(dim, mesh.lib)
@@ -419,7 +533,7 @@ class DistMesh:
                 ps.close()
                 with _Section(dm, "reghost"):
                     self.reghost()
-                return self.refine_by_size(opts)
+                return self._refine_by_size_py(opts)
             with _Section(dm, "begin(lib)"):
                 ps.begin(1)
                 # the qualities of this rank's own edges (depth <= 0) are final before any exchange
