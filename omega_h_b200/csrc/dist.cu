@@ -280,7 +280,12 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
   int* cells = reinterpret_cast<int*>(static_cast<char*>(ctx().dscratch) + 1408);  // 2 ints
 
   // ---- candidates + cavity qualities + set states; is there work anywhere?
-  pass_begin(ps, 1);
+  // Edges beyond the shell (depth > trust + 1) are stale on this rank -- their elements were not refined here in
+  // earlier passes -- and nobody ever asks for them: they are not candidates, so nothing is evaluated for them
+  // and the last call of a loop (nothing left within depth 0) evaluates nothing at all. With the halo used up
+  // only the candidate marks are needed to decide between "done" and "re-ghost".
+  pass_set_depth_limit(ps, trust + 1 < 0 ? 0 : trust + 1);
+  pass_begin(ps, trust < 0 ? 2 : 1);
   LOs edge_own = mesh->get_los(EDGE, "own:part");
   LO const* own = edge_own.data();
   LO const nedges = mesh->nedges();
@@ -288,14 +293,14 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
   Bytes state_a = pass_states(ps);
   Reals quals = pass_qualities(ps);
   I8 const* cd = cand.data();
-  I8* state = state_a.data();
+  I8* state = state_a.data();  // (absent after a candidates-only begin)
   {
     int z[2] = {0, 0};
     h2d(cells, z, sizeof(z));
     parallel_for(nedges, OSHB_LAMBDA(LO e) {
       if (depth_of(own[e]) > 0) return;  // not mine
       if (cd[e]) raise_flag(cells, 1);
-      if (state[e] == 2) raise_flag(cells + 1, 1);
+      if (state && state[e] == 2) raise_flag(cells + 1, 1);
     }, "dist(flags)");
     comm->allreduce_max_i32(cells, 2);
     d2h(z, cells, sizeof(z));

@@ -238,6 +238,7 @@ void pass_select_keys(Pass* p);
 void pass_number(Pass* p, bool external_globals);
 void pass_finish(Pass* p);
 LO pass_nkeys(Pass* p);
+void pass_set_depth_limit(Pass* p, int limit);  // partitioned callers: deeper edges are stale, not candidates
 Bytes pass_candidates(Pass* p);
 Bytes pass_states(Pass* p);
 Reals pass_qualities(Pass* p);

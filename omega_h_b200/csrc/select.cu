@@ -329,6 +329,9 @@ struct Pass {
   int rounds = 0;
   bool flags_clean = false;
   int* flags3 = nullptr;
+  // a partitioned caller: edges deeper than this layer of the "own:part" tag are stale (never refined on this rank,
+  // never sent to anyone) and are not candidates; 127 = no limit
+  int depth_limit = 127;
   // distributed numbering (runs_begin .. runs_commit): all dimensions on one concatenated axis
   struct Numbering {
     int me = 0, trust = 0, dim = 0;
@@ -390,8 +393,13 @@ int Pass::begin(int keep_going) {
   {
     Real const* len = lengths.data();
     Real const maxlen = opts.max_length_desired;
+    LOs own_tag;
+    if (depth_limit < 127) own_tag = mesh->get_los(EDGE, "own:part");
+    LO const* own = own_tag.exists() ? own_tag.data() : nullptr;
+    int const limit = depth_limit;
     parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool {
       bool c = len[e] > maxlen;
+      if (own && int(I8(own[e] & 0xff)) > limit) c = false;
       cand[e] = c ? 1 : 0;
       return c;
     }, flags3, 1, "each_gt");
@@ -828,6 +836,7 @@ Pass* pass_create(Mesh* mesh, AdaptOpts const& opts) {
   return p;
 }
 void pass_destroy(Pass* p) { delete p; }
+void pass_set_depth_limit(Pass* p, int limit) { p->depth_limit = limit; }
 int pass_begin(Pass* p, int keep_going) { return p->begin(keep_going); }
 int pass_restate(Pass* p, bool read) { return p->restate(read); }
 int pass_indset_round(Pass* p, bool read) { return p->indset_round(read); }
