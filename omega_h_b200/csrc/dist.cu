@@ -297,11 +297,11 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
   {
     int z[2] = {0, 0};
     h2d(cells, z, sizeof(z));
-    parallel_for(nedges, OSHB_LAMBDA(LO e) {
-      if (depth_of(own[e]) > 0) return;  // not mine
-      if (cd[e]) raise_flag(cells, 1);
-      if (state && state[e] == 2) raise_flag(cells + 1, 1);
-    }, "dist(flags)");
+    // block-reduced flags (one atomic per CTA): "is any of my own edges a candidate" / "... still undecided"
+    parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool { return cd[e] && depth_of(own[e]) <= 0; }, cells, 1, "dist(flags)");
+    if (state)
+      parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool { return state[e] == 2 && depth_of(own[e]) <= 0; }, cells + 1, 1,
+          "dist(flags)");
     comm->allreduce_max_i32(cells, 2);
     d2h(z, cells, sizeof(z));
     if (!z[0]) return 0;
@@ -393,9 +393,8 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
     ++rounds;
     int z = 0;
     h2d(cells, &z, sizeof(int));
-    parallel_for(nedges, OSHB_LAMBDA(LO e) {
-      if (depth_of(own[e]) <= 0 && state[e] == 2) raise_flag(cells, 1);
-    }, "dist(undecided)");
+    parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool { return state[e] == 2 && depth_of(own[e]) <= 0; }, cells, 1,
+        "dist(undecided)");
     comm->allreduce_max_i32(cells, 1);
     d2h(&z, cells, sizeof(int));
     if (!z) break;
