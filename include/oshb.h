@@ -44,6 +44,12 @@ int oshb_is_emulation(void);
 uint64_t oshb_launch_count(void);
 uint64_t oshb_sync_count(void);
 uint64_t oshb_peak_bytes(void);
+/* The library keeps freed device memory in its own pool (256 MB+ segments, best fit). oshb_trim returns every wholly
+ * free segment to the driver so that another allocator of the same process (torch's, a caller's) can use it;
+ * oshb_set_oom_callback registers what the library calls -- after trimming itself -- before it gives up on an
+ * allocation, e.g. to make that other allocator release ITS idle memory (torch.cuda.empty_cache). */
+int oshb_trim(void);
+int oshb_set_oom_callback(void (*fn)(void* user), void* user);
 /* raw device memory for callers without their own allocator (Write<T>, src/Omega_h_array.hpp:23) */
 int oshb_dev_alloc(uint64_t bytes, void** d_out);
 int oshb_dev_free(void* d_ptr, uint64_t bytes);

@@ -46,7 +46,7 @@ class PassStatsC(C.Structure):
 # every symbol include/oshb.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "oshb_init", "oshb_sync", "oshb_set_stream", "oshb_last_error", "oshb_is_emulation", "oshb_launch_count", "oshb_sync_count",
-    "oshb_peak_bytes", "oshb_dev_alloc", "oshb_dev_free", "oshb_h2d", "oshb_d2h",
+    "oshb_peak_bytes", "oshb_trim", "oshb_set_oom_callback", "oshb_dev_alloc", "oshb_dev_free", "oshb_h2d", "oshb_d2h",
     "oshb_offset_scan_i8", "oshb_offset_scan_i32", "oshb_offset_scan_i32_i64", "oshb_collect_marked",
     "oshb_max_i8", "oshb_minmax_f64", "oshb_sort_by_keys_i32", "oshb_sort_by_keys_i64",
     "oshb_unmap", "oshb_map_into", "oshb_expand_into", "oshb_mark_image", "oshb_invert_injective_map",

@@ -92,6 +92,12 @@ Block* new_segment(size_t need) {
       seg_size = ((need + kAlign - 1) / kAlign) * kAlign;
       e = cudaMalloc(&p, seg_size);
     }
+    if (e != cudaSuccess && oom_hook().fn) {
+      // another allocator in the process (e.g. torch's caching allocator) may hold idle memory: ask it to let go
+      cudaGetLastError();
+      oom_hook().fn(oom_hook().user);
+      e = cudaMalloc(&p, seg_size);
+    }
     if (e != cudaSuccess) {
       cudaGetLastError();
       fail(__FILE__, __LINE__, "out of device memory: cannot allocate " + std::to_string(seg_size) + " bytes (" +
@@ -105,6 +111,13 @@ Block* new_segment(size_t need) {
 }
 
 }  // namespace
+
+OomHook& oom_hook() {
+  static OomHook h;
+  return h;
+}
+// give every wholly free segment back to the driver (oshb_trim): lets another allocator of the process use it
+void dev_trim() { release_free_segments(); }
 
 void* dev_alloc(size_t bytes) {
   Ctx& c = ctx();
@@ -169,6 +182,11 @@ size_t dev_reserved_bytes() { return g_reserved; }
 #else
 
 size_t dev_reserved_bytes() { return 0; }
+OomHook& oom_hook() {
+  static OomHook h;
+  return h;
+}
+void dev_trim() {}
 
 #endif
 

@@ -91,6 +91,17 @@ int oshb_set_stream(void* cuda_stream) {
 #endif
   OSHB_CATCH
 }
+int oshb_trim(void) {
+  OSHB_TRY
+  dev_trim();
+  OSHB_CATCH
+}
+int oshb_set_oom_callback(void (*fn)(void* user), void* user) {
+  OSHB_TRY
+  oom_hook().fn = fn;
+  oom_hook().user = user;
+  OSHB_CATCH
+}
 const char* oshb_last_error(void) { return oshb::last_error_string().c_str(); }
 int oshb_is_emulation(void) {
 #ifdef OSHB_EMU

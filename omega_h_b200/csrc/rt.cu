@@ -127,7 +127,19 @@ void dev_memset(void* dst, int byte, size_t bytes) { memset(dst, byte, bytes); }
 
 void init_ctx(int device) {
   Ctx& c = g_ctx;
-  if (c.ready) return;
+  if (c.ready) {
+    // one process drives one GPU: a second oshb_init with another device is a caller error, and a host thread
+    // that has not selected the library's device yet must do so before it launches on the library's pointers
+    if (device >= 0 && device != c.device)
+      fail(__FILE__, __LINE__, "oshb_init(" + std::to_string(device) + ") after the library was bound to device " +
+                                   std::to_string(c.device) + " (the first ABI call binds it; call oshb_init(LOCAL_RANK) first)");
+    static thread_local bool device_selected = false;
+    if (!device_selected) {
+      OSHB_CUDA(cudaSetDevice(c.device));
+      device_selected = true;
+    }
+    return;
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {

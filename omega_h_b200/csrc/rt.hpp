@@ -100,6 +100,12 @@ inline void algo_bytes(int64_t bytes) {
 void init_ctx(int device);  // idempotent; fails loudly when no CUDA device is usable
 void sync_stream();
 
+struct OomHook {
+  void (*fn)(void*) = nullptr;
+  void* user = nullptr;
+};
+OomHook& oom_hook();
+void dev_trim();
 void* dev_alloc(size_t bytes);
 void dev_free(void* p, size_t bytes);
 void h2d(void* dst, void const* src, size_t bytes);

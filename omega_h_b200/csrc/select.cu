@@ -756,6 +756,16 @@ GOs Pass::runs_lookup(GOs keys) {
   GO const* b1 = n.bases[1].data();
   GO const* b2 = n.dim >= 2 ? n.bases[2].data() : nullptr;
   GO const* b3 = n.dim >= 3 ? n.bases[3].data() : nullptr;
+  GO const* g0 = n.gid[0].data();
+  GO const* g1 = n.gid[1].data();
+  GO const* g2 = n.dim >= 2 ? n.gid[2].data() : nullptr;
+  GO const* g3 = n.dim >= 3 ? n.gid[3].data() : nullptr;
+  LO const* o0 = n.own[0].data();
+  LO const* o1 = n.own[1].data();
+  LO const* o2 = n.dim >= 2 ? n.own[2].data() : nullptr;
+  LO const* o3 = n.dim >= 3 ? n.own[3].data() : nullptr;
+  GO const k0 = n.koff[0], k1 = n.koff[1], k2 = n.koff[2], k3 = n.koff[3];
+  int const me_ = n.me;
   int* err = device_error_cell();
   parallel_for(nk, OSHB_LAMBDA(LO j) {
     GO key = kp[j];
@@ -775,10 +785,20 @@ GOs Pass::runs_lookup(GOs keys) {
       return;
     }
     LO p = LO(pos);
-    if (p < l1) op[j] = b0[p];
-    else if (p < l2 || dim_ < 2) op[j] = b1[p - l1];
-    else if (p < l3 || dim_ < 3) op[j] = b2[p - l2];
-    else op[j] = b3[p - l3];
+    int d = (p < l1) ? 0 : ((p < l2 || dim_ < 2) ? 1 : ((p < l3 || dim_ < 3) ? 2 : 3));
+    LO i = p - ((d == 0) ? 0 : (d == 1 ? l1 : (d == 2 ? l2 : l3)));
+    GO const* gd = (d == 0) ? g0 : (d == 1 ? g1 : (d == 2 ? g2 : g3));
+    LO const* od = (d == 0) ? o0 : (d == 1 ? o1 : (d == 2 ? o2 : o3));
+    GO const kd = (d == 0) ? k0 : (d == 1 ? k1 : (d == 2 ? k2 : k3));
+    // the position must be counted by this rank and hold exactly the asked number (a key that falls between
+    // two runs, onto an entity another rank counts, would otherwise get a wrong base silently)
+    if ((od[i] >> 8) != me_ || gd[i] + kd != key) {
+      raise_flag(err, 8);
+      op[j] = -1;
+      return;
+    }
+    GO const* bd = (d == 0) ? b0 : (d == 1 ? b1 : (d == 2 ? b2 : b3));
+    op[j] = bd[i];
   }, "numbering(lookup)");
   return out;
 }

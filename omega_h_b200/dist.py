@@ -79,12 +79,35 @@ class _Section:
 _SHARED = {}
 
 
+_OOM_KEEP = {}
+
+
+def cooperate_on_memory(lib, device):
+    """Two caching allocators share the GPU (the library's pool and torch's): neither can reclaim the other's idle
+    blocks by itself. Register torch.cuda.empty_cache as the library's out-of-memory callback, and call
+    release_idle() after the big torch-side steps (distribute / reghost / gather) so that both pools shrink back."""
+    device = torch.device(device)
+    if device.type != "cuda" or id(lib) in _OOM_KEEP:
+        return
+    cb = C.CFUNCTYPE(None, C.c_void_p)(lambda user: torch.cuda.empty_cache())
+    _OOM_KEEP[id(lib)] = cb
+    lib.check(lib.c.oshb_set_oom_callback(cb, None))
+
+
+def release_idle(lib, device):
+    """torch's idle cache back to the driver (the library retries a failed allocation after its OOM callback; torch
+    does not call back, so its cache is emptied eagerly after the steps that use it heavily)"""
+    if torch.device(device).type == "cuda":
+        torch.cuda.empty_cache()
+
+
 def share_stream(lib, device):
     """Put torch (and with it torch.distributed's collectives) and the library on ONE CUDA stream, so
     buffers pass between them in stream order with no host synchronisation. Call once per process."""
     device = torch.device(device)
     if device.type != "cuda" or id(lib) in _SHARED:
         return
+    cooperate_on_memory(lib, device)
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)
     lib.check(lib.c.oshb_set_stream(C.c_void_p(stream.cuda_stream)))
@@ -697,6 +720,8 @@ class DistMesh:
         self.mesh, self.dm = fresh.mesh, fresh.dm
         self.passes = 0
         self.reghosts = getattr(self, "reghosts", 0) + 1
+        del own, depth, gid, down, cv2v, mine, band, got, uniq, new_down, new_tags, first
+        release_idle(mesh.lib, dev)
 
     # ---- the whole mesh on one rank ----------------------------------------------------------------
     def gather(self, root=0):
@@ -923,4 +948,7 @@ def distribute(base, halo, device, group=None, parting="hilbert"):
         tags[d] = [(name, nc, src.tag(d, name)) for name, _, nc in base.tags(d)
                    if name != "global" and not name.startswith("own:")]
     gids = {d: src.tag(d, "global") for d in range(dim + 1)}
-    return _build_part(base.lib, device, group, dim, n, down, cv2v, tags, gids, owner, halo, n)
+    part = _build_part(base.lib, device, group, dim, n, down, cv2v, tags, gids, owner, halo, n)
+    del down, cv2v, tags, gids, owner
+    release_idle(base.lib, device)
+    return part
