@@ -63,13 +63,100 @@ LOs collect_marked(Bytes marks, LO* count_out) {
 
 // ---------------------------------------------------------------------------------------
 // invert_adj: upward adjacency from downward.
-//   1. degree histogram of the lows (integer atomics)
+//   1. degree histogram of the lows (integer atomics, no return value)
 //   2. offset scan
 //   3. slot claim (atomics; arrival order is arbitrary)
-//   4. one thread per low sorts its short row by high-low use index (== by high index,
-//      src/Omega_h_adj.cpp:178-200) and emits high index + upward code in the same pass
+//   4. rows sorted by high-low use index (== by high index, src/Omega_h_adj.cpp:178-200) and
+//      high index + upward code emitted, one CTA per 256 consecutive lows: their rows are one
+//      contiguous segment of the slot array, which is staged in shared memory with coalesced
+//      loads; eight lanes share a row and every ENTRY ranks itself inside its row by counting the
+//      smaller entries (rows are short: the O(len^2) compares run on broadcast 16-byte
+//      shared-memory reads) and writes high + code straight to its sorted position. A segment
+//      that does not fit the stage, and meshes whose rows are short on average, go through one
+//      thread per row (register sorting networks, sortnet.hpp).
 // Algorithmic bytes: in 4*N*d (+N*d codes); out 4*(L+1) + 4*N*d + N*d.
 // ---------------------------------------------------------------------------------------
+OSHB_HD void emit_up(LO hl, int deg_h, I8 const* dcodes, LO* h_out, I8* c_out, int64_t at) {
+  LO h = hl / deg_h;
+  int which_down = hl - h * deg_h;
+  h_out[at] = h;
+  if (dcodes) {
+    I8 dc = dcodes[hl];
+    c_out[at] = make_code(code_is_flipped(dc), code_rotation(dc), which_down);
+  } else {
+    c_out[at] = make_code(false, 0, which_down);
+  }
+}
+
+#ifndef OSHB_EMU
+constexpr int IA_T = 256;     // threads per CTA
+constexpr int IA_R = 256;     // lows per CTA iteration (with vertex -> tets rows of ~24 the segment fills the stage)
+constexpr int IA_CAP = 8192;  // staged entries per CTA iteration
+constexpr int IA_G = 8;       // lanes that share a row
+
+template <int DEG>
+__global__ void __launch_bounds__(IA_T) k_rows_sort(LO const* off, LO* slots, LO nlows, int deg_rt, I8 const* dcodes,
+    LO* h_out, I8* c_out) {
+  __shared__ __align__(16) LO s_val[IA_CAP];
+  __shared__ LO s_off[IA_R + 1];
+  int const deg_h = DEG ? DEG : deg_rt;
+  int const tid = threadIdx.x;
+  int const grp = tid / IA_G, sub = tid % IA_G;
+  LO const nblk = (nlows + IA_R - 1) / IA_R;
+  for (LO blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    LO const l0 = blk * IA_R;
+    int const nrows = (nlows - l0 < IA_R) ? int(nlows - l0) : IA_R;
+    for (int r = tid; r <= nrows; r += IA_T) s_off[r] = off[l0 + r];
+    __syncthreads();
+    LO const seg_b = s_off[0];
+    int const n = int(s_off[nrows] - seg_b);
+    if (n <= IA_CAP) {
+      for (int i = tid; i < n; i += IA_T) s_val[i] = slots[int64_t(seg_b) + i];
+      __syncthreads();
+      for (int r = grp; r < nrows; r += IA_T / IA_G) {
+        int const b = int(s_off[r] - seg_b), e = int(s_off[r + 1] - seg_b);
+        for (int i = b + sub; i < e; i += IA_G) {
+          LO const v = s_val[i];
+          // rank of the entry inside its row: scalar head up to a 16-byte boundary, 4 entries per
+          // shared-memory load, scalar tail
+          int rank = 0;
+          int j = b;
+          for (; j < e && (j & 3); ++j) rank += (s_val[j] < v) ? 1 : 0;
+          for (; j + 4 <= e; j += 4) {
+            int4 const q = *reinterpret_cast<int4 const*>(s_val + j);
+            rank += ((q.x < v) ? 1 : 0) + ((q.y < v) ? 1 : 0) + ((q.z < v) ? 1 : 0) + ((q.w < v) ? 1 : 0);
+          }
+          for (; j < e; ++j) rank += (s_val[j] < v) ? 1 : 0;
+          emit_up(v, deg_h, dcodes, h_out, c_out, int64_t(seg_b) + b + rank);
+        }
+      }
+    } else {
+      for (int r = tid; r < nrows; r += IA_T) {
+        LO const b = s_off[r], e = s_off[r + 1];
+        sort_small_row(slots + b, e - b);
+        for (LO i = b; i < e; ++i) emit_up(slots[i], deg_h, dcodes, h_out, c_out, i);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int DEG>
+static void launch_rows_sort(LO const* off, LO* slots, LO nlows, int deg_h, I8 const* dcodes, LO* h_out, I8* c_out) {
+  Ctx& c = ctx();
+  int64_t blocks = (int64_t(nlows) + IA_R - 1) / IA_R;
+  int64_t const cap = int64_t(c.sms) * 6;
+  if (blocks > cap) blocks = cap;
+  if (blocks <= 0) return;
+  if (c.prof_on) prof_begin("invert_adj(sort+separate)");
+  k_rows_sort<DEG><<<unsigned(blocks), IA_T, 0, c.stream>>>(off, slots, nlows, deg_h, dcodes, h_out, c_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(__FILE__, __LINE__, std::string("kernel launch: ") + cudaGetErrorString(e));
+  if (c.prof_on) prof_end("invert_adj(sort+separate)");
+  c.launches++;
+}
+#endif
+
 Adj invert_adj(Adj const& down, int nlows_per_high, LO nlows) {
   int64_t const nhl = down.ab2b.size();
   LOs degrees = filled<LO>(nlows, 0);
@@ -92,24 +179,30 @@ Adj invert_adj(Adj const& down, int nlows_per_high, LO nlows) {
   I8* c_out = codes.data();
   I8 const* dcodes = down.codes.exists() ? down.codes.data() : nullptr;
   int const deg_h = nlows_per_high;
-  parallel_for(nlows, OSHB_LAMBDA(LO l) {
-    LO const b = off[l];
-    LO const e = off[l + 1];
-    LO const len = e - b;
-    sort_small_row(slots + b, len);  // sortnet.hpp: register networks up to 64 entries
-    for (LO i = b; i < e; ++i) {
-      LO hl = slots[i];
-      LO h = hl / deg_h;
-      int which_down = hl - h * deg_h;
-      h_out[i] = h;
-      if (dcodes) {
-        I8 dc = dcodes[hl];
-        c_out[i] = make_code(code_is_flipped(dc), code_rotation(dc), which_down);
-      } else {
-        c_out[i] = make_code(false, 0, which_down);
-      }
-    }
-  }, "invert_adj(sort+separate)");
+  // short rows (edge -> faces ~5, face -> tets <= 2): one thread per row, sorting network in registers
+  // (measured faster than the staged tile there: 2.8 / 4.0 / 3.9 ms against 4.9 / 6.5 / 6.6 at 100 M tets);
+  // long rows (vertex -> tets ~24): the staged tile (7.2 -> 2.7 ms)
+  bool per_row = nhl < int64_t(nlows) * 10;
+#ifdef OSHB_EMU
+  per_row = true;
+#endif
+  if (per_row) {
+    parallel_for(nlows, OSHB_LAMBDA(LO l) {
+      LO const b = off[l];
+      LO const e = off[l + 1];
+      sort_small_row(slots + b, e - b);
+      for (LO i = b; i < e; ++i) emit_up(slots[i], deg_h, dcodes, h_out, c_out, i);
+    }, "invert_adj(sort+separate)");
+  }
+#ifndef OSHB_EMU
+  else switch (deg_h) {
+    case 2: launch_rows_sort<2>(off, slots, nlows, deg_h, dcodes, h_out, c_out); break;
+    case 3: launch_rows_sort<3>(off, slots, nlows, deg_h, dcodes, h_out, c_out); break;
+    case 4: launch_rows_sort<4>(off, slots, nlows, deg_h, dcodes, h_out, c_out); break;
+    case 6: launch_rows_sort<6>(off, slots, nlows, deg_h, dcodes, h_out, c_out); break;
+    default: launch_rows_sort<0>(off, slots, nlows, deg_h, dcodes, h_out, c_out); break;
+  }
+#endif
   Adj up;
   up.a2ab = l2lh;
   up.ab2b = lh2h;
@@ -285,6 +378,79 @@ LOs form_uses(LOs hv2v, int high_dim, int low_dim) {
 // Algorithmic bytes: 4*N*(hd+1) + 4*L*(ld+1) in, 5*N*n_l out; the bucket
 // table adds one write + ~one read of (8|16)*L.
 // ---------------------------------------------------------------------------------------
+// probe: one thread per use rotates the use to its smallest vertex, streams that one bucket row (one vector
+// load per entry) and compares; the code follows from the two rotations and the flip. A one-thread-per-high
+// variant (one row per distinct smallest vertex: 2 rows per tet instead of 4, rows read once for three uses)
+// was built and measured SLOWER (14.1 against 10.3 ms at 100 M tets): the kernel is bound by the number of
+// distinct 32-byte sectors a warp asks of L1 per instruction, and the four uses of a tet in adjacent lanes
+// share theirs.
+static void reflect_probe(LO const* hv, LO const* off, LO const* tab, int64_t nhigh, int high_dim, int low_dim, LO* out,
+    I8* cout, int* err) {
+  int const nvh = high_dim + 1;
+  int const nvl = low_dim + 1;
+  int const nlh = simplex_degree(high_dim, low_dim);
+  parallel_for(nhigh * nlh, OSHB_LAMBDA(LO u) {
+    LO h = u / nlh;
+    int w = u - h * nlh;
+    LO uv[3];
+    for (int k = 0; k < nvl; ++k) uv[k] = hv[int64_t(h) * nvh + simplex_down_template(high_dim, low_dim, w, k)];
+    int um = 0;
+    for (int k = 1; k < nvl; ++k)
+      if (uv[k] < uv[um]) um = k;
+    LO const m = uv[um];
+    LO const rb = off[m];
+    LO const re = off[m + 1];
+    LO found = -1;
+    I8 code = 0;
+    if (nvl == 2) {
+      LO other = uv[1 - um];
+      for (LO s = rb; s < re; ++s) {
+#ifdef OSHB_EMU
+        LO const qx = tab[int64_t(s) * 2], qy = tab[int64_t(s) * 2 + 1];
+#else
+        int2 const q = reinterpret_cast<int2 const*>(tab)[s];
+        LO const qx = q.x, qy = q.y;
+#endif
+        if (qx == other) {
+          found = qy >> 1;
+          int jm = qy & 1;
+          // which_down = position in the low of the use's first vertex
+          code = make_code(false, (um == 0) ? jm : (1 - jm), 0);
+          break;
+        }
+      }
+    } else {
+      LO ua = uv[(um + 1) % 3];
+      LO ub = uv[(um + 2) % 3];
+      for (LO s = rb; s < re; ++s) {
+#ifdef OSHB_EMU
+        LO const qx = tab[int64_t(s) * 4], qy = tab[int64_t(s) * 4 + 1], qz = tab[int64_t(s) * 4 + 2],
+                 qw = tab[int64_t(s) * 4 + 3];
+#else
+        int4 const q = reinterpret_cast<int4 const*>(tab)[s];
+        LO const qx = q.x, qy = q.y, qz = q.z, qw = q.w;
+#endif
+        bool same = (qx == ua && qy == ub);
+        bool flip = (qx == ub && qy == ua);
+        if (same || flip) {
+          found = qz;
+          int jm = qw;
+          // low's vertex list b: b[jm]=m, b[jm+1]=va, b[jm+2]=vb.
+          // position j in b of the use's first vertex uv[0]:
+          //   same orientation: uv[0] = uv[um - um] sits um steps before m  -> j = jm - um
+          //   flipped         : walking the use forward walks the low backward -> j = jm + um
+          int j = same ? ((jm - um + 3) % 3) : ((jm + um) % 3);
+          code = make_code(flip, rotation_to_first(3, j), 0);
+          break;
+        }
+      }
+    }
+    if (found < 0) atomic_or_i32(err, 1);
+    out[u] = found;
+    cout[u] = code;
+  }, "reflect_down(probe)");
+}
+
 Adj reflect_down(LOs hv2v, LOs lv2v, LO nverts, int high_dim, int low_dim) {
   OSHB_CHECK(low_dim == 1 || low_dim == 2);
   OSHB_CHECK(high_dim > low_dim && high_dim <= 3);
@@ -354,61 +520,7 @@ Adj reflect_down(LOs hv2v, LOs lv2v, LO nverts, int high_dim, int low_dim) {
   LOs hl2l(nhigh * nlh);
   Bytes codes(nhigh * nlh);
   algo_bytes(nhigh * (4 * nvh + 5 * nlh) + nlow * 4 * ewords);
-  LO* out = hl2l.data();
-  I8* cout = codes.data();
-  LO const* hv = hv2v.data();
-  parallel_for(nhigh * nlh, OSHB_LAMBDA(LO u) {
-    LO h = u / nlh;
-    int w = u - h * nlh;
-    LO uv[3];
-    for (int k = 0; k < nvl; ++k) uv[k] = hv[int64_t(h) * nvh + simplex_down_template(high_dim, low_dim, w, k)];
-    // position of the smallest vertex of the use
-    int um = 0;
-    for (int k = 1; k < nvl; ++k)
-      if (uv[k] < uv[um]) um = k;
-    LO const m = uv[um];
-    LO const rb = off[m];
-    LO const re = off[m + 1];
-    LO found = -1;
-    I8 code = 0;
-    if (nvl == 2) {
-      LO other = uv[1 - um];
-      for (LO s = rb; s < re; ++s) {
-        if (tab[int64_t(s) * 2] == other) {
-          LO packed = tab[int64_t(s) * 2 + 1];
-          found = packed >> 1;
-          int jm = packed & 1;
-          // which_down = position in the low of the use's first vertex
-          int which_down = (um == 0) ? jm : (1 - jm);
-          code = make_code(false, which_down, 0);
-          break;
-        }
-      }
-    } else {
-      LO ua = uv[(um + 1) % 3];
-      LO ub = uv[(um + 2) % 3];
-      for (LO s = rb; s < re; ++s) {
-        LO va = tab[int64_t(s) * 4 + 0];
-        LO vb = tab[int64_t(s) * 4 + 1];
-        bool same = (va == ua && vb == ub);
-        bool flip = (va == ub && vb == ua);
-        if (same || flip) {
-          found = tab[int64_t(s) * 4 + 2];
-          int jm = tab[int64_t(s) * 4 + 3];
-          // low's vertex list b: b[jm]=m, b[jm+1]=va, b[jm+2]=vb.
-          // position j in b of the use's first vertex uv[0]:
-          //   same orientation: uv[0] = uv[um - um] sits um steps before m  -> j = jm - um
-          //   flipped         : walking the use forward walks the low backward -> j = jm + um
-          int j = same ? ((jm - um + 3) % 3) : ((jm + um) % 3);
-          code = make_code(flip, rotation_to_first(3, j), 0);
-          break;
-        }
-      }
-    }
-    if (found < 0) atomic_or_i32(err, 1);
-    out[u] = found;
-    cout[u] = code;
-  }, "reflect_down(probe)");
+  reflect_probe(hv2v.data(), off, tab, nhigh, high_dim, low_dim, hl2l.data(), codes.data(), err);
   Adj a;
   a.ab2b = hl2l;
   a.codes = codes;

@@ -22,6 +22,7 @@
 #include "mesh.hpp"
 
 #include <algorithm>
+#include <time.h>
 
 #ifndef OSHB_EMU
 #include <dlfcn.h>
@@ -187,6 +188,59 @@ int comm_size(Comm* c) { return c->size; }
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
+// OSHB_DIST_TIMING=1: wall clock per stage of the partitioned pass, the stream drained at every mark
+// (diagnosis only: the marks serialise host and device), printed per rank when the process ends
+struct StageClock {
+  bool on;
+  std::vector<std::pair<std::string, double>> acc;
+  double t_last = 0;
+  int calls = 0, skip = 0;
+  StageClock() {
+    on = getenv("OSHB_DIST_TIMING") != nullptr;
+    if (getenv("OSHB_DIST_TIMING_SKIP")) skip = atoi(getenv("OSHB_DIST_TIMING_SKIP"));
+  }
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return double(ts.tv_sec) + 1e-9 * double(ts.tv_nsec);
+  }
+  void start() {
+    if (!on) return;
+    sync_stream();
+    t_last = now();
+    ++calls;
+  }
+  void mark(char const* name) {
+    if (!on) return;
+    sync_stream();
+    double t = now();
+    if (calls <= skip) {  // warm-up calls (NCCL connects lazily on first use of every pair)
+      t_last = t;
+      return;
+    }
+    for (auto& kv : acc)
+      if (kv.first == name) {
+        kv.second += t - t_last;
+        t_last = t;
+        return;
+      }
+    acc.push_back(std::make_pair(std::string(name), t - t_last));
+    t_last = t;
+  }
+  ~StageClock() {
+    if (!on || acc.empty()) return;
+    char const* r = getenv("RANK");
+    double tot = 0;
+    for (auto& kv : acc) tot += kv.second;
+    fprintf(stderr, "[oshb dist timing] rank %s: %d calls after %d skipped, %.3f ms total\n", r ? r : "?", calls - skip, skip, tot * 1e3);
+    for (auto& kv : acc) fprintf(stderr, "[oshb dist timing] rank %s   %-28s %9.3f ms\n", r ? r : "?", kv.first.c_str(), kv.second * 1e3);
+  }
+};
+StageClock& stage_clock() {
+  static StageClock c;
+  return c;
+}
+
 OSHB_HD int depth_of(LO own) { return int(I8(own & 0xff)); }
 
 // first index in [0, n] with a[idx] >= x (a ascending)
@@ -284,8 +338,10 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
   // earlier passes -- and nobody ever asks for them: they are not candidates, so nothing is evaluated for them
   // and the last call of a loop (nothing left within depth 0) evaluates nothing at all. With the halo used up
   // only the candidate marks are needed to decide between "done" and "re-ghost".
+  stage_clock().start();
   pass_set_depth_limit(ps, trust + 1 < 0 ? 0 : trust + 1);
   pass_begin(ps, trust < 0 ? 2 : 1);
+  stage_clock().mark("begin");
   LOs edge_own = mesh->get_los(EDGE, "own:part");
   LO const* own = edge_own.data();
   LO const nedges = mesh->nedges();
@@ -304,6 +360,7 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
           "dist(flags)");
     comm->allreduce_max_i32(cells, 2);
     d2h(z, cells, sizeof(z));
+    stage_clock().mark("flags allreduce");
     if (!z[0]) return 0;
     if (trust < 0) return 2;
     if (!z[1]) return 0;
@@ -381,15 +438,20 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
     }, "dist(answers)");
     if (stats) stats->shell_edges = nshell;
   }
+  stage_clock().mark("shell plan");
 
   // ---- qualities of the shell from their owners, then the states follow from them
   pull<Real>(comm, plan, quals.data());
+  stage_clock().mark("pull qualities");
   pass_restate(ps, false);
+  stage_clock().mark("restate");
   // ---- independent set: one round, the shell's states from their owners, anybody undecided?
   int rounds = 0;
   while (true) {
     pass_indset_round(ps, false);
+    stage_clock().mark("indset round");
     pull<I8>(comm, plan, state);
+    stage_clock().mark("pull states");
     ++rounds;
     int z = 0;
     h2d(cells, &z, sizeof(int));
@@ -397,6 +459,7 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
         "dist(undecided)");
     comm->allreduce_max_i32(cells, 1);
     d2h(&z, cells, sizeof(int));
+    stage_clock().mark("undecided allreduce");
     if (!z) break;
     OSHB_CHECK(rounds < 10000);
   }
@@ -411,7 +474,9 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
     stats->rounds = rounds;
     stats->nkeys_local = nkeys;
   }
+  stage_clock().mark("select keys");
   if (nkeys) pass_number(ps, true);
+  stage_clock().mark("number");
 
   // ---- global numbers (a rank where nothing splits still renumbers: every number shifts with the others' products)
   GO nnext[4] = {0, 0, 0, 0};
@@ -428,6 +493,7 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
     LOs want_owner;
     pass_runs_get(ps, &run_key, &run_sum);
     pass_want_get(ps, &want_key, &want_owner);
+    stage_clock().mark("runs begin");
     LO const nr = LO(nruns), nw = LO(nwant);
     // runs per partition rank of the key axis + their sums; wanted entities per owner; new totals -> one all-gather
     GOs inc(int64_t(nr) + 1);
@@ -459,6 +525,7 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
     GOs table(int64_t(P) * W);
     comm->allgather_i64(mine.data(), W, table.data());
     std::vector<GO> th = table.to_host();
+    stage_clock().mark("numbering sizes allgather");
     auto T = [&](int r, int k) { return th[int64_t(r) * W + k]; };
     std::vector<int64_t> run_send(P), run_recv(P), want_send(P), want_recv(P);
     GO sums_total = 0, below = 0, next_total = 0;
@@ -516,7 +583,9 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
     comm->alltoallv(excl.data(), run_recv.data(), run_base.data(), run_send.data(), int(sizeof(GO)));
     GO new_off[4] = {0, 0, 0, 0};
     for (int d = 1; d < 4; ++d) new_off[d] = new_off[d - 1] + nnext[d - 1];
+    stage_clock().mark("run bases exchange");
     pass_runs_set_bases(ps, run_base, new_off);
+    stage_clock().mark("runs set bases");
     // entities another rank counts: ask the owner
     GOs want_sorted(nw);
     {
@@ -537,10 +606,13 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
       LO const* wo = worder.data();
       parallel_for(nw, OSHB_LAMBDA(LO i) { vp[wo[i]] = gp[i]; }, "dist(want values)");
     }
+    stage_clock().mark("want exchange");
     pass_want_set(ps, values);
     pass_runs_commit(ps);
+    stage_clock().mark("want set + commit");
   }
   if (nkeys) pass_finish(ps);
+  stage_clock().mark("finish");
   for (int d = 0; d < 4; ++d) nglobal[d] = nnext[d];
   *passes += 1;
   return 1;
