@@ -384,26 +384,32 @@ LOs form_uses(LOs hv2v, int high_dim, int low_dim) {
 // was built and measured SLOWER (14.1 against 10.3 ms at 100 M tets): the kernel is bound by the number of
 // distinct 32-byte sectors a warp asks of L1 per instruction, and the four uses of a tet in adjacent lanes
 // share theirs.
-static void reflect_probe(LO const* hv, LO const* off, LO const* tab, int64_t nhigh, int high_dim, int low_dim, LO* out,
-    I8* cout, int* err) {
-  int const nvh = high_dim + 1;
-  int const nvl = low_dim + 1;
-  int const nlh = simplex_degree(high_dim, low_dim);
+template <int high_dim, int low_dim>
+static void reflect_probe(LO const* hv, LO const* off, LO const* tab, int64_t nhigh, LO* out, I8* cout, int* err) {
+  constexpr int nvh = high_dim + 1;
+  constexpr int nvl = low_dim + 1;
+  constexpr int nlh = (high_dim == 3) ? (low_dim == 2 ? 4 : 6) : 3;
   parallel_for(nhigh * nlh, OSHB_LAMBDA(LO u) {
     LO h = u / nlh;
     int w = u - h * nlh;
     LO uv[3];
+#pragma unroll
     for (int k = 0; k < nvl; ++k) uv[k] = hv[int64_t(h) * nvh + simplex_down_template(high_dim, low_dim, w, k)];
+    // position of the use's smallest vertex (selects, no indexed register array)
     int um = 0;
+    LO m = uv[0];
+#pragma unroll
     for (int k = 1; k < nvl; ++k)
-      if (uv[k] < uv[um]) um = k;
-    LO const m = uv[um];
+      if (uv[k] < m) {
+        m = uv[k];
+        um = k;
+      }
     LO const rb = off[m];
     LO const re = off[m + 1];
     LO found = -1;
     I8 code = 0;
     if (nvl == 2) {
-      LO other = uv[1 - um];
+      LO const other = (um == 0) ? uv[1] : uv[0];
       for (LO s = rb; s < re; ++s) {
 #ifdef OSHB_EMU
         LO const qx = tab[int64_t(s) * 2], qy = tab[int64_t(s) * 2 + 1];
@@ -420,8 +426,8 @@ static void reflect_probe(LO const* hv, LO const* off, LO const* tab, int64_t nh
         }
       }
     } else {
-      LO ua = uv[(um + 1) % 3];
-      LO ub = uv[(um + 2) % 3];
+      LO const ua = (um == 0) ? uv[1] : ((um == 1) ? uv[2 % nvl] : uv[0]);
+      LO const ub = (um == 0) ? uv[2 % nvl] : ((um == 1) ? uv[0] : uv[1]);
       for (LO s = rb; s < re; ++s) {
 #ifdef OSHB_EMU
         LO const qx = tab[int64_t(s) * 4], qy = tab[int64_t(s) * 4 + 1], qz = tab[int64_t(s) * 4 + 2],
@@ -439,7 +445,7 @@ static void reflect_probe(LO const* hv, LO const* off, LO const* tab, int64_t nh
           // position j in b of the use's first vertex uv[0]:
           //   same orientation: uv[0] = uv[um - um] sits um steps before m  -> j = jm - um
           //   flipped         : walking the use forward walks the low backward -> j = jm + um
-          int j = same ? ((jm - um + 3) % 3) : ((jm + um) % 3);
+          int j = same ? mod_small(jm - um + 3, 3) : mod_small(jm + um, 3);
           code = make_code(flip, rotation_to_first(3, j), 0);
           break;
         }
@@ -520,7 +526,9 @@ Adj reflect_down(LOs hv2v, LOs lv2v, LO nverts, int high_dim, int low_dim) {
   LOs hl2l(nhigh * nlh);
   Bytes codes(nhigh * nlh);
   algo_bytes(nhigh * (4 * nvh + 5 * nlh) + nlow * 4 * ewords);
-  reflect_probe(hv2v.data(), off, tab, nhigh, high_dim, low_dim, hl2l.data(), codes.data(), err);
+  if (high_dim == 3 && low_dim == 2) reflect_probe<3, 2>(hv2v.data(), off, tab, nhigh, hl2l.data(), codes.data(), err);
+  else if (high_dim == 3 && low_dim == 1) reflect_probe<3, 1>(hv2v.data(), off, tab, nhigh, hl2l.data(), codes.data(), err);
+  else reflect_probe<2, 1>(hv2v.data(), off, tab, nhigh, hl2l.data(), codes.data(), err);
   Adj a;
   a.ab2b = hl2l;
   a.codes = codes;

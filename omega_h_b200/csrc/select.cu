@@ -468,6 +468,46 @@ int Pass::restate(bool read) {
   return read ? (read_scalar(flags3 + 1) != 0) : -1;
 }
 
+// one element-centric round of the independent set: the element's own edges compared pairwise (edge count at
+// compile time: the rows stay in registers)
+template <int NCE>
+static void indset_elements(LO nelems, LO const* ce2e, I8 const* state, Real const* eq, GO const* g, LO* fl) {
+  parallel_for(nelems, OSHB_LAMBDA(LO c) {
+    LO es[NCE];
+    I8 st[NCE];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < NCE; ++k) {
+      es[k] = ce2e[int64_t(c) * NCE + k];
+      st[k] = state[es[k]];
+      any = any || (st[k] == UNKNOWN);
+    }
+    if (!any) return;
+#pragma unroll
+    for (int i = 0; i < NCE; ++i) {
+      if (st[i] != UNKNOWN) continue;
+      LO v = es[i];
+      Real vq = eq[v];
+      GO vg = g[v];
+      int f = 0;
+#pragma unroll
+      for (int j = 0; j < NCE; ++j) {
+        if (j == i) continue;
+        if (st[j] == IN) {
+          f |= 1;
+        } else if (st[j] == UNKNOWN) {
+          // compare(u, v): u strictly below v in (quality, global id)
+          LO u = es[j];
+          Real uq = eq[u];
+          bool u_lt_v = (uq != vq) ? (uq < vq) : (g[u] < vg);
+          if (!u_lt_v) f |= 2;
+        }
+      }
+      if (f) atomic_or_i32(reinterpret_cast<int*>(fl) + v, f);
+    }
+  }, "indset(elements)");
+}
+
 // ---- independent set (find_indset, :29): one element-centric Jacobi round; returns whether
 // any edge of this mesh is still undecided
 int Pass::indset_round(bool read) {
@@ -484,37 +524,8 @@ int Pass::indset_round(bool read) {
   h2d(more, &z, sizeof(int));
   // a distributed caller asks for another round whenever ANY rank is undecided
   if (!flags_clean) dev_memset(fl, 0, size_t(nedges) * sizeof(LO));
-  parallel_for(nelems, OSHB_LAMBDA(LO c) {
-    LO es[6];
-    I8 st[6];
-    bool any = false;
-    for (int k = 0; k < nce_; ++k) {
-      es[k] = ce2e[int64_t(c) * nce_ + k];
-      st[k] = state[es[k]];
-      any = any || (st[k] == UNKNOWN);
-    }
-    if (!any) return;
-    for (int i = 0; i < nce_; ++i) {
-      if (st[i] != UNKNOWN) continue;
-      LO v = es[i];
-      Real vq = eq[v];
-      GO vg = g[v];
-      int f = 0;
-      for (int j = 0; j < nce_; ++j) {
-        if (j == i) continue;
-        if (st[j] == IN) {
-          f |= 1;
-        } else if (st[j] == UNKNOWN) {
-          // compare(u, v): u strictly below v in (quality, global id)
-          LO u = es[j];
-          Real uq = eq[u];
-          bool u_lt_v = (uq != vq) ? (uq < vq) : (g[u] < vg);
-          if (!u_lt_v) f |= 2;
-        }
-      }
-      if (f) atomic_or_i32(reinterpret_cast<int*>(fl) + v, f);
-    }
-  }, "indset(elements)");
+  if (nce_ == 6) indset_elements<6>(nelems, ce2e, state, eq, g, fl);
+  else indset_elements<3>(nelems, ce2e, state, eq, g, fl);
   parallel_for_any(nedges, OSHB_LAMBDA(LO e)->bool {
     if (state[e] != UNKNOWN) return false;
     int f = fl[e];
