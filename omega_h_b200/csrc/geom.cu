@@ -130,6 +130,31 @@ void measure_qualities_marked(Mesh* mesh, Bytes marks, Reals metrics, Reals into
   else fail(__FILE__, __LINE__, "measure_qualities: unsupported (dim, metric ncomps)");
 }
 
+// measure_elements_real (src/Omega_h_shape.cpp:51-89, real_simplex_size src/Omega_h_shape.hpp:165-170) of the
+// marked elements, in place: basis p[i+1] - p[0], triangle area cross/2, tet volume (b0 x b1) . b2 / 6
+template <int dim>
+static void measure_sizes_tmpl(LO const* cv2v, Real const* coords, LO n, I8 const* marks, Real* o) {
+  parallel_for(n, OSHB_LAMBDA(LO e) {
+    if (marks && !marks[e]) return;
+    Vec<dim> p[dim + 1];
+    for (int k = 0; k <= dim; ++k) p[k] = get_vec<dim>(coords, cv2v[int64_t(e) * (dim + 1) + k]);
+    Vec<dim> b[dim];
+    for (int i = 0; i < dim; ++i) b[i] = p[i + 1] - p[0];
+    o[e] = simplex_size_from_basis<dim>(b);
+  }, "measure_elements_real");
+}
+void measure_sizes_marked(Mesh* mesh, Bytes marks, Reals into) {
+  LO n = mesh->nelems();
+  if (n == 0) return;
+  int dim = mesh->dim();
+  LO const* cv2v = mesh->ask_verts_of(dim).data();
+  Real const* c = mesh->coords().data();
+  I8 const* mk = marks.exists() ? marks.data() : nullptr;
+  if (dim == 3) measure_sizes_tmpl<3>(cv2v, c, n, mk, into.data());
+  else if (dim == 2) measure_sizes_tmpl<2>(cv2v, c, n, mk, into.data());
+  else fail(__FILE__, __LINE__, "measure_elements_real: unsupported dimension");
+}
+
 Reals measure_qualities(Mesh* mesh, LOs a2e, Reals metrics) {
   LO n = a2e.exists() ? LO(a2e.size()) : mesh->nelems();
   int ncomps = int(metrics.size() / mesh->nverts());

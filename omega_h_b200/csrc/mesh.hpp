@@ -189,6 +189,7 @@ Reals measure_qualities(Mesh* mesh, LOs a2e, Reals metrics);        // src/Omega
 Reals measure_qualities_raw(int dim, LOs cv2v, Reals coords, Reals metrics, int metric_ncomps, LOs a2e, LO n);
 void measure_edges_metric_marked(Mesh* mesh, Bytes marks, Reals metrics, Reals into);  // marked edges only, in place
 void measure_qualities_marked(Mesh* mesh, Bytes marks, Reals metrics, Reals into);
+void measure_sizes_marked(Mesh* mesh, Bytes marks, Reals into);  // measure_elements_real of the marked elements, in place
 Reals get_mident_metrics(Mesh* mesh, int ent_dim, LOs a2e, Reals v2m);  // src/Omega_h_metric.cpp:56-99
 Reals refine_qualities(Mesh* mesh, LOs cands2edges);                // src/Omega_h_refine_qualities.cpp:34-107
 

@@ -665,7 +665,7 @@ void Rebuild::finish() {
   std::vector<Tag> new_tags[4];
   TagTable same_tab[4], inh_tab[4];
   struct Special {
-    int kind;  // 1 coords-like, 2 metric, 3 length, 4 quality
+    int kind;  // 1 coords-like, 2 metric, 3 length, 4 quality, 5 size
     Tag old_tag;
     size_t new_index;
   };
@@ -702,6 +702,7 @@ void Rebuild::finish() {
                (tag.ncomps == 1 || tag.ncomps == (dim * (dim + 1)) / 2)) kind = 2;
       else if (d == EDGE && tag.type == TAG_F64 && tag.name == "length" && tag.ncomps == 1) kind = 3;
       else if (d == dim && tag.type == TAG_F64 && tag.name == "quality" && tag.ncomps == 1) kind = 4;
+      else if (d == dim && tag.type == TAG_F64 && tag.name == "size" && tag.ncomps == 1) kind = 5;  // transfer_size, :364-376
       else if (d == dim && tag.type == TAG_F64 && (rule == XFER_DENSITY || rule == XFER_POINTWISE)) {
         // transfer_density_refine / transfer_pointwise_refine: the children inherit the parent element's value
         kind = 0;
@@ -730,7 +731,7 @@ void Rebuild::finish() {
         s.old_tag = tag;
         s.new_index = new_tags[d].size() - 1;
         specials[d].push_back(s);
-        if (kind == 3 || kind == 4) prod_marks[d] = Bytes(nnew[d]);
+        if (kind == 3 || kind == 4 || kind == 5) prod_marks[d] = Bytes(nnew[d]);
       }
     }
   }
@@ -867,6 +868,11 @@ void Rebuild::finish() {
     LOs list = collect_marked(prod_marks[dim]);
     Reals prod = measure_qualities(&new_mesh, list, new_mesh.get_reals(VERT, "metric"));
     scatter_by<Real>(prod.data(), new_tags[dim][s.new_index].f64.data(), list.data(), LO(list.size()), 1);
+  }
+  for (auto const& s : specials[dim]) {
+    if (s.kind != 5) continue;
+    // transfer_size (src/Omega_h_transfer.cpp:364-376): the real-space size of the product elements
+    measure_sizes_marked(&new_mesh, prod_marks[dim], new_tags[dim][s.new_index].f64);
   }
   // ---- UserTransfer::refine (src/Omega_h_transfer.cpp:422-426), once per dimension ---------------------
   if (user_transfer_hook().fn) {
