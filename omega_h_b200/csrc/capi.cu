@@ -468,8 +468,10 @@ int oshb_mesh_clone(const oshb_mesh* m, oshb_mesh** out) {
   OSHB_CATCH
 }
 int oshb_mesh_dim(const oshb_mesh* m, int* dim) {
+  OSHB_TRY
+  OSHB_CHECK(m != nullptr && dim != nullptr);
   *dim = m->m.dim();
-  return 0;
+  OSHB_CATCH
 }
 int oshb_mesh_nents(const oshb_mesh* m, int ent_dim, int32_t* n) {
   OSHB_TRY
@@ -478,8 +480,10 @@ int oshb_mesh_nents(const oshb_mesh* m, int ent_dim, int32_t* n) {
   OSHB_CATCH
 }
 int oshb_mesh_set_verts(oshb_mesh* m, int32_t nverts) {
+  OSHB_TRY
+  OSHB_CHECK(m != nullptr && nverts >= 0);
   m->m.set_verts(nverts);
-  return 0;
+  OSHB_CATCH
 }
 int oshb_mesh_set_ents(oshb_mesh* m, int ent_dim, int32_t nents, const int32_t* down, const int8_t* codes, int host) {
   OSHB_TRY

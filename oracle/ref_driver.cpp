@@ -43,6 +43,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #ifdef OSHB_REF_OPENMP
 #include <omp.h>
 #endif
@@ -350,6 +351,80 @@ static int mode_timeloops(Library* lib, int argc, char** argv) {
   return 0;
 }
 
+// digest: the complete while(refine_by_size) loop, then one line per array of the final mesh with a
+// position-dependent 64-bit checksum (sum over i of (bits_i + 1) * (2 i + 1) mod 2^64 -- order-sensitive, computable
+// with wrapping uint64 arithmetic anywhere) plus, for reals, sum / min / max. The full-size parity test compares
+// these against the same digests of the GPU result: the reference itself as the oracle at BASELINE's sizes, where
+// dumping every array would be gigabytes.
+template <typename T>
+static unsigned long long digest_bits(HostRead<T> const& a) {
+  unsigned long long h = 0;
+  for (LO i = 0; i < a.size(); ++i) {
+    unsigned long long bits = 0;
+    T v = a[i];
+    memcpy(&bits, &v, sizeof(T));  // little endian: the low bytes
+    h += (bits + 1ull) * (2ull * (unsigned long long)i + 1ull);
+  }
+  return h;
+}
+template <typename T>
+static void digest_line(std::string const& key, Read<T> arr, int ncomps) {
+  HostRead<T> a(arr);
+  printf("{\"key\":\"%s\",\"n\":%lld,\"ncomps\":%d,\"hash\":\"%llu\"", key.c_str(), (long long)a.size(), ncomps, digest_bits(a));
+  if (std::is_same<T, Real>::value) {
+    long double sum = 0;
+    double mn = 1e300, mx = -1e300;
+    for (LO i = 0; i < a.size(); ++i) {
+      double v = double(a[i]);
+      sum += v;
+      if (v < mn) mn = v;
+      if (v > mx) mx = v;
+    }
+    printf(",\"sum\":%.17g,\"min\":%.17g,\"max\":%.17g", double(sum), mn, mx);
+  }
+  printf("}\n");
+}
+static int mode_digest(Library* lib, int argc, char** argv) {
+  int dim = atoi(argv[2]);
+  int n = atoi(argv[3]);
+  int kind = atoi(argv[4]);
+  auto mesh = make_box(lib, dim, n);
+  set_metric(&mesh, n, kind);
+  if (argc > 5) {
+    // the input metric, raw doubles, so the other side starts from bit-identical inputs
+    HostRead<Real> hm(mesh.get_array<Real>(VERT, "metric"));
+    FILE* f = fopen(argv[5], "wb");
+    if (!f || fwrite(hm.data(), sizeof(Real), size_t(hm.size()), f) != size_t(hm.size())) return 3;
+    fclose(f);
+  }
+  auto opts = AdaptOpts(&mesh);
+  opts.verbosity = SILENT;
+  mesh.ask_lengths();
+  mesh.ask_qualities();
+  int passes = 0;
+  while (refine_by_size(&mesh, opts)) ++passes;
+  printf("{\"key\":\"passes\",\"n\":%d}\n", passes);
+  for (Int d = 0; d <= mesh.dim(); ++d) {
+    auto ds = std::to_string(d);
+    printf("{\"key\":\"nents%d\",\"n\":%lld}\n", d, (long long)mesh.nents(d));
+    if (d > 0) {
+      auto down = mesh.ask_down(d, d - 1);
+      digest_line<LO>("down" + ds, down.ab2b, d + 1);
+      if (down.codes.exists()) digest_line<I8>("codes" + ds, down.codes, d + 1);
+    }
+    for (Int i = 0; i < mesh.ntags(d); ++i) {
+      auto tag = mesh.get_tag(d, i);
+      auto key = "tag" + ds + ":" + tag->name();
+      if (is<I8>(tag)) digest_line<I8>(key, as<I8>(tag)->array(), tag->ncomps());
+      if (is<I32>(tag)) digest_line<I32>(key, as<I32>(tag)->array(), tag->ncomps());
+      if (is<I64>(tag)) digest_line<I64>(key, as<I64>(tag)->array(), tag->ncomps());
+      if (is<Real>(tag)) digest_line<Real>(key, as<Real>(tag)->array(), tag->ncomps());
+    }
+  }
+  fflush(stdout);
+  return 0;
+}
+
 // rib: Mesh::balance()'s element -> rank assignment without MPI. recursively_bisect (src/Omega_h_inertia.cpp:162-193)
 // marks a group's elements with inertia::mark_bisection, sends unmarked / marked elements to the lower / upper half
 // of the group's ranks (bi_partition, src/Omega_h_bipart.cpp:9-33) and recurses on each half; the marks depend on
@@ -473,6 +548,7 @@ int main(int argc, char** argv) {
   if (mode == "refine") return mode_refine(&lib, argc, argv);
   if (mode == "time") return mode_time(&lib, argc, argv);
   if (mode == "timeloops") return mode_timeloops(&lib, argc, argv);
+  if (mode == "digest") return mode_digest(&lib, argc, argv);
   if (mode == "box") return mode_box(&lib, argc, argv);
   if (mode == "diff") return mode_diff(&lib, argc, argv);
   if (mode == "rib") return mode_rib(&lib, argc, argv);

@@ -127,6 +127,81 @@ def test_full_size_loop_properties(gpu_lib):
         assert inside.all()
 
 
+def _digest(arr):
+    """the checksum of oracle/ref_driver.cpp `digest`: sum_i (bits_i + 1) * (2 i + 1) mod 2^64 over the flat array,
+    bits_i = the value's bytes zero-extended to 64 bits"""
+    import numpy as np
+    a = np.ascontiguousarray(arr).reshape(-1)
+    u = a.view({1: np.uint8, 4: np.uint32, 8: np.uint64}[a.dtype.itemsize]).astype(np.uint64)
+    idx = np.arange(a.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return int(((u + np.uint64(1)) * (np.uint64(2) * idx + np.uint64(1))).sum(dtype=np.uint64))
+
+
+@pytest.mark.parametrize("n,kind", [(64, 0), (24, 2)], ids=["config1_64cube_iso", "aniso_24cube"])
+def test_full_size_loop_matches_reference_digests(gpu_lib, ref_driver, tmp_path, n, kind):
+    """The reference ITSELF as the oracle at BASELINE's full size: oracle/_ref/ref_driver_omp (the unmodified
+    reference, OpenMP) runs the complete loop of config[1] (64^3, 1.57 M -> 25.2 M tets) on the box's host cores and
+    prints an order-sensitive 64-bit checksum of every array of its final mesh; the CUDA loop's final mesh must give
+    the same checksums for EVERY integer array (connectivity, codes, globals, classification of all dimensions),
+    and for the real arrays either the same checksum (bit-identical doubles) or sum / min / max within 1e-12.
+    The second case is the anisotropic tanh-layer metric (3x3 tensors, field transfer) at 24^3."""
+    import json
+    import numpy as np
+    import subprocess
+    from omega_h_b200 import VERT, AdaptOpts, build_box, refine_by_size
+    omp = ref_driver + "_omp"
+    exe = omp if os.path.exists(omp) else ref_driver
+    metric_file = os.path.join(str(tmp_path), "metric.bin")
+    r = subprocess.run([exe, "digest", "3", str(n), str(kind), metric_file], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = {}
+    for line in r.stdout.splitlines():
+        if line.startswith("{"):
+            d = json.loads(line)
+            ref[d["key"]] = d
+    m = build_box(1.0, 1.0, 1.0, n, n, n, lib=gpu_lib)
+    metric = np.fromfile(metric_file, dtype=np.float64)   # the reference's own input metric, bit for bit
+    assert metric.size % m.nverts() == 0
+    m.add_tag(VERT, "metric", metric.size // m.nverts(), metric)
+    m.ask_lengths()
+    m.ask_qualities()
+    opts = AdaptOpts(m)
+    passes = 0
+    while refine_by_size(m, opts):
+        passes += 1
+    assert passes == ref["passes"]["n"]
+    checked = 0
+    bitwise_reals = 0
+    for d in range(4):
+        assert m.nents(d) == ref["nents%d" % d]["n"]
+        arrays = {}
+        if d > 0:
+            ab2b, codes = m.ask_down(d, d - 1)
+            arrays["down%d" % d] = ab2b
+            if d > 1:
+                arrays["codes%d" % d] = codes
+        for name, _t, _nc in m.tags(d):
+            arrays["tag%d:%s" % (d, name)] = m.get_array(d, name)
+        ref_keys = {k for k in ref if k.startswith("tag%d:" % d) or k in ("down%d" % d, "codes%d" % d)}
+        assert set(arrays) == ref_keys, (sorted(arrays), sorted(ref_keys))
+        for key, a in arrays.items():
+            want = ref[key]
+            assert a.size == want["n"], key
+            same = _digest(a) == int(want["hash"])
+            if a.dtype == np.float64:
+                bitwise_reals += int(same)
+                if not same:
+                    assert abs(float(a.sum(dtype=np.longdouble)) - want["sum"]) <= 1e-12 * max(1.0, abs(want["sum"])), key
+                    assert abs(a.min() - want["min"]) <= 1e-12 * max(1.0, abs(want["min"])), key
+                    assert abs(a.max() - want["max"]) <= 1e-12 * max(1.0, abs(want["max"])), key
+            else:
+                assert same, "%s differs from the reference at full size" % key
+            checked += 1
+    assert checked >= 20
+    print("full-size digests: %d arrays, %d real arrays bit-identical" % (checked, bitwise_reals))
+
+
 @pytest.mark.parametrize("fixture,seed,aniso", [("d3n3m0_pass0", 21, False), ("d3n4m2_pass0", 22, True),
                                                ("d2n6m1_pass0", 23, True), ("d2n6m2_pass0", 24, False),
                                                ("d3n4m3_pass0", 25, False)])
