@@ -49,7 +49,10 @@ def parse_args():
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table to stderr and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="N = 1: skip the `also` block (aniso n=64 loop, 100 M-tet adjacency microbench)")
+    ap.add_argument("--time-reghost", action="store_true",
+                    help="N > 1: also time DistMesh.reghost of the refined anisotropic part (twice: cold, warm)")
+    ap.add_argument("--no-also", action="store_true", help="skip the `also` block (N = 1: aniso n=64 loop + 100 M-tet adjacency microbench; N > 1: the "
+                         "anisotropic partitioned loop)")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the N-rank == serial self-check")
     ap.add_argument("--halo", type=int, default=4, help="N > 1: element layers each part keeps of its neighbours")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent boxes instead of one partitioned box")
@@ -393,6 +396,100 @@ def also_adj(lib):
             "bytes": "algorithmic (SURVEY.md 8d): compulsory reads + writes of each primitive",
             "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
                         for k, v in out["kernels"].items()}}
+
+
+def aniso_metric_of_box(m, n):
+    """BASELINE config[2]/[3]'s tanh shock layer, one layer per unit cube of the box (z taken modulo 1) so that every
+    rank's share of an N-cube box is the N = 1 workload: hx = 1/n, hy = 0.7/n, hz = (1/n)(1 - 0.75 sech^2(20(z' - 1/2)))"""
+    import numpy as np
+    x = m.coords().reshape(-1, 3)
+    z = x[:, 2] - np.floor(x[:, 2])
+    z[x[:, 2] == np.floor(x[:, 2])] = 0.0
+    t = np.tanh(20.0 * (z - 0.5))
+    hz = (1.0 / n) * (1.0 - 0.75 * (1.0 - t * t))
+    met = np.zeros((m.nverts(), 6))
+    met[:, 0] = 1.0 / (1.0 / n) ** 2
+    met[:, 1] = 1.0 / (0.7 / n) ** 2
+    met[:, 2] = 1.0 / hz ** 2
+    return met.reshape(-1)
+
+
+def also_aniso_partitioned(lib, device, n, halo, parting, steps=3, time_reghost=False):
+    """BASELINE config[3] (the anisotropic cube partitioned over the ranks, metric + coordinates + classification
+    transferred every pass): N x n^3 cells, one shock layer per unit cube, RIB parts. The loop has 8 passes; it runs on
+    an 8-layer halo so that no re-ghosting falls into it; with --time-reghost a re-ghosting (DistMesh.reghost, torch
+    ops) of the refined part is timed separately (cold + warm): a loop on a thinner halo pays that once per `halo` passes."""
+    import torch
+    import torch.distributed as dist
+    from omega_h_b200 import VERT, AdaptOpts, build_box
+    from omega_h_b200 import dist as D
+    world = dist.get_world_size()
+    shape = box_shape(world)
+    base = build_box(float(shape[0]), float(shape[1]), float(shape[2]), shape[0] * n, shape[1] * n, shape[2] * n, lib=lib)
+    base.add_tag(VERT, "metric", 6, aniso_metric_of_box(base, n))
+    base.ask_lengths()
+    base.ask_qualities()
+    nglobal0 = base.nelems()
+    halo = max(halo, 8)
+    part0 = D.distribute(base, halo, device, parting=parting)
+    del base
+    torch.cuda.empty_cache()
+    opts = AdaptOpts(part0.mesh)
+
+    def barrier():
+        lib.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def loop(part):
+        passes = 0
+        while part.refine_by_size(opts):
+            passes += 1
+        return passes
+    for _ in range(2):
+        part = part0.clone()
+        npasses = loop(part)
+    t = torch.tensor([float(part.owned_nelems())], device=device, dtype=torch.float64)
+    dist.all_reduce(t)
+    nglobal1 = int(t.item())
+    reghosts = int(getattr(part, "nreghosts", 0))
+    del part
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        part = part0.clone()
+        loop(part)
+    lib.sync()
+    ev1.record()
+    barrier()
+    tm = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm[0]) / steps
+    # one re-ghosting of the refined part (what a loop on a halo thinner than its pass count pays per `halo` passes)
+    local_tets = part.mesh.nelems()
+    reghost_ms = [None, None]
+    for k in range(2 if time_reghost else 0):   # the first call also sets up NCCL's point-to-point connections
+        barrier()
+        t0 = time.perf_counter()
+        part.reghost()
+        barrier()
+        tr = torch.tensor([(time.perf_counter() - t0) * 1e3], device=device, dtype=torch.float64)
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        reghost_ms[k] = float(tr[0])
+    del part, part0
+    torch.cuda.empty_cache()
+    lib.trim()
+    return {"workload": "3D tet box %dx%dx%d cells (x6 tets) = %d ranks x %d^3, anisotropic tanh shock-layer metric (3x3; one "
+                        "layer per unit cube), while(refine_by_size) loop on the partitioned mesh with field transfer" %
+                        (shape[0] * n, shape[1] * n, shape[2] * n, world, n),
+            "value": (nglobal1 - nglobal0) / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "passes_per_step": npasses, "tets_per_step": "%d -> %d" % (nglobal0, nglobal1), "halo": halo,
+            "reghosts_per_step": reghosts, "parting": parting,
+            "reghost_ms": reghost_ms[1], "reghost_first_call_ms": reghost_ms[0], "reghost_local_tets_rank0": int(local_tets),
+            "timing": "CUDA events between two barriers, max over ranks; reghost_ms: wall clock of one DistMesh.reghost of "
+                      "the refined part between two barriers, max over ranks, outside the loop's timed region"}
 
 
 def partition_parity_check(lib, device, halo, n=16):
@@ -850,6 +947,13 @@ def main_b200_partitioned(args):
                "ms_per_step": e_s * 1e3 / args.steps,
                "timing": "wall clock around upload + partitioned loop + download of every rank's part, max over ranks"}
 
+    also = None
+    if not args.no_also:
+        torch.cuda.empty_cache()
+        lib.trim()
+        also = {"aniso_n%d" % n: also_aniso_partitioned(lib, device, n, halo, args.parting,
+                                                        time_reghost=args.time_reghost)}
+
     if rank == 0:
         cfg = workload_config(n, "iso")
         cfg["workload"] = ("3D tet box build_box %dx%dx%d cells (x6 tets) = %d ranks x %d^3, uniform isotropic metric "
@@ -867,7 +971,7 @@ def main_b200_partitioned(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
-            "peak_device_bytes": lib.peak_bytes(), "parity_check": parity,
+            "peak_device_bytes": lib.peak_bytes(), "parity_check": parity, "also": also,
         }
         print(json.dumps(line))
     if os.environ.get("OSHB_DIST_CPROFILE") and rank == 0:

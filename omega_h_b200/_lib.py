@@ -108,6 +108,10 @@ class Lib:
     def sync_count(self):
         return int(self.c.oshb_sync_count())
 
+    def trim(self):
+        """return the library's wholly free device segments to the driver (oshb_trim)"""
+        self.check(self.c.oshb_trim())
+
     def peak_bytes(self):
         return int(self.c.oshb_peak_bytes())
 

@@ -459,6 +459,7 @@ class DistMesh:
         self.size = dist.get_world_size(group)
         self.nglobal = [0, 0, 0, 0]
         self.last = {}
+        self.nreghosts = 0
 
     def clone(self):
         """a fresh handle on the same (immutable) arrays, as Mesh.copy()"""
@@ -619,6 +620,7 @@ class DistMesh:
         its neighbours (their own elements within halo + 1 layers of the partition boundary, closure
         and tags included, entities named by global number); the union is merged by global number --
         which keeps the local order equal to the global one -- and cut to `halo` layers."""
+        self.nreghosts += 1
         mesh, dm, dev = self.mesh, self.dm, self.device
         dim, P, me = mesh.dim(), self.size, self.rank
         nloc = [mesh.nents(d) for d in range(dim + 1)]
