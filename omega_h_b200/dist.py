@@ -648,10 +648,15 @@ class DistMesh:
                 rec.append(gid[0][cv2v[idx]].flatten())
             return rec
 
+        _sec = _Section(dm, "reghost: records")
+        _sec.__enter__()
         keep_idx = [torch.nonzero(depth[d] <= 0).flatten() for d in range(dim + 1)]
         band_idx = [torch.nonzero(depth[d] < 0).flatten() for d in range(dim + 1)]
         mine = [records(d, keep_idx[d]) for d in range(dim + 1)]
         band = [records(d, band_idx[d]) for d in range(dim + 1)]
+        _sec.__exit__()
+        _sec = _Section(dm, "reghost: exchange")
+        _sec.__enter__()
         # who exchanges with whom: ranks whose elements I hold, and theirs (an element one layer
         # beyond my halo may belong to a rank I have not met yet; it decides "own:part" at the rim)
         seen = torch.zeros(P, dtype=torch.int64, device=dev)
@@ -685,6 +690,9 @@ class DistMesh:
                 if ops:
                     for req in dist.batch_isend_irecv(ops):
                         req.wait()
+        _sec.__exit__()
+        _sec = _Section(dm, "reghost: merge")
+        _sec.__enter__()
         # merge by global number
         n, uniq, new_down, new_tags, first = [0] * (dim + 1), {}, {}, {}, {}
         for d in range(dim + 1):
@@ -717,8 +725,12 @@ class DistMesh:
                 owner = torch.cat([p[k] for p in parts])[f]
                 vg = torch.cat([p[k + 1] for p in parts]).view(-1, dim + 1)[f]
                 new_cv2v = torch.searchsorted(uniq[0], vg.flatten()).view(-1, dim + 1)
+        _sec.__exit__()
+        _sec = _Section(dm, "reghost: build_part")
+        _sec.__enter__()
         fresh = _build_part(mesh.lib, dev, self.group, dim, n, new_down, new_cv2v, new_tags, uniq, owner, self.halo,
                             self.nglobal[:dim + 1])
+        _sec.__exit__()
         self.mesh, self.dm = fresh.mesh, fresh.dm
         self.passes = 0
         self.reghosts = getattr(self, "reghosts", 0) + 1
