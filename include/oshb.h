@@ -274,6 +274,13 @@ typedef struct oshb_dist_stats {
 } oshb_dist_stats;
 int oshb_dist_refine_by_size(oshb_mesh* part, oshb_comm* comm, const oshb_adapt_opts* opts, int halo, int* passes_inout,
     int64_t* nglobal_inout, int* result, oshb_dist_stats* stats_or_null);
+/* Re-ghosting: when oshb_dist_refine_by_size answers 2 the halo of the part is used up. Every rank keeps the closure
+ * of its own elements and receives the bands of its neighbours (their own elements within halo + 1 layers of the
+ * partition boundary, closure, codes and tags included, entities named by global number), merges them by global number
+ * (the local order stays the global order), rebuilds the layers and "own:part", and cuts the part to `halo` layers:
+ * what ghost_mesh + migrate_mesh do in the reference (src/Omega_h_ghost.cpp:102-141, src/Omega_h_migrate.cpp:15-225),
+ * once per `halo` passes instead of twice per pass. The part is replaced in place; the caller resets its pass count. */
+int oshb_dist_reghost(oshb_mesh* part, oshb_comm* comm, int halo);
 
 /* ---- one refine pass, stage by stage -------------------------------------------------------------
  * The same pass as oshb_refine_by_size, cut at the points where the reference synchronises

@@ -327,6 +327,13 @@ int oshb_dist_refine_by_size(oshb_mesh* part, oshb_comm* comm, const oshb_adapt_
   OSHB_CATCH
 }
 
+int oshb_dist_reghost(oshb_mesh* part, oshb_comm* comm, int halo) {
+  OSHB_TRY
+  OSHB_CHECK(part && comm);
+  dist_reghost(&part->m, reinterpret_cast<Comm*>(comm), halo);
+  OSHB_CATCH
+}
+
 // ---- transfer rules ---------------------------------------------------------------------------
 int oshb_mesh_set_transfer(oshb_mesh* m, const char* tag_name, int transfer_type) {
   OSHB_TRY

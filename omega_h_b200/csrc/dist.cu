@@ -618,4 +618,456 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
   return 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// re-ghosting
+// ---------------------------------------------------------------------------------------------------
+// When the halo is used up (dist_refine_by_size returned 2) every rank keeps the closure of its own elements
+// and receives the BANDS of its neighbours and their neighbours -- own elements within halo + 1 layers of the
+// partition boundary, marked by negative depths in "own:part" and inherited through the passes like everything
+// else, with their closure, codes and tags, every entity named by its global number. This is the role of the
+// reference's ghost_mesh + migrate_mesh (src/Omega_h_ghost.cpp:102-141, src/Omega_h_migrate.cpp:15-225), once per
+// `halo` passes instead of twice per pass, and O(boundary) apart from one copy of the part:
+//   1. the kept set and the band of every dimension are compacted from the depth byte;
+//   2. one all-gather tells who holds whose elements; a rank exchanges with the ranks it has met and theirs;
+//   3. bands travel array by array (grouped send/recv); the received entities are sorted by global number
+//      (the library's radix sort: they are boundary-sized), duplicates and entities already kept are dropped,
+//      and the two sorted lists are merged by bisection -- the local order stays the global order;
+//   4. kept rows are re-indexed through old -> new maps, received rows by bisection of the new numbers;
+//   5. layers are rebuilt by sweeps over element -> vertex rows (halo outward from the own elements, halo + 1
+//      inward from the foreign ones), "own:part" = (lowest owner rank, lowest depth) over the adjacent elements
+//      passed down the stored adjacencies with atomic minima, the part is cut to `halo` layers and compacted.
+namespace {
+
+// rows of `row_bytes` bytes: dst[dst_idx ? dst_idx[i] : i] = src[src_idx ? src_idx[i] : i]
+void copy_rows(void* dst, LO const* dst_idx, void const* src, LO const* src_idx, int64_t n, int row_bytes) {
+  if (n == 0 || row_bytes == 0) return;
+  if (row_bytes % 8 == 0) {
+    int const w = row_bytes / 8;
+    GO* d = static_cast<GO*>(dst);
+    GO const* sp = static_cast<GO const*>(src);
+    parallel_for(n * w, OSHB_LAMBDA(LO t) {
+      LO i = t / w;
+      int c = t - i * w;
+      d[int64_t(dst_idx ? dst_idx[i] : i) * w + c] = sp[int64_t(src_idx ? src_idx[i] : i) * w + c];
+    }, "reghost(rows)");
+  } else if (row_bytes % 4 == 0) {
+    int const w = row_bytes / 4;
+    LO* d = static_cast<LO*>(dst);
+    LO const* sp = static_cast<LO const*>(src);
+    parallel_for(n * w, OSHB_LAMBDA(LO t) {
+      LO i = t / w;
+      int c = t - i * w;
+      d[int64_t(dst_idx ? dst_idx[i] : i) * w + c] = sp[int64_t(src_idx ? src_idx[i] : i) * w + c];
+    }, "reghost(rows)");
+  } else {
+    int const w = row_bytes;
+    I8* d = static_cast<I8*>(dst);
+    I8 const* sp = static_cast<I8 const*>(src);
+    parallel_for(n * w, OSHB_LAMBDA(LO t) {
+      LO i = t / w;
+      int c = t - i * w;
+      d[int64_t(dst_idx ? dst_idx[i] : i) * w + c] = sp[int64_t(src_idx ? src_idx[i] : i) * w + c];
+    }, "reghost(rows)");
+  }
+}
+
+Tag tag_like(Tag const& tag, int64_t nents) {
+  Tag nt;
+  nt.name = tag.name;
+  nt.type = tag.type;
+  nt.ncomps = tag.ncomps;
+  int64_t n = nents * tag.ncomps;
+  switch (tag.type) {
+    case TAG_I8: nt.i8 = Bytes(n); break;
+    case TAG_I32: nt.i32 = LOs(n); break;
+    case TAG_I64: nt.i64 = GOs(n); break;
+    default: nt.f64 = Reals(n); break;
+  }
+  return nt;
+}
+
+constexpr int DEEP = 127;
+
+}  // namespace
+
+void dist_reghost(Mesh* mesh, Comm* comm, int halo) {
+  int const P = comm->size, me = comm->rank;
+  int const dim = mesh->dim();
+  OSHB_CHECK(halo >= 1 && halo <= 125);
+  int* err = device_error_cell();
+  device_error_reset();
+  stage_clock().start();
+
+  // ---- 1. kept set (depth <= 0: the closure of the own elements) and band (depth < 0) of every dimension
+  LOs own[4], keep_idx[4], band_idx[4];
+  GOs gid[4], gK[4];
+  LO nold[4] = {0, 0, 0, 0}, nK[4] = {0, 0, 0, 0}, nB[4] = {0, 0, 0, 0};
+  for (int d = 0; d <= dim; ++d) {
+    nold[d] = mesh->nents(d);
+    own[d] = mesh->get_los(d, "own:part");
+    gid[d] = mesh->globals(d);
+    Bytes km(nold[d]), bm(nold[d]);
+    I8* kp = km.data();
+    I8* bp = bm.data();
+    LO const* op = own[d].data();
+    parallel_for(nold[d], OSHB_LAMBDA(LO i) {
+      int dp = depth_of(op[i]);
+      kp[i] = (dp <= 0) ? 1 : 0;
+      bp[i] = (dp < 0) ? 1 : 0;
+    }, "reghost(marks)");
+    keep_idx[d] = collect_marked(km);
+    band_idx[d] = collect_marked(bm);
+    nK[d] = LO(keep_idx[d].size());
+    nB[d] = LO(band_idx[d].size());
+    gK[d] = gather_at<GO>(gid[d].data(), keep_idx[d].data(), nK[d]);
+  }
+  // ---- 2. who exchanges with whom: ranks whose elements I hold, and theirs (an element one layer beyond my halo
+  // may belong to a rank I have not met yet; it decides "own:part" at the rim). One all-gather: seen[P] + band sizes
+  int const W = P + 4;
+  GOs mine_row(W);
+  {
+    std::vector<GO> init(size_t(W), 0);
+    for (int d = 0; d <= dim; ++d) init[size_t(P + d)] = nB[d];
+    h2d(mine_row.data(), init.data(), init.size() * sizeof(GO));
+    GO* mp = mine_row.data();
+    LO const* oe = own[dim].data();
+    parallel_for(nold[dim], OSHB_LAMBDA(LO e) {
+      LO r = oe[e] >> 8;
+      if (r >= 0 && r < P) mp[r] = 1;  // every writer stores the same value
+    }, "reghost(seen)");
+  }
+  GOs table(int64_t(P) * W);
+  comm->allgather_i64(mine_row.data(), W, table.data());
+  std::vector<GO> th = table.to_host();
+  auto T = [&](int r, int k) { return th[size_t(r) * W + k]; };
+  std::vector<char> adj(size_t(P) * P, 0), two(size_t(P) * P, 0);
+  for (int r = 0; r < P; ++r)
+    for (int q = 0; q < P; ++q) adj[size_t(r) * P + q] = (T(r, q) != 0 || T(q, r) != 0) ? 1 : 0;
+  for (int r = 0; r < P; ++r)
+    for (int q = 0; q < P; ++q) {
+      char t = adj[size_t(r) * P + q];
+      for (int k = 0; k < P && !t; ++k) t = adj[size_t(r) * P + k] && adj[size_t(k) * P + q];
+      two[size_t(r) * P + q] = t;
+    }
+  std::vector<int> nbrs;
+  for (int r = 0; r < P; ++r)
+    if (r != me && two[size_t(me) * P + r]) nbrs.push_back(r);
+  int const nn = int(nbrs.size());
+  stage_clock().mark("reghost: marks + neighbours");
+
+  // the same band goes to every neighbour: one grouped exchange per array
+  auto exchange = [&](void const* band_data, int d, int row_bytes, int64_t* nrecv_out) -> Bytes {
+    std::vector<int64_t> sc(size_t(P), 0), rc(size_t(P), 0);
+    int64_t nrecv = 0;
+    for (int r : nbrs) {
+      sc[size_t(r)] = nB[d];
+      rc[size_t(r)] = T(r, P + d);
+      nrecv += rc[size_t(r)];
+    }
+    Bytes send(int64_t(nn) * nB[d] * row_bytes);
+    for (int k = 0; k < nn; ++k)
+      if (nB[d]) d2d(send.data() + int64_t(k) * nB[d] * row_bytes, band_data, size_t(nB[d]) * row_bytes);
+    Bytes recv(nrecv * row_bytes);
+    comm->alltoallv(send.data(), sc.data(), recv.data(), rc.data(), row_bytes);
+    *nrecv_out = nrecv;
+    return recv;
+  };
+
+  // ---- 3/4. dimension by dimension (ascending: the rows of dimension d name entities of d - 1)
+  LO nnew[4] = {0, 0, 0, 0};
+  GOs new_gid[4];
+  LOs o2n[4], new_down[4], owner_new;
+  Bytes new_codes[4];
+  std::vector<Tag> new_tags[4];
+  for (int d = 0; d <= dim; ++d) {
+    int const deg = (d >= 1) ? simplex_degree(d, d - 1) : 0;
+    int64_t nR = 0;
+    // band gids out, everybody's in
+    GOs bg = gather_at<GO>(gid[d].data(), band_idx[d].data(), nB[d]);
+    Bytes rg_b = exchange(bg.data(), d, int(sizeof(GO)), &nR);
+    GO const* Rg = reinterpret_cast<GO const*>(rg_b.data());
+    // received entities in global-number order, first copy of each, not already kept
+    LOs r_src;  // index into the received arrays, per accepted entity, ascending global number
+    LO nRp = 0;
+    {
+      LOs perm(nR);
+      if (nR) sort_by_keys(Rg, nR, 1, perm.data());
+      Bytes take(nR);
+      I8* tk = take.data();
+      LO const* pp = perm.data();
+      GO const* gk = gK[d].data();
+      LO const nk = nK[d];
+      parallel_for(nR, OSHB_LAMBDA(LO s) {
+        GO g = Rg[pp[s]];
+        bool first = (s == 0) || (Rg[pp[s - 1]] != g);
+        LO pos = lower_bound_dev<GO>(gk, nk, g);
+        bool in_k = (pos < nk && gk[pos] == g);
+        tk[s] = (first && !in_k) ? 1 : 0;
+      }, "reghost(accept)");
+      LOs sel = collect_marked(take);
+      nRp = LO(sel.size());
+      r_src = LOs(nRp);
+      LO* rs = r_src.data();
+      LO const* sp = sel.data();
+      parallel_for(nRp, OSHB_LAMBDA(LO j) { rs[j] = pp[sp[j]]; }, "reghost(accepted)");
+    }
+    nnew[d] = nK[d] + nRp;
+    // merge of the two ascending lists by bisection
+    GOs rpg = gather_at<GO>(Rg, r_src.data(), nRp);
+    LOs posK(nK[d]), posR(nRp);
+    new_gid[d] = GOs(nnew[d]);
+    o2n[d] = filled<LO>(nold[d], -1);
+    {
+      LO* pk = posK.data();
+      LO* pr = posR.data();
+      GO* ng = new_gid[d].data();
+      LO* on = o2n[d].data();
+      GO const* gk = gK[d].data();
+      GO const* rp = rpg.data();
+      LO const* ki = keep_idx[d].data();
+      LO const nk = nK[d], nr = nRp;
+      parallel_for(nk, OSHB_LAMBDA(LO i) {
+        LO p = i + lower_bound_dev<GO>(rp, nr, gk[i]);
+        pk[i] = p;
+        ng[p] = gk[i];
+        on[ki[i]] = p;
+      }, "reghost(merge kept)");
+      parallel_for(nr, OSHB_LAMBDA(LO j) {
+        LO p = j + lower_bound_dev<GO>(gk, nk, rp[j]);
+        pr[j] = p;
+        ng[p] = rp[j];
+      }, "reghost(merge received)");
+    }
+    // rows: downward entities (by global number on the wire), codes
+    if (d >= 1) {
+      Adj old_down = mesh->ask_down(d, d - 1);
+      LO const* od = old_down.ab2b.data();
+      GO const* glow = gid[d - 1].data();
+      LO const* bi = band_idx[d].data();
+      GOs bdg(int64_t(nB[d]) * deg);
+      GO* bd = bdg.data();
+      parallel_for(int64_t(nB[d]) * deg, OSHB_LAMBDA(LO t) {
+        LO i = t / deg;
+        int k = t - i * deg;
+        bd[t] = glow[od[int64_t(bi[i]) * deg + k]];
+      }, "reghost(band rows)");
+      int64_t nr2 = 0;
+      Bytes rdg_b = exchange(bdg.data(), d, int(sizeof(GO)) * deg, &nr2);
+      OSHB_CHECK(nr2 == nR);
+      GO const* rdg = reinterpret_cast<GO const*>(rdg_b.data());
+      new_down[d] = LOs(int64_t(nnew[d]) * deg);
+      LO* nd = new_down[d].data();
+      LO const* ki = keep_idx[d].data();
+      LO const* pk = posK.data();
+      LO const* pr = posR.data();
+      LO const* rs = r_src.data();
+      LO const* onl = o2n[d - 1].data();
+      GO const* ngl = new_gid[d - 1].data();
+      LO const nlow = nnew[d - 1];
+      parallel_for(int64_t(nK[d]) * deg, OSHB_LAMBDA(LO t) {
+        LO i = t / deg;
+        int k = t - i * deg;
+        LO l = onl[od[int64_t(ki[i]) * deg + k]];
+        if (l < 0) raise_flag(err, 128);  // the kept set is not closed
+        nd[int64_t(pk[i]) * deg + k] = l;
+      }, "reghost(kept rows)");
+      parallel_for(int64_t(nRp) * deg, OSHB_LAMBDA(LO t) {
+        LO j = t / deg;
+        int k = t - j * deg;
+        GO g = rdg[int64_t(rs[j]) * deg + k];
+        LO pos = lower_bound_dev<GO>(ngl, nlow, g);
+        if (pos >= nlow || ngl[pos] != g) {
+          raise_flag(err, 128);  // a bounding entity of a received entity is missing
+          pos = 0;
+        }
+        nd[int64_t(pr[j]) * deg + k] = pos;
+      }, "reghost(received rows)");
+      if (d >= 2) {
+        Bytes bc(int64_t(nB[d]) * deg);
+        copy_rows(bc.data(), nullptr, old_down.codes.data(), band_idx[d].data(), nB[d], deg);
+        int64_t nr3 = 0;
+        Bytes rc_b = exchange(bc.data(), d, deg, &nr3);
+        new_codes[d] = Bytes(int64_t(nnew[d]) * deg);
+        copy_rows(new_codes[d].data(), posK.data(), old_down.codes.data(), keep_idx[d].data(), nK[d], deg);
+        copy_rows(new_codes[d].data(), posR.data(), rc_b.data(), r_src.data(), nRp, deg);
+      }
+    }
+    // tags (every tag but the numbering and the partition bookkeeping, which are rebuilt)
+    for (auto const& tag : mesh->tags_[d]) {
+      if (tag.name == "global" || tag.name.compare(0, 4, "own:") == 0) continue;
+      int const rb = Tag::elem_bytes(tag.type) * tag.ncomps;
+      Bytes bt(int64_t(nB[d]) * rb);
+      copy_rows(bt.data(), nullptr, tag.data(), band_idx[d].data(), nB[d], rb);
+      int64_t nr4 = 0;
+      Bytes rt = exchange(bt.data(), d, rb, &nr4);
+      Tag nt = tag_like(tag, nnew[d]);
+      copy_rows(nt.data(), posK.data(), tag.data(), keep_idx[d].data(), nK[d], rb);
+      copy_rows(nt.data(), posR.data(), rt.data(), r_src.data(), nRp, rb);
+      new_tags[d].push_back(nt);
+    }
+    if (d == dim) {
+      // owner rank of every element: mine for the kept ones, the sender's word for the received
+      LOs bo(nB[d]);
+      {
+        LO* b = bo.data();
+        LO const* bi = band_idx[d].data();
+        LO const* oe = own[d].data();
+        parallel_for(nB[d], OSHB_LAMBDA(LO i) { b[i] = oe[bi[i]] >> 8; }, "reghost(band owners)");
+      }
+      int64_t nr5 = 0;
+      Bytes ro_b = exchange(bo.data(), d, int(sizeof(LO)), &nr5);
+      LO const* ro = reinterpret_cast<LO const*>(ro_b.data());
+      owner_new = LOs(nnew[d]);
+      LO* ow = owner_new.data();
+      LO const* pk = posK.data();
+      LO const* pr = posR.data();
+      LO const* rs = r_src.data();
+      LO const* ki = keep_idx[d].data();
+      LO const* oe = own[d].data();
+      parallel_for(nK[d], OSHB_LAMBDA(LO i) { ow[pk[i]] = oe[ki[i]] >> 8; }, "reghost(owners)");
+      parallel_for(nRp, OSHB_LAMBDA(LO j) { ow[pr[j]] = ro[rs[j]]; }, "reghost(owners)");
+    }
+  }
+  device_error_check("re-ghosting: merge");
+  stage_clock().mark("reghost: exchange + merge");
+
+  // ---- 5. layers, "own:part", the cut
+  Mesh merged = mesh->copy_meta();
+  merged.set_verts(nnew[0]);
+  for (int d = 1; d <= dim; ++d) {
+    Adj a;
+    a.ab2b = new_down[d];
+    a.codes = new_codes[d];
+    merged.set_ents(d, a);
+  }
+  LOs cv2v_a = merged.ask_verts_of(dim);
+  LO const* cv2v = cv2v_a.data();
+  int const nve = dim + 1;
+  LO const ne = nnew[dim], nv = nnew[0];
+  LOs depth_a(ne), inner_a = filled<LO>(ne, 0);
+  LO* depth = depth_a.data();
+  LO* inner = inner_a.data();
+  LO const* ow = owner_new.data();
+  parallel_for(ne, OSHB_LAMBDA(LO e) { depth[e] = (ow[e] == me) ? 0 : DEEP; }, "reghost(depth0)");
+  Bytes vmark_a(nv);
+  I8* vmark = vmark_a.data();
+  for (int layer = 1; layer <= halo; ++layer) {
+    dev_memset(vmark, 0, size_t(nv));
+    parallel_for(ne, OSHB_LAMBDA(LO e) {
+      if (depth[e] < layer)
+        for (int k = 0; k < nve; ++k) vmark[cv2v[int64_t(e) * nve + k]] = 1;
+    }, "reghost(layer mark)");
+    parallel_for(ne, OSHB_LAMBDA(LO e) {
+      if (depth[e] != DEEP) return;
+      bool touched = false;
+      for (int k = 0; k < nve; ++k) touched = touched || vmark[cv2v[int64_t(e) * nve + k]];
+      if (touched) depth[e] = layer;
+    }, "reghost(layer grow)");
+  }
+  // the band: own elements within halo + 1 layers of a foreign one get depth -1, -2, ...
+  for (int layer = 1; layer <= halo + 1; ++layer) {
+    dev_memset(vmark, 0, size_t(nv));
+    parallel_for(ne, OSHB_LAMBDA(LO e) {
+      if (ow[e] != me || inner[e] > 0)
+        for (int k = 0; k < nve; ++k) vmark[cv2v[int64_t(e) * nve + k]] = 1;
+    }, "reghost(band mark)");
+    parallel_for(ne, OSHB_LAMBDA(LO e) {
+      if (ow[e] != me || inner[e] != 0) return;
+      bool touched = false;
+      for (int k = 0; k < nve; ++k) touched = touched || vmark[cv2v[int64_t(e) * nve + k]];
+      if (touched) inner[e] = layer;
+    }, "reghost(band grow)");
+  }
+  parallel_for(ne, OSHB_LAMBDA(LO e) {
+    if (inner[e] > 0) depth[e] = -inner[e];
+  }, "reghost(band depth)");
+  // (lowest owner rank, lowest depth) over the adjacent elements, passed down the stored adjacencies BEFORE the cut
+  LOs rk[4], dp[4];
+  rk[dim] = owner_new;
+  dp[dim] = depth_a;
+  for (int d = dim; d >= 1; --d) {
+    int const deg = simplex_degree(d, d - 1);
+    rk[d - 1] = filled<LO>(nnew[d - 1], P);
+    dp[d - 1] = filled<LO>(nnew[d - 1], DEEP);
+    LO* rl = rk[d - 1].data();
+    LO* dl = dp[d - 1].data();
+    LO const* rh = rk[d].data();
+    LO const* dh = dp[d].data();
+    LO const* nd = new_down[d].data();
+    parallel_for(int64_t(nnew[d]) * deg, OSHB_LAMBDA(LO t) {
+      LO h = t / deg;
+      LO l = nd[t];
+      atomic_min_i32(&rl[l], rh[h]);
+      atomic_min_i32(&dl[l], dh[h]);
+    }, "reghost(chain min)");
+  }
+  // the cut: elements within `halo` layers, and their closure
+  Bytes keep[4];
+  keep[dim] = Bytes(ne);
+  {
+    I8* k = keep[dim].data();
+    parallel_for(ne, OSHB_LAMBDA(LO e) { k[e] = (depth[e] <= halo) ? 1 : 0; }, "reghost(keep elements)");
+  }
+  for (int d = dim; d >= 1; --d) {
+    int const deg = simplex_degree(d, d - 1);
+    keep[d - 1] = filled<I8>(nnew[d - 1], 0);
+    I8* kl = keep[d - 1].data();
+    I8 const* kh = keep[d].data();
+    LO const* nd = new_down[d].data();
+    parallel_for(int64_t(nnew[d]) * deg, OSHB_LAMBDA(LO t) {
+      if (kh[t / deg]) kl[nd[t]] = 1;
+    }, "reghost(keep closure)");
+  }
+  Mesh out = mesh->copy_meta();
+  LOs cut_idx[4], cut_o2n[4];
+  for (int d = 0; d <= dim; ++d) {
+    cut_idx[d] = collect_marked(keep[d]);
+    LO const nc = LO(cut_idx[d].size());
+    cut_o2n[d] = filled<LO>(nnew[d], -1);
+    LO* on = cut_o2n[d].data();
+    LO const* ci = cut_idx[d].data();
+    parallel_for(nc, OSHB_LAMBDA(LO i) { on[ci[i]] = i; }, "reghost(cut map)");
+    if (d == 0) {
+      out.set_verts(nc);
+    } else {
+      int const deg = simplex_degree(d, d - 1);
+      Adj a;
+      a.ab2b = LOs(int64_t(nc) * deg);
+      LO* rows = a.ab2b.data();
+      LO const* nd = new_down[d].data();
+      LO const* onl = cut_o2n[d - 1].data();
+      parallel_for(int64_t(nc) * deg, OSHB_LAMBDA(LO t) {
+        LO i = t / deg;
+        int k = t - i * deg;
+        rows[t] = onl[nd[int64_t(ci[i]) * deg + k]];
+      }, "reghost(cut rows)");
+      if (d >= 2) {
+        a.codes = Bytes(int64_t(nc) * deg);
+        copy_rows(a.codes.data(), nullptr, new_codes[d].data(), ci, nc, deg);
+      }
+      out.set_ents(d, a);
+    }
+    GOs g(nc);
+    copy_rows(g.data(), nullptr, new_gid[d].data(), ci, nc, int(sizeof(GO)));
+    out.add_tag(d, "global", 1, g, true);
+    for (auto const& nt : new_tags[d]) {
+      Tag ct = tag_like(nt, nc);
+      copy_rows(ct.data(), nullptr, nt.data(), ci, nc, Tag::elem_bytes(nt.type) * nt.ncomps);
+      out.add_tag(d, ct, true);
+    }
+    LOs op(nc);
+    {
+      LO* o = op.data();
+      LO const* r = rk[d].data();
+      LO const* q = dp[d].data();
+      parallel_for(nc, OSHB_LAMBDA(LO i) { o[i] = (r[ci[i]] << 8) | (q[ci[i]] & 0xff); }, "reghost(own:part)");
+    }
+    out.add_tag(d, "own:part", 1, op, true);
+  }
+  device_error_check("re-ghosting: cut");
+  *mesh = out;
+  stage_clock().mark("reghost: layers + cut");
+}
+
 }  // namespace oshb

@@ -281,6 +281,10 @@ int comm_size(Comm* c);
 int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo, int* passes, GO* nglobal,
     DistPassStats* stats);
 
+// re-ghosting of a part whose halo is used up (dist.cu; the role of ghost_mesh + migrate_mesh,
+// src/Omega_h_ghost.cpp:102-141, src/Omega_h_migrate.cpp:15-225)
+void dist_reghost(Mesh* mesh, Comm* comm, int halo);
+
 struct PassStats {
   LO ncands = 0, nkeys = 0, indset_rounds = 0;
   LO nents_before[4] = {0, 0, 0, 0};

@@ -190,6 +190,9 @@ OSHB_HD LO atomic_add(LO* p, LO v) {
 OSHB_HD void atomic_max_i32(int* p, int v) {
   if (v > *p) *p = v;
 }
+OSHB_HD void atomic_min_i32(int* p, int v) {
+  if (v < *p) *p = v;
+}
 OSHB_HD void atomic_or_i32(int* p, int v) { *p |= v; }
 OSHB_HD void raise_flag(int* cell, int v) { *cell |= v; }
 #else
@@ -243,6 +246,7 @@ void parallel_for_any(int64_t n, F f, int* cell, int bit, char const* name = nul
 }
 __device__ __forceinline__ LO atomic_add(LO* p, LO v) { return atomicAdd(p, v); }
 __device__ __forceinline__ void atomic_max_i32(int* p, int v) { atomicMax(p, v); }
+__device__ __forceinline__ void atomic_min_i32(int* p, int v) { atomicMin(p, v); }
 // idempotent OR on scattered addresses: skip the atomic when the bits are already set
 __device__ __forceinline__ void atomic_or_i32(int* p, int v) {
   if ((*reinterpret_cast<volatile int*>(p) & v) != v) atomicOr(p, v);

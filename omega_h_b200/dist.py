@@ -44,6 +44,9 @@ _PASS_DTYPE = {PASS_CANDIDATES: torch.int8, PASS_STATES: torch.int8, PASS_QUALIT
                PASS_OFFSETS: torch.int32, PASS_OLD2NEW: torch.int32, PASS_KEYS2EDGES: torch.int32}
 DEEP = 127
 USE_PY_PASS = __import__("os").environ.get("OSHB_DIST_PY", "0") == "1"
+# OSHB_REGHOST_PY=1: the earlier torch-level re-ghosting instead of the library's (oshb_dist_reghost); kept as a
+# second implementation the tests compare against
+USE_PY_REGHOST = __import__("os").environ.get("OSHB_REGHOST_PY", "0") == "1"
 CHECK = bool(int(__import__("os").environ.get("OSHB_DIST_CHECK", "0")))  # consistency asserts (tests turn them on)
 
 # optional wall-clock breakdown of the partitioned pass (OSHB_DIST_TIMING=1): every section is
@@ -614,6 +617,21 @@ class DistMesh:
 
     # ---- a fresh halo ---------------------------------------------------------------------------
     def reghost(self):
+        """Replace the worn halo by a fresh one: the library's C++ re-ghosting (csrc/dist.cu dist_reghost,
+        oshb_dist_reghost) over the same transport as the pass. OSHB_REGHOST_PY=1 runs the torch-level version
+        below instead."""
+        if USE_PY_REGHOST:
+            return self._reghost_py()
+        self.nreghosts += 1
+        mesh = self.mesh
+        comm = library_comm(mesh.lib, self.device, self.group)
+        self.dm._pre()
+        mesh.lib.check(mesh.lib.c.oshb_dist_reghost(mesh.h, comm, C.c_int(self.halo)))
+        self.dm = DevMesh(mesh, self.device)
+        self.passes = 0
+        self.reghosts = getattr(self, "reghosts", 0) + 1
+
+    def _reghost_py(self):
         """Replace the worn halo by a fresh one (what ghost_mesh + migrate_mesh do in the reference,
         src/Omega_h_ghost.cpp:102-141, src/Omega_h_migrate.cpp:15-225, once per `halo` passes instead
         of twice per pass). Every rank keeps the closure of its own elements and receives the bands of
