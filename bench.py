@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table to stderr and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--parity-halo", type=int, default=0,
+                    help="N > 1: halo of the N-rank == serial self-check (default: --halo; a halo below the pass count "
+                         "puts the library's re-ghosting into the check)")
     ap.add_argument("--time-reghost", action="store_true",
                     help="N > 1: also time DistMesh.reghost of the refined anisotropic part (twice: cold, warm)")
     ap.add_argument("--no-also", action="store_true", help="skip the `also` block (N = 1: aniso n=64 loop + 100 M-tet adjacency microbench; N > 1: the "
@@ -520,7 +523,7 @@ def partition_parity_check(lib, device, halo, n=16):
         passes += 1
     whole = part.gather(0)
     res = {"ok": True, "ranks": world, "box": "%dx%dx%d cells" % (shape[0] * n, shape[1] * n, shape[2] * n),
-           "halo": halo, "passes": passes, "arrays_compared": 0}
+           "halo": halo, "passes": passes, "reghosts": int(getattr(part, "nreghosts", 0)), "arrays_compared": 0}
     if rank == 0:
         bad = []
         if passes != spasses:
@@ -832,7 +835,7 @@ def main_b200_partitioned(args):
     shape = box_shape(world)
     parity = None
     if not args.no_parity_check:
-        parity = partition_parity_check(lib, device, args.halo)
+        parity = partition_parity_check(lib, device, args.parity_halo or args.halo)
         torch.cuda.empty_cache()
     base = build_box(float(shape[0]), float(shape[1]), float(shape[2]), shape[0] * n, shape[1] * n, shape[2] * n, lib=lib)
     h = 1.0 / n / 2.0
