@@ -49,9 +49,9 @@ def parse_args():
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table to stderr and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--parity-halo", type=int, default=0,
-                    help="N > 1: halo of the N-rank == serial self-check (default: --halo; a halo below the pass count "
-                         "puts the library's re-ghosting into the check)")
+    ap.add_argument("--parity-halo", type=int, default=2,
+                    help="N > 1: halo of the N-rank == serial self-check (default 2: below its 4 passes, so the library's "
+                         "re-ghosting over NCCL is part of what is checked; 0 = --halo)")
     ap.add_argument("--time-reghost", action="store_true",
                     help="N > 1: also time DistMesh.reghost of the refined anisotropic part (twice: cold, warm)")
     ap.add_argument("--no-also", action="store_true", help="skip the `also` block (N = 1: aniso n=64 loop + 100 M-tet adjacency microbench; N > 1: the "
