@@ -52,8 +52,11 @@ def parse_args():
     ap.add_argument("--parity-halo", type=int, default=2,
                     help="N > 1: halo of the N-rank == serial self-check (default 2: below its 4 passes, so the library's "
                          "re-ghosting over NCCL is part of what is checked; 0 = --halo)")
-    ap.add_argument("--time-reghost", action="store_true",
-                    help="N > 1: also time DistMesh.reghost of the refined anisotropic part (twice: cold, warm)")
+    ap.add_argument("--no-time-reghost", dest="time_reghost", action="store_false",
+                    help="N > 1: do not time the library's re-ghosting (oshb_dist_reghost) of the refined anisotropic part "
+                         "(twice: first call, warm) after the `also` loop")
+    ap.add_argument("--time-reghost", dest="time_reghost", action="store_true", help=argparse.SUPPRESS)
+    ap.set_defaults(time_reghost=True)
     ap.add_argument("--no-also", action="store_true", help="skip the `also` block (N = 1: aniso n=64 loop + 100 M-tet adjacency microbench; N > 1: the "
                          "anisotropic partitioned loop)")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the N-rank == serial self-check")
@@ -420,8 +423,8 @@ def aniso_metric_of_box(m, n):
 def also_aniso_partitioned(lib, device, n, halo, parting, steps=3, time_reghost=False):
     """BASELINE config[3] (the anisotropic cube partitioned over the ranks, metric + coordinates + classification
     transferred every pass): N x n^3 cells, one shock layer per unit cube, RIB parts. The loop has 8 passes; it runs on
-    an 8-layer halo so that no re-ghosting falls into it; with --time-reghost a re-ghosting (DistMesh.reghost, torch
-    ops) of the refined part is timed separately (cold + warm): a loop on a thinner halo pays that once per `halo` passes."""
+    an 8-layer halo so that no re-ghosting falls into it; a re-ghosting (DistMesh.reghost = oshb_dist_reghost) of the
+    refined part is timed separately (first call + warm): a loop on a thinner halo pays that once per `halo` passes."""
     import torch
     import torch.distributed as dist
     from omega_h_b200 import VERT, AdaptOpts, build_box
