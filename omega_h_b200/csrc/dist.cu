@@ -285,7 +285,7 @@ void pull(Comm* comm, Plan const& plan, T* array) {
 LOs group_by_rank(LOs keys, int P, GOs* counts_out) {
   int64_t const n = keys.size();
   LOs perm(n);
-  if (n) sort_by_keys(keys.data(), n, 1, perm.data());
+  if (n) sort_by_keys_bounded(keys.data(), n, perm.data(), LO(P - 1));  // ranks: no planning read-back
   GOs counts(P);
   GO* cp = counts.data();
   LO const* kp = keys.data();
@@ -568,7 +568,7 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
       LO const nn = LO(nrecv_runs);
       parallel_for(nn, OSHB_LAMBDA(LO i) { rgp[i] = bp[2 * int64_t(i)]; }, "dist(run keys)");
       LOs order(nrecv_runs);
-      sort_by_keys(rg.data(), nrecv_runs, 1, order.data());
+      sort_by_keys_bounded(rg.data(), nrecv_runs, order.data(), N);  // keys of the flattened number axis
       LO const* op = order.data();
       GO* rss = rs_sorted.data();
       parallel_for(nn, OSHB_LAMBDA(LO i) { rss[i] = bp[2 * int64_t(op[i]) + 1]; }, "dist(run sums sorted)");

@@ -54,6 +54,8 @@ static void sort_emu(T const* keys, int64_t n, int width, LO* perm) {
 }
 void sort_by_keys(LO const* keys, int64_t n, int width, LO* perm) { sort_emu(keys, n, width, perm); }
 void sort_by_keys(GO const* keys, int64_t n, int width, LO* perm) { sort_emu(keys, n, width, perm); }
+void sort_by_keys_bounded(LO const* keys, int64_t n, LO* perm, LO) { sort_emu(keys, n, 1, perm); }
+void sort_by_keys_bounded(GO const* keys, int64_t n, LO* perm, GO) { sort_emu(keys, n, 1, perm); }
 
 #else
 // =====================================================================================
@@ -510,8 +512,11 @@ __global__ void __launch_bounds__(OS_T, 3) k_os_scatter(W const* __restrict__ wo
   }
 }
 
+// `bound` >= 0 (width 1 only): the caller vouches that 0 <= key <= bound; the passes are planned from the bound and
+// the pre-pass with its read-back -- the sort's only host synchronisation -- is skipped (the partitioned pass sorts
+// boundary-sized lists three times per pass, where a drained stream costs more than the sort)
 template <class W>
-static void sort_impl(W const* keys, int64_t n, int width, LO* perm) {
+static void sort_impl(W const* keys, int64_t n, int width, LO* perm, long long bound = -1) {
   Ctx& c = ctx();
   OSHB_CHECK(width >= 1 && width <= 4);  // uses have <= 4 vertices
   if (n <= 1) {
@@ -520,9 +525,18 @@ static void sort_impl(W const* keys, int64_t n, int width, LO* perm) {
   }
   OSHB_CHECK(n < (int64_t(1) << 31));
   int const nbytes = int(sizeof(W));
-  // ---- pre-pass: OR/AND of every column, one read of the keys
-  DArr<unsigned long long> orand(2 * int64_t(width));
-  {
+  std::vector<unsigned long long> oa(2 * size_t(width));
+  if (bound >= 0 && width == 1) {
+    // every bit up to the highest bit of the bound may vary (in the order-preserving image the sign bit is constant)
+    unsigned long long m = 0;
+    while (m < static_cast<unsigned long long>(bound)) m = (m << 1) | 1ull;
+    // image of 0 under os_ordered (a device function: restated here for the host)
+    unsigned long long const sign = (sizeof(W) == 4) ? 0x80000000ull : 0x8000000000000000ull;
+    oa[0] = sign | m;
+    oa[1] = sign;
+  } else {
+    // ---- pre-pass: OR/AND of every column, one read of the keys
+    DArr<unsigned long long> orand(2 * int64_t(width));
     std::vector<unsigned long long> init(2 * size_t(width));
     for (int k = 0; k < width; ++k) {
       init[2 * k] = 0ull;
@@ -541,8 +555,8 @@ static void sort_impl(W const* keys, int64_t n, int width, LO* perm) {
     OSHB_CUDA(cudaGetLastError());
     if (c.prof_on) prof_end("sort_by_keys(pre)");
     c.launches++;
+    oa = orand.to_host();  // the sort's one read-back
   }
-  std::vector<unsigned long long> oa = orand.to_host();  // the sort's one read-back
   // ---- plan: the bytes that vary, last word first
   struct Pass {
     int word, byte;
@@ -598,11 +612,13 @@ static void sort_impl(W const* keys, int64_t n, int width, LO* perm) {
     pout = palt;
     palt = tp;
   }
-  sync_stream();  // temporaries are released stream-ordered, but keep the host view simple
+  // (temporaries are released in stream order: no synchronisation needed here)
 }
 
 void sort_by_keys(LO const* keys, int64_t n, int width, LO* perm) { sort_impl<LO>(keys, n, width, perm); }
 void sort_by_keys(GO const* keys, int64_t n, int width, LO* perm) { sort_impl<GO>(keys, n, width, perm); }
+void sort_by_keys_bounded(LO const* keys, int64_t n, LO* perm, LO bound) { sort_impl<LO>(keys, n, 1, perm, bound); }
+void sort_by_keys_bounded(GO const* keys, int64_t n, LO* perm, GO bound) { sort_impl<GO>(keys, n, 1, perm, bound); }
 
 #endif  // OSHB_EMU
 

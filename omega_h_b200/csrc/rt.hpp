@@ -274,6 +274,9 @@ void minmax_f64(Real const* in, int64_t n, Real* mn, Real* mx);
 // stable sort of n keys of `width` words each; writes the permutation (sorted -> original)
 void sort_by_keys(LO const* keys, int64_t n, int width, LO* perm);  // src/Omega_h_sort.cpp:57-92
 void sort_by_keys(GO const* keys, int64_t n, int width, LO* perm);
+// one-word keys known to lie in [0, bound]: no planning read-back, no host synchronisation at all
+void sort_by_keys_bounded(LO const* keys, int64_t n, LO* perm, LO bound);
+void sort_by_keys_bounded(GO const* keys, int64_t n, LO* perm, GO bound);
 
 // ---- small helpers built on parallel_for ------------------------------------------
 template <class T>
