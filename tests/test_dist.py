@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 WORKER = os.path.join(HERE, "dist_worker.py")
 
 
-def run_worker(nranks, lib_path, device, n, halo, aniso, dim, port, timeout=900, parting="hilbert", py_pass=False):
+def run_worker(nranks, lib_path, device, n, halo, aniso, dim, port, timeout=900, parting="hilbert", py_pass=False,
+               py_reghost=False):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
            "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, lib_path, device, str(n), str(halo),
            str(aniso), str(dim), parting]
@@ -18,6 +19,7 @@ def run_worker(nranks, lib_path, device, n, halo, aniso, dim, port, timeout=900,
     env["OMP_NUM_THREADS"] = "1"
     env["OSHB_DIST_CHECK"] = "1"
     env["OSHB_DIST_PY"] = "1" if py_pass else "0"   # 0: the library's C++ pass (csrc/dist.cu); 1: the torch-level pass
+    env["OSHB_REGHOST_PY"] = "1" if py_reghost else "0"   # 0: the library's re-ghosting (oshb_dist_reghost); 1: torch ops
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     return r.stdout
@@ -45,6 +47,14 @@ def test_reghosting_gloo(emu_lib, nranks, n, halo, aniso, dim):
     """loops longer than the halo: DistMesh.reghost() must hand every rank a halo on which the
     remaining passes again equal the serial ones"""
     out = run_worker(nranks, emu_lib.path, "cpu", n, halo, aniso, dim, 29560 + nranks + n + halo)
+    assert int(out.split("reghosts=")[1].split()[0]) >= 1
+
+
+@pytest.mark.parametrize("nranks,n,halo,aniso,dim", [(2, 8, 2, 0, 3), (3, 6, 1, 0, 3)])
+def test_torch_level_reghost_still_matches_serial_gloo(emu_lib, nranks, n, halo, aniso, dim):
+    """the earlier re-ghosting in torch ops (dist.py _reghost_py, OSHB_REGHOST_PY=1): a second, independent
+    implementation the library's oshb_dist_reghost is compared with (both must reproduce the serial loop)"""
+    out = run_worker(nranks, emu_lib.path, "cpu", n, halo, aniso, dim, 29650 + nranks + n + halo, py_reghost=True)
     assert int(out.split("reghosts=")[1].split()[0]) >= 1
 
 
