@@ -281,6 +281,12 @@ int oshb_dist_refine_by_size(oshb_mesh* part, oshb_comm* comm, const oshb_adapt_
  * what ghost_mesh + migrate_mesh do in the reference (src/Omega_h_ghost.cpp:102-141, src/Omega_h_migrate.cpp:15-225),
  * once per `halo` passes instead of twice per pass. The part is replaced in place; the caller resets its pass count. */
 int oshb_dist_reghost(oshb_mesh* part, oshb_comm* comm, int halo);
+/* The start of a partitioned run: from a mesh every rank holds in full (entities in global-number order, "global" tags
+ * on it) this rank's part = its own elements + `halo` layers of vertex-adjacent elements, with "own:part" on every
+ * dimension. parting 0: contiguous ranges of the element order; 1: recursive inertial bisection = the assignment
+ * Mesh::balance() makes (src/Omega_h_mesh.cpp:536-568, src/Omega_h_inertia.cpp:162-193; nranks a power of two). The
+ * reference reaches the same state through balance + ghost_mesh (src/Omega_h_ghost.cpp:102-141). Purely local. */
+int oshb_dist_distribute(oshb_mesh* full, int rank, int nranks, int halo, int parting, oshb_mesh** out_part);
 
 /* ---- one refine pass, stage by stage -------------------------------------------------------------
  * The same pass as oshb_refine_by_size, cut at the points where the reference synchronises

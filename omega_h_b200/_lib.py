@@ -60,7 +60,7 @@ SYMBOLS = [
     "oshb_adapt_opts_init", "oshb_mesh_set_transfer", "oshb_set_user_transfer", "oshb_refine_qualities", "oshb_mident_metrics", "oshb_find_indset",
     "oshb_rep_vertex2md_order", "oshb_refine_by_size", "oshb_last_pass_stats",
     "oshb_comm_nccl_unique_id", "oshb_comm_create_nccl", "oshb_comm_create_callbacks", "oshb_comm_destroy",
-    "oshb_dist_refine_by_size", "oshb_dist_reghost",
+    "oshb_dist_refine_by_size", "oshb_dist_reghost", "oshb_dist_distribute",
     "oshb_pass_create", "oshb_pass_destroy", "oshb_pass_begin", "oshb_pass_restate", "oshb_pass_indset_round",
     "oshb_pass_select_keys", "oshb_pass_number", "oshb_pass_finish", "oshb_pass_size", "oshb_pass_get",
     "oshb_pass_set", "oshb_pass_gather", "oshb_pass_scatter", "oshb_pass_runs_begin", "oshb_pass_runs_get",

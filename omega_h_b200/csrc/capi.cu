@@ -327,6 +327,19 @@ int oshb_dist_refine_by_size(oshb_mesh* part, oshb_comm* comm, const oshb_adapt_
   OSHB_CATCH
 }
 
+int oshb_dist_distribute(oshb_mesh* full, int rank, int nranks, int halo, int parting, oshb_mesh** out_part) {
+  OSHB_TRY
+  OSHB_CHECK(full && out_part);
+  auto* h = new oshb_mesh();
+  try {
+    h->m = dist_distribute(&full->m, rank, nranks, halo, parting);
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  *out_part = h;
+  OSHB_CATCH
+}
 int oshb_dist_reghost(oshb_mesh* part, oshb_comm* comm, int halo) {
   OSHB_TRY
   OSHB_CHECK(part && comm);

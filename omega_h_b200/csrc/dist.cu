@@ -691,6 +691,149 @@ constexpr int DEEP = 127;
 
 }  // namespace
 
+// From a mesh that contains this rank's own elements and at least `halo` + 1 layers around them (entities in
+// increasing global number, every tag to keep on it, "global" included): the part = own elements + `halo` layers,
+// with "own:part" = (lowest owner rank << 8) | lowest depth over the adjacent elements on every dimension, taken
+// BEFORE the cut (the layer beyond the halo still counts). Layers by sweeps over element -> vertex rows: `halo`
+// outward from the own elements (depth 1 .. halo), `halo` + 1 inward from the foreign ones (the band, depth -1 ...).
+static Mesh cut_part(Mesh* src, LOs owner_new, int halo, int me, int P) {
+  int const dim = src->dim();
+  LO nnew[4] = {0, 0, 0, 0};
+  LOs new_down[4];
+  Bytes new_codes[4];
+  for (int d = 0; d <= dim; ++d) {
+    nnew[d] = src->nents(d);
+    if (d >= 1) {
+      Adj a = src->ask_down(d, d - 1);
+      new_down[d] = a.ab2b;
+      new_codes[d] = a.codes;
+    }
+  }
+  LOs cv2v_a = src->ask_verts_of(dim);
+  LO const* cv2v = cv2v_a.data();
+  int const nve = dim + 1;
+  LO const ne = nnew[dim], nv = nnew[0];
+  LOs depth_a(ne), inner_a = filled<LO>(ne, 0);
+  LO* depth = depth_a.data();
+  LO* inner = inner_a.data();
+  LO const* ow = owner_new.data();
+  parallel_for(ne, OSHB_LAMBDA(LO e) { depth[e] = (ow[e] == me) ? 0 : DEEP; }, "reghost(depth0)");
+  Bytes vmark_a(nv);
+  I8* vmark = vmark_a.data();
+  for (int layer = 1; layer <= halo; ++layer) {
+    dev_memset(vmark, 0, size_t(nv));
+    parallel_for(ne, OSHB_LAMBDA(LO e) {
+      if (depth[e] < layer)
+        for (int k = 0; k < nve; ++k) vmark[cv2v[int64_t(e) * nve + k]] = 1;
+    }, "reghost(layer mark)");
+    parallel_for(ne, OSHB_LAMBDA(LO e) {
+      if (depth[e] != DEEP) return;
+      bool touched = false;
+      for (int k = 0; k < nve; ++k) touched = touched || vmark[cv2v[int64_t(e) * nve + k]];
+      if (touched) depth[e] = layer;
+    }, "reghost(layer grow)");
+  }
+  // the band: own elements within halo + 1 layers of a foreign one get depth -1, -2, ...
+  for (int layer = 1; layer <= halo + 1; ++layer) {
+    dev_memset(vmark, 0, size_t(nv));
+    parallel_for(ne, OSHB_LAMBDA(LO e) {
+      if (ow[e] != me || inner[e] > 0)
+        for (int k = 0; k < nve; ++k) vmark[cv2v[int64_t(e) * nve + k]] = 1;
+    }, "reghost(band mark)");
+    parallel_for(ne, OSHB_LAMBDA(LO e) {
+      if (ow[e] != me || inner[e] != 0) return;
+      bool touched = false;
+      for (int k = 0; k < nve; ++k) touched = touched || vmark[cv2v[int64_t(e) * nve + k]];
+      if (touched) inner[e] = layer;
+    }, "reghost(band grow)");
+  }
+  parallel_for(ne, OSHB_LAMBDA(LO e) {
+    if (inner[e] > 0) depth[e] = -inner[e];
+  }, "reghost(band depth)");
+  // (lowest owner rank, lowest depth) over the adjacent elements, passed down the stored adjacencies BEFORE the cut
+  LOs rk[4], dp[4];
+  rk[dim] = owner_new;
+  dp[dim] = depth_a;
+  for (int d = dim; d >= 1; --d) {
+    int const deg = simplex_degree(d, d - 1);
+    rk[d - 1] = filled<LO>(nnew[d - 1], P);
+    dp[d - 1] = filled<LO>(nnew[d - 1], DEEP);
+    LO* rl = rk[d - 1].data();
+    LO* dl = dp[d - 1].data();
+    LO const* rh = rk[d].data();
+    LO const* dh = dp[d].data();
+    LO const* nd = new_down[d].data();
+    parallel_for(int64_t(nnew[d]) * deg, OSHB_LAMBDA(LO t) {
+      LO h = t / deg;
+      LO l = nd[t];
+      atomic_min_i32(&rl[l], rh[h]);
+      atomic_min_i32(&dl[l], dh[h]);
+    }, "reghost(chain min)");
+  }
+  // the cut: elements within `halo` layers, and their closure
+  Bytes keep[4];
+  keep[dim] = Bytes(ne);
+  {
+    I8* k = keep[dim].data();
+    parallel_for(ne, OSHB_LAMBDA(LO e) { k[e] = (depth[e] <= halo) ? 1 : 0; }, "reghost(keep elements)");
+  }
+  for (int d = dim; d >= 1; --d) {
+    int const deg = simplex_degree(d, d - 1);
+    keep[d - 1] = filled<I8>(nnew[d - 1], 0);
+    I8* kl = keep[d - 1].data();
+    I8 const* kh = keep[d].data();
+    LO const* nd = new_down[d].data();
+    parallel_for(int64_t(nnew[d]) * deg, OSHB_LAMBDA(LO t) {
+      if (kh[t / deg]) kl[nd[t]] = 1;
+    }, "reghost(keep closure)");
+  }
+  Mesh out = src->copy_meta();
+  LOs cut_idx[4], cut_o2n[4];
+  for (int d = 0; d <= dim; ++d) {
+    cut_idx[d] = collect_marked(keep[d]);
+    LO const nc = LO(cut_idx[d].size());
+    cut_o2n[d] = filled<LO>(nnew[d], -1);
+    LO* on = cut_o2n[d].data();
+    LO const* ci = cut_idx[d].data();
+    parallel_for(nc, OSHB_LAMBDA(LO i) { on[ci[i]] = i; }, "reghost(cut map)");
+    if (d == 0) {
+      out.set_verts(nc);
+    } else {
+      int const deg = simplex_degree(d, d - 1);
+      Adj a;
+      a.ab2b = LOs(int64_t(nc) * deg);
+      LO* rows = a.ab2b.data();
+      LO const* nd = new_down[d].data();
+      LO const* onl = cut_o2n[d - 1].data();
+      parallel_for(int64_t(nc) * deg, OSHB_LAMBDA(LO t) {
+        LO i = t / deg;
+        int k = t - i * deg;
+        rows[t] = onl[nd[int64_t(ci[i]) * deg + k]];
+      }, "reghost(cut rows)");
+      if (d >= 2) {
+        a.codes = Bytes(int64_t(nc) * deg);
+        copy_rows(a.codes.data(), nullptr, new_codes[d].data(), ci, nc, deg);
+      }
+      out.set_ents(d, a);
+    }
+    for (auto const& nt : src->tags_[d]) {
+      if (nt.name.compare(0, 4, "own:") == 0) continue;
+      Tag ct = tag_like(nt, nc);
+      copy_rows(ct.data(), nullptr, nt.data(), ci, nc, Tag::elem_bytes(nt.type) * nt.ncomps);
+      out.add_tag(d, ct, true);
+    }
+    LOs op(nc);
+    {
+      LO* o = op.data();
+      LO const* r = rk[d].data();
+      LO const* q = dp[d].data();
+      parallel_for(nc, OSHB_LAMBDA(LO i) { o[i] = (r[ci[i]] << 8) | (q[ci[i]] & 0xff); }, "reghost(own:part)");
+    }
+    out.add_tag(d, "own:part", 1, op, true);
+  }
+  return out;
+}
+
 void dist_reghost(Mesh* mesh, Comm* comm, int halo) {
   int const P = comm->size, me = comm->rank;
   int const dim = mesh->dim();
@@ -941,133 +1084,36 @@ void dist_reghost(Mesh* mesh, Comm* comm, int halo) {
     a.codes = new_codes[d];
     merged.set_ents(d, a);
   }
-  LOs cv2v_a = merged.ask_verts_of(dim);
-  LO const* cv2v = cv2v_a.data();
-  int const nve = dim + 1;
-  LO const ne = nnew[dim], nv = nnew[0];
-  LOs depth_a(ne), inner_a = filled<LO>(ne, 0);
-  LO* depth = depth_a.data();
-  LO* inner = inner_a.data();
-  LO const* ow = owner_new.data();
-  parallel_for(ne, OSHB_LAMBDA(LO e) { depth[e] = (ow[e] == me) ? 0 : DEEP; }, "reghost(depth0)");
-  Bytes vmark_a(nv);
-  I8* vmark = vmark_a.data();
-  for (int layer = 1; layer <= halo; ++layer) {
-    dev_memset(vmark, 0, size_t(nv));
-    parallel_for(ne, OSHB_LAMBDA(LO e) {
-      if (depth[e] < layer)
-        for (int k = 0; k < nve; ++k) vmark[cv2v[int64_t(e) * nve + k]] = 1;
-    }, "reghost(layer mark)");
-    parallel_for(ne, OSHB_LAMBDA(LO e) {
-      if (depth[e] != DEEP) return;
-      bool touched = false;
-      for (int k = 0; k < nve; ++k) touched = touched || vmark[cv2v[int64_t(e) * nve + k]];
-      if (touched) depth[e] = layer;
-    }, "reghost(layer grow)");
-  }
-  // the band: own elements within halo + 1 layers of a foreign one get depth -1, -2, ...
-  for (int layer = 1; layer <= halo + 1; ++layer) {
-    dev_memset(vmark, 0, size_t(nv));
-    parallel_for(ne, OSHB_LAMBDA(LO e) {
-      if (ow[e] != me || inner[e] > 0)
-        for (int k = 0; k < nve; ++k) vmark[cv2v[int64_t(e) * nve + k]] = 1;
-    }, "reghost(band mark)");
-    parallel_for(ne, OSHB_LAMBDA(LO e) {
-      if (ow[e] != me || inner[e] != 0) return;
-      bool touched = false;
-      for (int k = 0; k < nve; ++k) touched = touched || vmark[cv2v[int64_t(e) * nve + k]];
-      if (touched) inner[e] = layer;
-    }, "reghost(band grow)");
-  }
-  parallel_for(ne, OSHB_LAMBDA(LO e) {
-    if (inner[e] > 0) depth[e] = -inner[e];
-  }, "reghost(band depth)");
-  // (lowest owner rank, lowest depth) over the adjacent elements, passed down the stored adjacencies BEFORE the cut
-  LOs rk[4], dp[4];
-  rk[dim] = owner_new;
-  dp[dim] = depth_a;
-  for (int d = dim; d >= 1; --d) {
-    int const deg = simplex_degree(d, d - 1);
-    rk[d - 1] = filled<LO>(nnew[d - 1], P);
-    dp[d - 1] = filled<LO>(nnew[d - 1], DEEP);
-    LO* rl = rk[d - 1].data();
-    LO* dl = dp[d - 1].data();
-    LO const* rh = rk[d].data();
-    LO const* dh = dp[d].data();
-    LO const* nd = new_down[d].data();
-    parallel_for(int64_t(nnew[d]) * deg, OSHB_LAMBDA(LO t) {
-      LO h = t / deg;
-      LO l = nd[t];
-      atomic_min_i32(&rl[l], rh[h]);
-      atomic_min_i32(&dl[l], dh[h]);
-    }, "reghost(chain min)");
-  }
-  // the cut: elements within `halo` layers, and their closure
-  Bytes keep[4];
-  keep[dim] = Bytes(ne);
-  {
-    I8* k = keep[dim].data();
-    parallel_for(ne, OSHB_LAMBDA(LO e) { k[e] = (depth[e] <= halo) ? 1 : 0; }, "reghost(keep elements)");
-  }
-  for (int d = dim; d >= 1; --d) {
-    int const deg = simplex_degree(d, d - 1);
-    keep[d - 1] = filled<I8>(nnew[d - 1], 0);
-    I8* kl = keep[d - 1].data();
-    I8 const* kh = keep[d].data();
-    LO const* nd = new_down[d].data();
-    parallel_for(int64_t(nnew[d]) * deg, OSHB_LAMBDA(LO t) {
-      if (kh[t / deg]) kl[nd[t]] = 1;
-    }, "reghost(keep closure)");
-  }
-  Mesh out = mesh->copy_meta();
-  LOs cut_idx[4], cut_o2n[4];
   for (int d = 0; d <= dim; ++d) {
-    cut_idx[d] = collect_marked(keep[d]);
-    LO const nc = LO(cut_idx[d].size());
-    cut_o2n[d] = filled<LO>(nnew[d], -1);
-    LO* on = cut_o2n[d].data();
-    LO const* ci = cut_idx[d].data();
-    parallel_for(nc, OSHB_LAMBDA(LO i) { on[ci[i]] = i; }, "reghost(cut map)");
-    if (d == 0) {
-      out.set_verts(nc);
-    } else {
-      int const deg = simplex_degree(d, d - 1);
-      Adj a;
-      a.ab2b = LOs(int64_t(nc) * deg);
-      LO* rows = a.ab2b.data();
-      LO const* nd = new_down[d].data();
-      LO const* onl = cut_o2n[d - 1].data();
-      parallel_for(int64_t(nc) * deg, OSHB_LAMBDA(LO t) {
-        LO i = t / deg;
-        int k = t - i * deg;
-        rows[t] = onl[nd[int64_t(ci[i]) * deg + k]];
-      }, "reghost(cut rows)");
-      if (d >= 2) {
-        a.codes = Bytes(int64_t(nc) * deg);
-        copy_rows(a.codes.data(), nullptr, new_codes[d].data(), ci, nc, deg);
-      }
-      out.set_ents(d, a);
-    }
-    GOs g(nc);
-    copy_rows(g.data(), nullptr, new_gid[d].data(), ci, nc, int(sizeof(GO)));
-    out.add_tag(d, "global", 1, g, true);
-    for (auto const& nt : new_tags[d]) {
-      Tag ct = tag_like(nt, nc);
-      copy_rows(ct.data(), nullptr, nt.data(), ci, nc, Tag::elem_bytes(nt.type) * nt.ncomps);
-      out.add_tag(d, ct, true);
-    }
-    LOs op(nc);
-    {
-      LO* o = op.data();
-      LO const* r = rk[d].data();
-      LO const* q = dp[d].data();
-      parallel_for(nc, OSHB_LAMBDA(LO i) { o[i] = (r[ci[i]] << 8) | (q[ci[i]] & 0xff); }, "reghost(own:part)");
-    }
-    out.add_tag(d, "own:part", 1, op, true);
+    merged.add_tag(d, "global", 1, new_gid[d], true);
+    for (auto const& nt : new_tags[d]) merged.add_tag(d, nt, true);
   }
+  Mesh out = cut_part(&merged, owner_new, halo, me, P);
   device_error_check("re-ghosting: cut");
   *mesh = out;
   stage_clock().mark("reghost: layers + cut");
+}
+
+// Cut a mesh that every rank holds in full into this rank's part + `halo` layers of vertex-adjacent elements (the
+// start of a partitioned run; the reference reaches the same state through Mesh::balance + ghost_mesh,
+// src/Omega_h_mesh.cpp:536-568, src/Omega_h_ghost.cpp:102-141). parting 0: contiguous ranges of the element order,
+// 1: recursive inertial bisection (rib.cu, bit-identical to the reference's assignment).
+Mesh dist_distribute(Mesh* full, int rank, int nranks, int halo, int parting) {
+  OSHB_CHECK(halo >= 1 && halo <= 125 && nranks >= 1 && rank >= 0 && rank < nranks);
+  device_error_reset();
+  LO const ne = full->nelems();
+  LOs owner;
+  if (parting == 1) {
+    owner = rib_partition(full, nranks, nullptr);
+  } else {
+    owner = LOs(ne);
+    LO* o = owner.data();
+    int const P = nranks;
+    parallel_for(ne, OSHB_LAMBDA(LO e) { o[e] = LO((int64_t(e) * P) / ne); }, "distribute(ranges)");
+  }
+  Mesh out = cut_part(full, owner, halo, rank, nranks);
+  device_error_check("distribute");
+  return out;
 }
 
 }  // namespace oshb

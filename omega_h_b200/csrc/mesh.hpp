@@ -284,6 +284,8 @@ int dist_refine_by_size(Mesh* mesh, Comm* comm, AdaptOpts const& opts, int halo,
 // re-ghosting of a part whose halo is used up (dist.cu; the role of ghost_mesh + migrate_mesh,
 // src/Omega_h_ghost.cpp:102-141, src/Omega_h_migrate.cpp:15-225)
 void dist_reghost(Mesh* mesh, Comm* comm, int halo);
+// this rank's part (+ halo layers, "own:part" tags) of a mesh every rank holds in full; parting 0 ranges, 1 RIB
+Mesh dist_distribute(Mesh* full, int rank, int nranks, int halo, int parting);
 
 struct PassStats {
   LO ncands = 0, nkeys = 0, indset_rounds = 0;

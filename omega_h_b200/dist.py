@@ -961,6 +961,18 @@ def distribute(base, halo, device, group=None, parting="hilbert"):
                            (src/Omega_h_mesh.cpp:536-568; library: oshb_mesh_rib_partition) -- world size 2^k."""
     P = dist.get_world_size(group)
     assert 1 <= halo <= 125, "depths are kept in a signed byte (DEEP = 127, band down to -(halo + 1))"
+    if not USE_PY_REGHOST:
+        # the library's cut (csrc/dist.cu dist_distribute): owners by ranges or RIB, layers, "own:part", compaction
+        assert parting in ("hilbert", "rib")
+        src = DevMesh(base, device)
+        src._pre()
+        h = C.c_void_p()
+        base.lib.check(base.lib.c.oshb_dist_distribute(base.h, C.c_int(dist.get_rank(group)), C.c_int(P), C.c_int(int(halo)),
+                                                       C.c_int(1 if parting == "rib" else 0), C.byref(h)))
+        src._post()
+        part = DistMesh(Mesh(base.dim(), base.lib, h), device, halo, group)
+        part.nglobal = [base.nents(d) for d in range(base.dim() + 1)] + [0] * (3 - base.dim())
+        return part
     src = DevMesh(base, device)
     dev = src.device
     dim = base.dim()
