@@ -60,3 +60,28 @@ def test_cpp_caller_corner_trace_emulation(emu_lib):
 def test_cpp_caller_corner_trace_gpu(gpu_lib):
     out = _run_example("corner_refine")
     assert CORNER_KEYS in out and "sm_100a" in out
+
+
+def _run_partitioned(exe, *args):
+    """examples/partitioned_refine.cpp: a C++ host of the partitioned loop over the C ABI only -- oshb_dist_distribute,
+    oshb_dist_refine_by_size, oshb_dist_reghost when the halo is used up -- compared by the program itself with the
+    serial loop (pass count, global and local element counts)"""
+    import subprocess
+    build = os.path.join(ROOT, "examples", "_build")
+    if not os.path.exists(os.path.join(build, exe)):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "examples"), "emu" if exe.endswith("_emu") else "all"], check=True)
+    r = subprocess.run([os.path.join(build, exe)] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PARTITIONED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_cpp_host_partitioned_loop_emulation(emu_lib):
+    out = _run_partitioned("partitioned_refine_emu", 6, 2)    # callbacks transport, two re-ghostings
+    assert "2 re-ghostings" in out
+    _run_partitioned("partitioned_refine_emu", 5, 4)
+
+
+@pytest.mark.gpu
+def test_cpp_host_partitioned_loop_gpu(gpu_lib):
+    out = _run_partitioned("partitioned_refine", 16, 2)       # NCCL transport bound at run time, no Python, no torch
+    assert "1 re-ghostings" in out
