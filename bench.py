@@ -226,8 +226,8 @@ def main_reference(args):
     else:
         recs = run_reference_loops(args.n, kind, args.warmup + args.steps, budget)
     if not recs:
-        print(json.dumps({"impl": args.impl, "unavailable": "oracle/_ref/%s missing or failed" %
-                          ("ref_driver_cuda (make -C oracle refcuda)" if cuda else "ref_driver_omp")}))
+        emit({"impl": args.impl, "unavailable": "oracle/_ref/%s missing or failed" %
+              ("ref_driver_cuda (make -C oracle refcuda)" if cuda else "ref_driver_omp")})
         return 0
     warm = min(args.warmup, max(len(recs) - 1, 0))
     timed = recs[warm:]
@@ -253,7 +253,7 @@ def main_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -498,6 +498,28 @@ def also_aniso_partitioned(lib, device, n, halo, parting, steps=3, time_reghost=
                       "the refined part between two barriers, max over ranks, outside the loop's timed region"}
 
 
+ALSO_TIMEOUT_S = 300
+
+
+def run_guarded(seconds, on_timeout, fn):
+    """fn() with a dead-man's switch: if it has not returned after `seconds`, on_timeout() runs on a timer thread
+    (bench.py uses it to print the headline line and end the process when the optional `also` block hangs)"""
+    import threading
+    done = threading.Event()
+
+    def fire():
+        if not done.is_set():
+            on_timeout()
+    timer = threading.Timer(seconds, fire)
+    timer.daemon = True
+    timer.start()
+    try:
+        return fn()
+    finally:
+        done.set()
+        timer.cancel()
+
+
 def partition_parity_check(lib, device, halo, n=16):
     """N-rank == serial, checked on the GPUs of this very run before anything is timed: an n^3-per-rank box
     goes through the partitioned loop (NCCL exchanges and all), is assembled on rank 0 (DistMesh.gather) and
@@ -559,7 +581,7 @@ def partition_parity_check(lib, device, halo, n=16):
     dist.broadcast(flag, 0)
     if int(flag.item()) != 1:
         if rank == 0:
-            print(json.dumps({"parity_check": res}))
+            emit({"parity_check": res})
         raise SystemExit("partitioned result differs from the serial loop: refusing to time it")
     return res
 
@@ -793,7 +815,7 @@ def main_b200(args):
             "wall_ms_per_step": wall_ms / args.steps, "syncs_per_step": None,
             "peak_device_bytes": lib.peak_bytes(), "gpu_baseline": gpu_base, "also": also,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -953,14 +975,8 @@ def main_b200_partitioned(args):
                "ms_per_step": e_s * 1e3 / args.steps,
                "timing": "wall clock around upload + partitioned loop + download of every rank's part, max over ranks"}
 
-    also = None
-    if not args.no_also:
-        torch.cuda.empty_cache()
-        lib.trim()
-        also = {"aniso_n%d" % n: also_aniso_partitioned(lib, device, n, halo, args.parting,
-                                                        time_reghost=args.time_reghost)}
-
-    if rank == 0:
+    def headline(also):
+        """rank 0's ONE json line (the headline numbers are complete before the `also` block starts)"""
         cfg = workload_config(n, "iso")
         cfg["workload"] = ("3D tet box build_box %dx%dx%d cells (x6 tets) = %d ranks x %d^3, uniform isotropic metric "
                            "h=1/(2n), while(refine_by_size) loop on the partitioned mesh" %
@@ -972,14 +988,39 @@ def main_b200_partitioned(args):
         cfg["tets_per_step"] = "%d -> %d" % (nglobal0, nglobal1)
         cfg["local_tets_rank0"] = local1
         cfg["last_pass"] = last
-        line = {
+        return {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
-            "peak_device_bytes": lib.peak_bytes(), "parity_check": parity, "also": also,
+            "peak_device_bytes": peak_bytes, "parity_check": parity, "also": also,
         }
-        print(json.dumps(line))
+
+    peak_bytes = lib.peak_bytes()
+    also = None
+    if not args.no_also:
+        # the `also` block must not be able to lose the headline: if it hangs (a rank that failed leaves the others in
+        # a collective) rank 0 prints the line without it after ALSO_TIMEOUT_S and every rank ends
+        def give_up():
+            if rank == 0:
+                emit(headline({"error": "the also block did not finish within %d s" % ALSO_TIMEOUT_S}))
+            os._exit(0)
+
+        def run_also():
+            torch.cuda.empty_cache()
+            lib.trim()
+            return {"aniso_n%d" % n: also_aniso_partitioned(lib, device, n, halo, args.parting,
+                                                            time_reghost=args.time_reghost)}
+        try:
+            also = run_guarded(ALSO_TIMEOUT_S, give_up, run_also)
+        except Exception as e:  # noqa: BLE001
+            also = {"error": str(e)[:300]}
+            if rank == 0:
+                emit(headline(also))
+            os._exit(0)   # the other ranks may be inside a collective of the block: do not wait for them
+
+    if rank == 0:
+        emit(headline(also))
     if os.environ.get("OSHB_DIST_CPROFILE") and rank == 0:
         # diagnosis only: where the host spends its time in the partitioned loop
         import cProfile
@@ -1019,8 +1060,26 @@ def main_b200_partitioned(args):
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(obj):
+    """the ONE json line of the contract, written to the process's real stdout (main() points fd 1 at stderr for
+    everything else: NCCL prints its version banner to stdout when the library creates its communicator)"""
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)   # C-level and Python-level stdout of everything below -> stderr; emit() keeps the real one
     if args.impl in ("reference", "reference-cuda"):
         return main_reference(args)
     if (int(os.environ.get("WORLD_SIZE", "1")) > 1 or os.environ.get("OSHB_FORCE_PARTITIONED")) and not args.replicas:
