@@ -69,6 +69,7 @@ def test_torch_level_pass_still_matches_serial_gloo(emu_lib, nranks, n, halo, an
     (2, 8, 4, 0, 3),    # RIB halves of the cube
     (4, 6, 2, 1, 3),    # four RIB parts, anisotropic, with re-ghosting
     (2, 12, 4, 0, 2),   # triangles
+    (8, 8, 2, 0, 3),    # eight RIB octants (the 8-GPU layout), one re-ghosting: seven neighbours per rank
 ])
 def test_partitioned_loop_on_rib_parts_gloo(emu_lib, nranks, n, halo, aniso, dim):
     """parts cut by recursive inertial bisection (Mesh::balance, BASELINE config[3]) instead of ranges of the
